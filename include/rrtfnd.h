@@ -1,0 +1,215 @@
+/*
+ * rrtfnd.h — C ABI of the B200-native RRT / RRT* / RRT*-FN / RRT*-FND hot path.
+ *
+ * The reference (grzesiek2201/RRT-STAR-FND-Algorithm) is pure Python and has no FFI layer; its
+ * boundary is the Python surface of src/algorithm.py, src/graph.py and src/map.py. Every entry point
+ * below names the reference function(s) it replaces (file:line relative to the reference root). The
+ * Python shim in rrt_star_fnd_algorithm_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - no allocation or ownership transfer inside the device-pointer entry points;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream);
+ *   - return value: 0 = OK, > 0 = cudaError_t, < 0 = RRTFND_E_* below;
+ *   - all coordinates / costs are IEEE fp64 evaluated one rounding per written operation (no FMA
+ *     contraction) except the one fused multiply-add of `calc_distance` (DESIGN.md "Arithmetic contract").
+ *
+ * The same parameter / state structs are used by the CPU oracle (oracle/rrt_oracle.c), which is test
+ * infrastructure only.
+ */
+#ifndef RRTFND_H
+#define RRTFND_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRTFND_ABI_VERSION 1
+
+/* planner kinds: src/algorithm.py:55 (RRT), :98 (RRT_star), :190 (RRT_star_FN) */
+#define RRTFND_MODE_RRT 0
+#define RRTFND_MODE_STAR 1
+#define RRTFND_MODE_FN 2
+
+/* random word source */
+#define RRTFND_STREAM_WORDS 0  /* explicit uint32 buffer per planner (drop-in: MT19937 words of `random`) */
+#define RRTFND_STREAM_PHILOX 1 /* counter-based Philox4x32-10 keyed by (seed, stream_id) */
+
+/* flags */
+#define RRTFND_FLAG_EVAL_CHOOSE_PARENT 1   /* evaluate choose_parent_kdtree's return value (src/algorithm.py:822-852) */
+#define RRTFND_FLAG_COMMIT_CHOOSE_PARENT 2 /* EXTENSION: use that return value as the new node's edge (the reference drops it, :146/:224) */
+#define RRTFND_FLAG_TRACE 4                /* write one rrtfnd_trace_t per successful iteration */
+
+/* per-planner status (rrtfnd_planner_t.status) */
+#define RRTFND_ST_RUNNING 0        /* iter < iter_num, can be resumed */
+#define RRTFND_ST_DONE 1           /* iter == iter_num (or RRT reached the goal) */
+#define RRTFND_ST_NEED_WORDS 2     /* word buffer exhausted at an attempt boundary; refill and call again */
+#define RRTFND_ST_ATTEMPT_CAP 3    /* max_attempts reached (reference would still be looping, src/algorithm.py:74-75) */
+#define RRTFND_ST_CAPACITY (-1)    /* node capacity exhausted */
+#define RRTFND_ST_NEAR_CAP (-2)    /* near-set larger than near_cap */
+#define RRTFND_ST_FINISH_CAP (-3)  /* more goal-reaching nodes than finish_cap */
+#define RRTFND_ST_PATH_CAP (-4)    /* best path longer than path_cap */
+#define RRTFND_ST_DUPLICATE (-5)   /* steered point coincides with an existing vertex (src/graph.py:54-56 corner) */
+#define RRTFND_ST_NO_CHILDLESS (-6)/* forced_removal would spin forever (src/algorithm.py:815-816) */
+
+/* library errors (negative return values) */
+#define RRTFND_E_BADARG (-100)
+#define RRTFND_E_NOGPU (-101)
+#define RRTFND_E_SMEM (-102)
+
+typedef struct rrtfnd_params {
+    int32_t mode;          /* RRTFND_MODE_* */
+    int32_t iter_num;      /* successful iterations to reach (src/algorithm.py:71, :118, :214) */
+    int32_t max_nodes;     /* RRT*-FN node cap (src/algorithm.py:233) */
+    int32_t capacity;      /* node slots per planner */
+    int32_t n_obst;        /* circles in the obstacle table */
+    int32_t near_cap;      /* max near-set size handled */
+    int32_t finish_cap;    /* max goal-reaching nodes tracked (finish_nodes_of_path, :116) */
+    int32_t path_cap;      /* max ids stored for best_path["path"] */
+    int32_t stream_mode;   /* RRTFND_STREAM_* */
+    int32_t flags;         /* RRTFND_FLAG_* */
+    int32_t trace_cap;     /* trace records per planner */
+    int32_t reserved;
+    int64_t words_per_planner; /* RRTFND_STREAM_WORDS: words available per planner */
+    int64_t max_attempts;      /* attempts allowed per planner over its lifetime (<=0: unlimited) */
+    double step_length;    /* steer() max_length (src/algorithm.py:731) */
+    double radius;         /* near-set / rewire radius (:837, :893) */
+    double node_radius;    /* Map.node_radius (src/map.py:45) and goal test 2*node_radius (:758) */
+    double bias;           /* Graph.random_node bias (src/graph.py:96) */
+    double x_lo, x_hi, y_lo, y_hi; /* Graph.xy_range (src/graph.py:98) */
+} rrtfnd_params_t;
+
+/* Per-planner scalars. One entry per planner, device resident, read back by the host. */
+typedef struct rrtfnd_planner {
+    double start_x, start_y;   /* Graph.start (root position) */
+    double goal_x, goal_y;     /* Graph.goal */
+    double best_cost;          /* best_path["cost"], +inf when none (src/algorithm.py:115) */
+    uint64_t seed, stream_id;  /* Philox key / stream */
+    uint64_t cursor;           /* next random word index */
+    int64_t attempts;          /* new_node() calls (src/algorithm.py:36) */
+    int64_t n_edge_checks;     /* unique segments submitted to through_obstacle (:581) */
+    int64_t n_edge_checks_ref; /* reference-equivalent count: nearest rounds + 2 x near-set (:847 and :904) */
+    int64_t n_circle_tests;    /* intersection_circle evaluations actually performed on the device */
+    int64_t n_scan_nodes;      /* nodes visited by nearest / near-set scans (x 16 B = algorithmic bytes) */
+    int64_t n_chain_hops;      /* parent-chain hops walked by get_cost / find_path (x 12 B) */
+    int32_t n_slots;           /* slots in use (live + tombstones) */
+    int32_t n_live;            /* live nodes (n_of_nodes, :209) */
+    int32_t last_id;           /* Graph.last_id (src/graph.py:32) */
+    int32_t iter;              /* successful iterations so far */
+    int32_t root_slot;         /* slot of the tree root (Graph.id_vertex[Graph.start]) */
+    int32_t n_finish;          /* len(finish_nodes_of_path) */
+    int32_t best_len;          /* len(best_path["path"]) */
+    int32_t status;            /* RRTFND_ST_* */
+    int32_t n_rewired;         /* total rewired nodes */
+    int32_t n_removed;         /* total forced removals */
+    int32_t solution_found;    /* src/algorithm.py:114 */
+    int32_t n_compactions;
+} rrtfnd_planner_t;
+
+/* One record per successful iteration (RRTFND_FLAG_TRACE). */
+typedef struct rrtfnd_trace {
+    int32_t id_new;     /* id given by Graph.add_vertex (src/graph.py:57-58) */
+    int32_t id_near;    /* nearest visible node (src/algorithm.py:44) */
+    int32_t n_near;     /* near-set size without the new node itself (:837) */
+    int32_t n_rewired;  /* nodes re-parented by rewire_kdtree (:905-910) */
+    int32_t removed_id; /* forced_removal result or -1 (:234) */
+    int32_t cp_parent;  /* parent id in choose_parent_kdtree's RETURNED edge (:852), -1 if not evaluated */
+    double cp_cost;     /* cost in that returned edge */
+} rrtfnd_trace_t;
+
+/* Device-resident batch of P independent planners, structure-of-arrays, fixed capacity. */
+typedef struct rrtfnd_batch {
+    int32_t n_planners;
+    int32_t reserved;
+    rrtfnd_planner_t* planners; /* [P] */
+    double* x;                  /* [P][capacity] node x; NaN in a tombstone slot */
+    double* y;                  /* [P][capacity] */
+    double* ecost;              /* [P][capacity] edge cost to parent (Graph.cost, src/graph.py:29) */
+    int32_t* parent;            /* [P][capacity] parent SLOT, -1 = none */
+    int32_t* nchild;            /* [P][capacity] len(Graph.children[id]) */
+    int32_t* id;                /* [P][capacity] reference node id, -1 = tombstone; ascending in slot order */
+    int32_t* finish;            /* [P][finish_cap] slots of goal-reaching nodes, in discovery order */
+    int32_t* best_path;         /* [P][path_cap] ids leaf -> root (best_path["path"]) */
+    const double* obst;         /* [n_obst][4]: ox, oy, r, K = ((-(r*r)) + ox*ox) + oy*oy */
+    const uint32_t* words;      /* [P][words_per_planner] or NULL */
+    rrtfnd_trace_t* trace;      /* [P][trace_cap] or NULL */
+} rrtfnd_batch_t;
+
+/* ---- library info ------------------------------------------------------------------------ */
+int rrtfnd_abi_version(void);
+const char* rrtfnd_status_string(int status);
+/* dynamic shared memory (bytes) the fused planner kernel needs for these parameters; <0 = does not fit */
+int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm);
+
+/* ---- stateless batched operators (device pointers) ------------------------------------------ */
+
+/* through_obstacle(Line(p1, p2), obstacles) for n_edges segments (src/algorithm.py:581-591,
+ * :555-578, :594-635; src/line.py:5-16). One warp per edge, lanes stride over the obstacle tile in
+ * shared memory. out_hit[i] = 1 if segment i collides. */
+int rrtfnd_edges_vs_circles(const double* p1x, const double* p1y, const double* p2x, const double* p2y,
+                            int64_t n_edges, const double* obst, int32_t n_obst, uint8_t* out_hit, void* stream);
+
+/* Map.is_occupied_c(p) for n points (src/map.py:38-47): any circle with
+ * sqrt(dx*dx+dy*dy) < node_radius + r. */
+int rrtfnd_points_occupied(const double* px, const double* py, int64_t n_points, const double* obst,
+                           int32_t n_obst, double node_radius, uint8_t* out_occ, void* stream);
+
+/* nearest_node_kdtree (src/algorithm.py:666-699) for one query per planner: the slot of the nearest node
+ * (plain d2, lowest id on ties) whose segment Line(q, node) is collision free; -1 if none is visible,
+ * -2 if q coincides exactly with a vertex (:676-678). q is [P][2]. */
+int rrtfnd_nearest_visible(const rrtfnd_batch_t* batch, int32_t capacity, const double* q, int32_t n_obst,
+                           int32_t* out_slot, int32_t* out_rounds, void* stream);
+
+/* cKDTree.query_ball_point(q, r) (src/algorithm.py:837, :893): slots with d2 <= r*r in ascending slot
+ * order, per planner. out_slots is [P][near_cap]; out_count[p] may exceed near_cap (then truncated). */
+int rrtfnd_near_set(const rrtfnd_batch_t* batch, int32_t capacity, const double* q, double radius,
+                    int32_t near_cap, int32_t* out_slots, int32_t* out_count, void* stream);
+
+/* Graph.get_cost (src/graph.py:34-46) for n (planner, slot) pairs: leaf -> root sequential fp64 sum. */
+int rrtfnd_chain_cost(const rrtfnd_batch_t* batch, int32_t capacity, const int32_t* planner_idx,
+                      const int32_t* slot, int64_t n, double* out_cost, void* stream);
+
+/* ---- fused planner driver ---------------------------------------------------------------------- */
+
+/* Advance every planner of the batch until iter == prm->iter_num (or a status other than RUNNING).
+ * Replaces the loops of RRT / RRT_star / RRT_star_FN (src/algorithm.py:71-94, :118-186, :214-265) with
+ * new_node (:36-51), choose_parent_kdtree (:822-852), rewire_kdtree (:882-910), forced_removal (:800-819),
+ * check_solution (:749-760), find_path (:778-797) fused into one persistent CTA per planner. Resumable. */
+int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, void* stream);
+
+/* Initialise planner p's tree to the single root node `start` (Graph.__init__, src/graph.py:25-32) and
+ * zero its counters. planners[p].start/goal/seed/stream_id must already be set. */
+int rrtfnd_init_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, void* stream);
+
+/* ---- RRT*-FND tree surgery (src/algorithm.py:294-552), one CTA per planner --------------------- */
+
+/* select_branch (src/algorithm.py:294-325): re-root at `current_slot[p]`, delete everything outside its subtree. */
+int rrtfnd_fnd_select_branch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* current_slot,
+                             void* stream);
+/* valid_path (src/algorithm.py:344-367) over the stored best path: delete occupied path nodes and their
+ * off-path subtrees; out_separate_root[p] = slot of the last orphaned on-path child (or the previous root). */
+int rrtfnd_fnd_valid_path(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, int32_t* out_separate_root,
+                          void* stream);
+/* reconnect (src/algorithm.py:370-404): link the separate root to the first (lowest id) root-tree node within
+ * `radius` (calc_distance <= radius) whose segment is free. out_linked[p] = slot linked to or -1. */
+int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root,
+                         double radius, int32_t* out_linked, void* stream);
+
+/* ---- host-buffer entry point (what the Python drop-in and bench `e2e` call) -------------------- */
+
+/* Plan P independent problems given HOST buffers; allocates device memory, copies in, runs to completion,
+ * copies results back. starts_goals_host is [P][4] (sx, sy, gx, gy); seeds_host is [P][2] (seed, stream_id);
+ * obst_host is [M][3] (ox, oy, r). Outputs (all host, may be NULL to skip): planners_host [P];
+ * tree arrays [P][capacity] x, y, ecost, parent (slot), nchild, id; best_path_host [P][path_cap]. */
+int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t n_planners, const double* starts_goals_host,
+                     const uint64_t* seeds_host, const double* obst_host, const uint32_t* words_host,
+                     rrtfnd_planner_t* planners_host, double* x_host, double* y_host, double* ecost_host,
+                     int32_t* parent_host, int32_t* nchild_host, int32_t* id_host, int32_t* best_path_host,
+                     int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTFND_H */

@@ -1,0 +1,125 @@
+"""CPU: the C oracle (oracle/rrt_oracle.c) against the golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import cases as K
+from oracle.philox import philox_words, WordStreamRandom
+from rrt_star_fnd_algorithm_b200 import _structs as S
+
+from util import assert_trace_equal, assert_tree_equal, load_golden, load_npz
+
+CASES = [c["name"] for c in K.all_cases()]
+
+
+def run_oracle(case, stream_mode=S.STREAM_WORDS, flags=None):
+    words = philox_words(case["seed"], case["stream_id"], K.words_needed(case))
+    prm = K.params_for(case, stream_mode=stream_mode, n_words=len(words), flags=flags)
+    tree = O.OracleTree(case["start"], case["iter_num"] + 2)
+    if stream_mode == S.STREAM_WORDS:
+        st, tr = tree.run(prm, case["obstacles"], case["goal"], words=words, trace=True)
+    else:
+        st, tr = tree.run(prm, case["obstacles"], case["goal"], seed=case["seed"], stream_id=case["stream_id"], trace=True)
+    return tree, st, tr
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("stream_mode", [S.STREAM_WORDS, S.STREAM_PHILOX])
+def test_oracle_matches_reference_golden(name, stream_mode):
+    case, g = K.case_by_name(name), load_golden(name)
+    tree, st, tr = run_oracle(case, stream_mode)
+    pl = tree.planner()
+    assert st == S.ST_DONE
+    assert_tree_equal(tree.export(), g, name)
+    assert pl.iter == int(g["iter"])
+    assert pl.cursor == int(g["words_used"])
+    assert pl.attempts == int(g["attempts"])
+    assert pl.last_id == int(g["last_id"])
+    assert pl.n_edge_checks_ref == int(g["edge_calls"])          # every through_obstacle call of the reference
+    assert np.array_equal(tree.best_path(), g["best_path"])
+    assert pl.best_cost == float(g["best_cost"])                  # bit-equal (stricter than the 1e-9 the spec asks)
+    n = pl.iter
+    assert_trace_equal(tr, g, n, case["mode"], name)
+    if case["mode"] != "rrt":   # value RETURNED by choose_parent_kdtree (dropped by the planners)
+        assert np.array_equal(tr["cp_parent"][:n], g["rec_cp_parent"][:n])
+        assert np.array_equal(tr["cp_cost"][:n], g["rec_cp_cost"][:n])
+
+
+def test_choose_parent_eval_does_not_change_the_tree():
+    """Reference drops choose_parent_kdtree's return value (src/algorithm.py:146): skipping it is a no-op."""
+    case = K.case_by_name("float_star")
+    a, _, _ = run_oracle(case, flags=S.FLAG_TRACE)
+    assert_tree_equal(a.export(), load_golden("float_star"), "no-eval")
+
+
+def test_collision_booleans_recorded_from_reference():
+    col = load_npz("collision.npz")
+    n_checked = 0
+    for case in K.all_cases():
+        for prefix in (case["name"], "synth_" + case["name"]):
+            if prefix + "_seg" not in col:
+                continue
+            seg, hit = col[prefix + "_seg"], col[prefix + "_hit"]
+            got = np.array([O.through_obstacle(s[:2], s[2:], case["obstacles"]) for s in seg], np.uint8)
+            bad = np.flatnonzero(got != hit)
+            assert bad.size == 0, f"{prefix}: {bad.size} collision booleans differ, first {bad[:5]}"
+            n_checked += len(seg)
+    assert n_checked > 20000
+
+
+def test_occupancy_booleans_from_reference():
+    occ = load_npz("occupancy.npz")
+    for name in ("float_fn", "int_star", "main_star", "dense_fn"):
+        case = K.case_by_name(name)
+        got = np.array([O.is_occupied(p, case["obstacles"], case["node_radius"]) for p in occ[name + "_pts"]], np.uint8)
+        assert np.array_equal(got, occ[name + "_occ"])
+
+
+def test_word_stream_resume_is_exact():
+    """Stopping on NEED_WORDS and resuming with a longer buffer gives the same tree as one uninterrupted run."""
+    case = K.case_by_name("float_fn")
+    g = load_golden("float_fn")
+    words = philox_words(case["seed"], 0, K.words_needed(case))
+    tree = O.OracleTree(case["start"], case["iter_num"] + 2)
+    n, calls = 500, 0
+    while True:
+        prm = K.params_for(case, n_words=n)
+        st, _ = tree.run(prm, case["obstacles"], case["goal"], words=words[:n])
+        calls += 1
+        if st != S.ST_NEED_WORDS:
+            break
+        n += 700
+    assert st == S.ST_DONE and calls > 3
+    assert_tree_equal(tree.export(), g, "resume")
+    assert tree.planner().cursor == int(g["words_used"])
+
+
+def test_philox_known_answer_and_cpython_arithmetic():
+    # Random123 known-answer vector for philox4x32-10, counter = key = 0
+    assert [hex(w) for w in philox_words(0, 0, 4)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert np.array_equal(philox_words(3, 9, 11, first_word=5), philox_words(3, 9, 16)[5:])
+    import random
+    r = random.Random(123)
+    state = r.getstate()
+    words = [r.getrandbits(32) for _ in range(2000)]
+    r.setstate(state)
+    w = WordStreamRandom(words)
+    for n in (1, 2, 3, 7, 64, 1000):
+        for _ in range(20):
+            assert w.random() == r.random()
+            assert w.uniform(-210, 210) == r.uniform(-210, 210)
+            assert w.choice(range(n)) == r.choice(range(n))
+
+
+def test_batch_driver_matches_single_runs():
+    case = K.case_by_name("float_star")
+    prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0)
+    prm.iter_num = 200
+    sg = np.array([[5, 5, 95, 95], [10, 80, 90, 10], [50, 5, 50, 95]], np.float64)
+    seeds = np.array([[11, 0], [11, 1], [12, 0]], np.uint64)
+    out1, bad1 = O.run_batch(prm, sg, seeds, case["obstacles"], n_threads=1)
+    out3, bad3 = O.run_batch(prm, sg, seeds, case["obstacles"], n_threads=3)
+    assert bad1 == 0 and bad3 == 0
+    for f in ("iter", "attempts", "best_cost", "cursor", "n_live", "n_rewired", "n_edge_checks"):
+        assert np.array_equal(out1[f], out3[f]), f
+    assert (out1["iter"] == 200).all()
