@@ -53,6 +53,7 @@ extern "C" {
 #define RRTFND_ST_PATH_CAP (-4)    /* best path longer than path_cap */
 #define RRTFND_ST_DUPLICATE (-5)   /* steered point coincides with an existing vertex (src/graph.py:54-56 corner) */
 #define RRTFND_ST_NO_CHILDLESS (-6)/* forced_removal would spin forever (src/algorithm.py:815-816) */
+#define RRTFND_ST_STREAM_EXHAUSTED (-7) /* word buffer ran out inside forced_removal's redraw loop */
 
 /* library errors (negative return values) */
 #define RRTFND_E_BADARG (-100)

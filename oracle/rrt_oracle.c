@@ -515,7 +515,7 @@ int orc_run(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, doubl
     }
     if (t->status == RRTFND_ST_RUNNING && t->iter >= prm->iter_num) t->status = RRTFND_ST_DONE;
 out:
-    if (rng.exhausted) t->status = RRTFND_ST_NEED_WORDS;
+    if (rng.exhausted) t->status = RRTFND_ST_STREAM_EXHAUSTED;
     t->cursor = rng.cursor;
     return t->status;
 }

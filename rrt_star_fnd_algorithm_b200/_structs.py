@@ -8,7 +8,7 @@ STREAM_WORDS, STREAM_PHILOX = 0, 1
 FLAG_EVAL_CHOOSE_PARENT, FLAG_COMMIT_CHOOSE_PARENT, FLAG_TRACE = 1, 2, 4
 
 ST_RUNNING, ST_DONE, ST_NEED_WORDS, ST_ATTEMPT_CAP = 0, 1, 2, 3
-ST_CAPACITY, ST_NEAR_CAP, ST_FINISH_CAP, ST_PATH_CAP, ST_DUPLICATE, ST_NO_CHILDLESS = -1, -2, -3, -4, -5, -6
+ST_CAPACITY, ST_NEAR_CAP, ST_FINISH_CAP, ST_PATH_CAP, ST_DUPLICATE, ST_NO_CHILDLESS, ST_STREAM_EXHAUSTED = -1, -2, -3, -4, -5, -6, -7
 
 STATUS_NAMES = {
     ST_RUNNING: "running", ST_DONE: "done", ST_NEED_WORDS: "need-words", ST_ATTEMPT_CAP: "attempt-cap",
@@ -16,6 +16,7 @@ STATUS_NAMES = {
     ST_FINISH_CAP: "finish list full", ST_PATH_CAP: "best path longer than path_cap",
     ST_DUPLICATE: "steered point coincides with an existing vertex",
     ST_NO_CHILDLESS: "forced_removal has no removable childless node",
+    ST_STREAM_EXHAUSTED: "random word buffer exhausted inside forced_removal",
 }
 
 RESERVE_WORDS = 64  # words that must remain when an attempt starts in STREAM_WORDS mode

@@ -1,0 +1,161 @@
+"""PlannerBatch: P independent planners resident on one GPU as structure-of-arrays (torch tensors own the
+memory, the CUDA library does the work). This is the batch API behind the drop-in entry points in
+planners.py and the object bench.py drives."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._structs import (
+    Batch, Params, PLANNER_BYTES, PLANNER_DTYPE, TRACE_BYTES, TRACE_DTYPE,
+    MODE_RRT, MODE_STAR, MODE_FN, STREAM_WORDS, STREAM_PHILOX, FLAG_EVAL_CHOOSE_PARENT, FLAG_TRACE,
+    ST_DONE, ST_RUNNING, ST_NEED_WORDS, STATUS_NAMES,
+)
+
+_MODES = {"rrt": MODE_RRT, "star": MODE_STAR, "fn": MODE_FN, MODE_RRT: MODE_RRT, MODE_STAR: MODE_STAR, MODE_FN: MODE_FN}
+
+
+def obstacle_table(obstacles) -> np.ndarray:
+    """Rows (ox, oy, r, K) from the reference's obstacle list `[(pos, r), ...]` or from (ox, oy, r) triples.
+
+    K is the circle-only part of calc_delta's `c` (src/algorithm.py:619), evaluated with the reference's own
+    expression on the caller's own number types: `-r ** 2 + x0 ** 2 + y0 ** 2`.
+    """
+    rows = []
+    for ob in obstacles:
+        if len(ob) == 2:
+            (x0, y0), r = (ob[0][0], ob[0][1]), ob[1]
+        else:
+            x0, y0, r = ob
+        K = -r ** 2 + x0 ** 2 + y0 ** 2
+        rows.append((float(x0), float(y0), float(r), float(K)))
+    return np.asarray(rows, dtype=np.float64).reshape(-1, 4)
+
+
+def fn_capacity(max_nodes: int) -> int:
+    """Slots for an RRT*-FN planner: the cap, the transient extra node, and tombstone slack between compactions."""
+    return int(max_nodes) + 2 + max(256, int(max_nodes) // 4)
+
+
+class PlannerBatch:
+    def __init__(self, mode, *, starts, goals, obstacles, xy_range, iter_num, step_length, radius=0.0,
+                 node_radius=1.0, bias=0.0, max_nodes=200, seeds=None, stream_ids=None, words=None,
+                 capacity=None, near_cap=512, finish_cap=1024, path_cap=1024, trace=False,
+                 eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PlannerBatch needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        starts = np.asarray(starts, dtype=np.float64).reshape(-1, 2)
+        goals = np.asarray(goals, dtype=np.float64).reshape(-1, 2)
+        P = len(starts)
+        assert len(goals) == P
+        self.P = P
+        m = _MODES[mode]
+        if capacity is None:
+            capacity = fn_capacity(max_nodes) if m == MODE_FN else int(iter_num) + 2
+        prm = Params()
+        prm.mode, prm.iter_num, prm.max_nodes, prm.capacity = m, int(iter_num), int(max_nodes), int(capacity)
+        self.obst_host = obstacle_table(obstacles)
+        prm.n_obst = len(self.obst_host)
+        prm.near_cap, prm.finish_cap, prm.path_cap = int(near_cap), int(finish_cap), int(path_cap)
+        prm.flags = (FLAG_EVAL_CHOOSE_PARENT if eval_choose_parent else 0) | (2 if commit_choose_parent else 0) | \
+            (FLAG_TRACE if trace else 0)
+        prm.trace_cap = int(iter_num) + 1 if trace else 0
+        prm.max_attempts = int(max_attempts)
+        prm.step_length, prm.radius, prm.node_radius, prm.bias = float(step_length), float(radius or 0.0), \
+            float(node_radius), float(bias)
+        (prm.x_lo, prm.x_hi), (prm.y_lo, prm.y_hi) = [(float(a), float(b)) for a, b in xy_range]
+        self.prm = prm
+
+        dev = self.device
+        pl = np.zeros(P, dtype=PLANNER_DTYPE)
+        pl["start_x"], pl["start_y"] = starts[:, 0], starts[:, 1]
+        pl["goal_x"], pl["goal_y"] = goals[:, 0], goals[:, 1]
+        if words is not None:
+            w = np.ascontiguousarray(words, dtype=np.uint32).reshape(P, -1)
+            prm.stream_mode, prm.words_per_planner = STREAM_WORDS, w.shape[1]
+            self.words = torch.from_numpy(w.view(np.int32)).to(dev)
+        else:
+            prm.stream_mode, prm.words_per_planner = STREAM_PHILOX, 0
+            self.words = None
+            pl["seed"] = np.asarray(seeds if seeds is not None else np.arange(P), dtype=np.uint64)
+            pl["stream_id"] = np.asarray(stream_ids if stream_ids is not None else np.zeros(P), dtype=np.uint64)
+        self.planners_t = torch.from_numpy(pl.view(np.uint8).reshape(P, PLANNER_BYTES).copy()).to(dev)
+        Cn = prm.capacity
+        self.x = torch.empty((P, Cn), dtype=torch.float64, device=dev)
+        self.y = torch.empty((P, Cn), dtype=torch.float64, device=dev)
+        self.ecost = torch.empty((P, Cn), dtype=torch.float64, device=dev)
+        self.parent = torch.empty((P, Cn), dtype=torch.int32, device=dev)
+        self.nchild = torch.empty((P, Cn), dtype=torch.int32, device=dev)
+        self.id = torch.empty((P, Cn), dtype=torch.int32, device=dev)
+        self.finish = torch.empty((P, prm.finish_cap), dtype=torch.int32, device=dev)
+        self.best_path_t = torch.empty((P, prm.path_cap), dtype=torch.int32, device=dev)
+        self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(dev)
+        self.trace_t = torch.zeros((P, max(prm.trace_cap, 1) * TRACE_BYTES), dtype=torch.uint8, device=dev) if trace else None
+        self._initialised = False
+        smem = _abi.lib.rrtfnd_plan_smem_bytes(C.byref(prm))
+        if smem < 0:
+            raise _abi.LibraryError(f"planner does not fit in shared memory: {_abi.status_string(smem)}")
+        self.smem_bytes = int(smem)
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def _batch(self) -> Batch:
+        b = Batch()
+        b.n_planners = self.P
+        b.planners = self.planners_t.data_ptr()
+        b.x, b.y, b.ecost = self.x.data_ptr(), self.y.data_ptr(), self.ecost.data_ptr()
+        b.parent, b.nchild, b.id = self.parent.data_ptr(), self.nchild.data_ptr(), self.id.data_ptr()
+        b.finish, b.best_path = self.finish.data_ptr(), self.best_path_t.data_ptr()
+        b.obst = self.obst.data_ptr()
+        b.words = self.words.data_ptr() if self.words is not None else None
+        b.trace = self.trace_t.data_ptr() if self.trace_t is not None else None
+        return b
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self):
+        """Graph.__init__ for every planner (src/graph.py:25-32): a single root node at `start`."""
+        with torch.cuda.device(self.device):
+            b = self._batch()
+            _abi.check(_abi.lib.rrtfnd_init_batch(C.byref(self.prm), C.byref(b), self._stream()), "rrtfnd_init_batch")
+        self._initialised = True
+
+    def run(self):
+        """Grow every tree until iter == iter_num (asynchronous on the current stream)."""
+        if not self._initialised:
+            self.reset()
+        with torch.cuda.device(self.device):
+            b = self._batch()
+            _abi.check(_abi.lib.rrtfnd_plan_batch(C.byref(self.prm), C.byref(b), self._stream()), "rrtfnd_plan_batch")
+        return self
+
+    # ------------------------------------------------------------------ results
+    def planners(self) -> np.ndarray:
+        return self.planners_t.cpu().numpy().reshape(-1).view(PLANNER_DTYPE).copy()
+
+    def check_status(self):
+        st = self.planners()["status"]
+        bad = np.flatnonzero((st != ST_DONE))
+        if bad.size:
+            p = int(bad[0])
+            raise RuntimeError(f"planner {p}: status {int(st[p])} ({STATUS_NAMES.get(int(st[p]), '?')}); {bad.size} planners not done")
+
+    def tree(self, p: int) -> dict:
+        """Canonical tree of planner p: live nodes in ascending id, parent as id (-1 = none)."""
+        n = int(self.planners()[p]["n_slots"])
+        ids = self.id[p, :n].cpu().numpy()
+        live = ids >= 0
+        par_slot = self.parent[p, :n].cpu().numpy()
+        parent = np.where(par_slot >= 0, ids[np.clip(par_slot, 0, None)], -1).astype(np.int32)
+        return dict(ids=ids[live].copy(), x=self.x[p, :n].cpu().numpy()[live], y=self.y[p, :n].cpu().numpy()[live],
+                    parent=parent[live], cost=self.ecost[p, :n].cpu().numpy()[live],
+                    nchild=self.nchild[p, :n].cpu().numpy()[live])
+
+    def best_path(self, p: int) -> np.ndarray:
+        n = int(self.planners()[p]["best_len"])
+        return self.best_path_t[p, :n].cpu().numpy().copy()
+
+    def trace(self, p: int) -> np.ndarray:
+        return self.trace_t[p].cpu().numpy().view(TRACE_DTYPE).copy()

@@ -1,0 +1,90 @@
+// arith.cuh — the fp64 arithmetic contract of the reference, as device functions.
+//
+// Every operation is an explicitly rounded IEEE fp64 intrinsic (__dadd_rn, __dmul_rn, __ddiv_rn,
+// __dsqrt_rn), so nothing here can be contracted into an FMA whatever the compiler flags are; the one
+// fused multiply-add of the contract (calc_distance) is written as __fma_rn.
+// Reference lines are relative to the reference root (src/...).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace rrtfnd {
+
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+
+// calc_distance (src/algorithm.py:954-961): np.linalg.norm(p - q) = sqrt(ddot(v, v)); OpenBLAS' ddot tail
+// loop is FMA-contracted, i.e. sqrt(fma(dy, dy, fl(dx*dx))).
+__device__ __forceinline__ double dist_fma(double px, double py, double qx, double qy) {
+    const double dx = dsub(px, qx), dy = dsub(py, qy);
+    return dsqrt(__fma_rn(dy, dy, dmul(dx, dx)));
+}
+
+// cKDTree squared distance: k-NN order (src/algorithm.py:684) and ball membership d2 <= r*r (:837, :893)
+__device__ __forceinline__ double dist2(double nx, double ny, double qx, double qy) {
+    const double dx = dsub(nx, qx), dy = dsub(ny, qy);
+    return dadd(dmul(dx, dx), dmul(dy, dy));
+}
+
+// np.linalg.norm(in_radius_pos - q_new, axis=1) (src/algorithm.py:842, :899)
+__device__ __forceinline__ double dist_plain(double nx, double ny, double qx, double qy) {
+    return dsqrt(dist2(nx, ny, qx, qy));
+}
+
+// Line(p1, p2) in slope / intercept form (src/line.py:5-16) plus the per-segment terms of calc_delta
+// (src/algorithm.py:607-621) that do not depend on the circle.
+struct Seg {
+    double p1x;      // x_pos of a vertical line
+    double m, k;     // Line.dir, Line.const_term
+    double mk, kk;   // m*k, k*k (k**2)
+    double a2, a4;   // 2*a, 4*a with a = 1 + m*m   (exact scalings)
+    double lo, hi;   // min / max of the endpoint x (is_between, :632-633)
+    bool vertical;   // p2x == p1x (src/line.py:9)
+};
+
+__device__ __forceinline__ Seg make_seg(double p1x, double p1y, double p2x, double p2y) {
+    Seg s;
+    s.p1x = p1x;
+    s.vertical = (p2x == p1x);
+    s.m = ddiv(dsub(p2y, p1y), dsub(p2x, p1x));            // src/line.py:15
+    s.k = dsub(p1y, dmul(s.m, p1x));                       // src/line.py:16 (uses p1)
+    s.mk = dmul(s.m, s.k);
+    s.kk = dmul(s.k, s.k);
+    const double a = dadd(1.0, dmul(s.m, s.m));            // src/algorithm.py:617
+    s.a2 = dadd(a, a);
+    s.a4 = dmul(4.0, a);
+    s.lo = p1x < p2x ? p1x : p2x;
+    s.hi = p1x < p2x ? p2x : p1x;
+    return s;
+}
+
+// intersection_circle (src/algorithm.py:555-578) for one circle (ox, oy, r) with
+// K = ((-(r*r)) + ox*ox) + oy*oy precomputed (first three terms of `c`, :619).
+__device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double oy, double r, double K) {
+    if (s.vertical) return fabs(dsub(ox, s.p1x)) <= r;                          // :563-567
+    const double b = dmul(2.0, dsub(dadd(-ox, s.mk), dmul(s.m, oy)));           // :618
+    const double c = dadd(dsub(K, dmul(dadd(oy, oy), s.k)), s.kk);              // :619
+    const double delta = dsub(dmul(b, b), dmul(s.a4, c));                       // :620
+    if (!(delta >= 0.0)) return false;                                          // :569 (NaN -> no hit as well)
+    const double sq = dsqrt(delta);                                             // :602-603
+    const double x1 = ddiv(dadd(-b, sq), s.a2);
+    const double x2 = ddiv(dsub(-b, sq), s.a2);
+    return (x1 > s.lo && x1 < s.hi) || (x2 > s.lo && x2 < s.hi);                // :576, :632-635
+}
+
+// Map.is_occupied_c for one circle (src/map.py:44-45)
+__device__ __forceinline__ bool point_in_inflated(double px, double py, double ox, double oy, double r,
+                                                  double node_radius) {
+    const double dx = dsub(px, ox), dy = dsub(py, oy);
+    return dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))) < dadd(node_radius, r);
+}
+
+// lexicographic (d2, slot) order: nearest first, lowest slot (= lowest id) on ties
+__device__ __forceinline__ bool key_less(double d1, int s1, double d2, int s2) {
+    return d1 < d2 || (d1 == d2 && s1 < s2);
+}
+
+}  // namespace rrtfnd

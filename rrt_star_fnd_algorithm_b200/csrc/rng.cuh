@@ -1,0 +1,69 @@
+// rng.cuh — 32-bit random word source + CPython `random` arithmetic on top of it.
+//
+// The reference draws from Python's global `random` (src/graph.py:96-98, src/algorithm.py:813-816).
+// Here the planner consumes a stream of 32-bit words and applies CPython's own formulas:
+//   random()      = ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53
+//   uniform(a, b) = a + (b - a) * random()
+//   choice(seq)   = seq[_randbelow(len)],  _randbelow(n): k = n.bit_length(); r = w >> (32 - k) until r < n
+// The words come either from an explicit buffer (drop-in mode: the MT19937 words `random` itself would
+// have produced) or from Philox4x32-10 keyed by (seed, stream_id).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/rrtfnd.h"
+
+namespace rrtfnd {
+
+struct WordSrc {
+    const uint32_t* words;  // STREAM_WORDS buffer of this planner
+    long long n_words;
+    unsigned long long seed, stream, cursor, blk_idx;
+    uint32_t blk[4];
+    int mode;
+    bool have_blk, exhausted;
+};
+
+__device__ __forceinline__ void philox4x32_10(unsigned long long blk, unsigned long long stream,
+                                              unsigned long long seed, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ uint32_t next_word(WordSrc& r) {
+    const unsigned long long i = r.cursor++;
+    if (r.mode == RRTFND_STREAM_WORDS) {
+        if ((long long)i >= r.n_words) { r.exhausted = true; return 0u; }
+        return r.words[i];
+    }
+    const unsigned long long b = i >> 2;
+    if (!r.have_blk || b != r.blk_idx) {
+        philox4x32_10(b, r.stream, r.seed, r.blk);
+        r.blk_idx = b;
+        r.have_blk = true;
+    }
+    return r.blk[i & 3];
+}
+
+__device__ __forceinline__ double next_random(WordSrc& r) {
+    const uint32_t a = next_word(r) >> 5, b = next_word(r) >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);  // all three ops are exact
+}
+
+__device__ __forceinline__ uint32_t next_randbelow(WordSrc& r, uint32_t n) {
+    const int k = 32 - __clz(n);
+    uint32_t v = next_word(r) >> (32 - k);
+    while (v >= n && !r.exhausted) v = next_word(r) >> (32 - k);
+    return v;
+}
+
+}  // namespace rrtfnd

@@ -1,0 +1,115 @@
+"""GPU: the fused planner kernel (through the C ABI) against the golden vectors of the reference and the oracle."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import cases as K
+from oracle.philox import philox_words
+from rrt_star_fnd_algorithm_b200 import _structs as S
+
+from util import assert_trace_equal, assert_tree_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+CASES = [c["name"] for c in K.all_cases()]
+
+
+def make_batch(case, *, words=None, seeds=None, stream_ids=None, starts=None, goals=None, trace=True, **kw):
+    from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
+    P = 1 if starts is None else len(starts)
+    return PlannerBatch(
+        case["mode"], starts=[case["start"]] * P if starts is None else starts,
+        goals=[case["goal"]] * P if goals is None else goals, obstacles=case["obstacles"], xy_range=case["xy_range"],
+        iter_num=case["iter_num"], step_length=case["step_length"], radius=case["radius"],
+        node_radius=case["node_radius"], bias=case["bias"], max_nodes=case["max_nodes"], words=words, seeds=seeds,
+        stream_ids=stream_ids, trace=trace, **kw)
+
+
+def check_against_golden(b, case, g, p=0):
+    pl = b.planners()[p]
+    assert pl["status"] == S.ST_DONE, S.STATUS_NAMES.get(int(pl["status"]))
+    assert_tree_equal(b.tree(p), g, case["name"])
+    assert pl["iter"] == int(g["iter"])
+    assert pl["cursor"] == int(g["words_used"])
+    assert pl["attempts"] == int(g["attempts"])
+    assert pl["last_id"] == int(g["last_id"])
+    assert pl["n_edge_checks_ref"] == int(g["edge_calls"])
+    assert np.array_equal(b.best_path(p), g["best_path"])
+    assert pl["best_cost"] == float(g["best_cost"])
+    n = int(pl["iter"])
+    tr = b.trace(p)
+    assert_trace_equal(tr, g, n, case["mode"], case["name"])
+    if case["mode"] != "rrt":
+        assert np.array_equal(tr["cp_parent"][:n], g["rec_cp_parent"][:n])
+        assert np.array_equal(tr["cp_cost"][:n], g["rec_cp_cost"][:n])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_planner_word_buffer_matches_reference_golden(name):
+    case, g = K.case_by_name(name), load_golden(name)
+    words = philox_words(case["seed"], case["stream_id"], K.words_needed(case))
+    b = make_batch(case, words=words[None, :]).run()
+    check_against_golden(b, case, g)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_planner_philox_matches_reference_golden(name):
+    case, g = K.case_by_name(name), load_golden(name)
+    b = make_batch(case, seeds=[case["seed"]], stream_ids=[case["stream_id"]]).run()
+    check_against_golden(b, case, g)
+
+
+@pytest.mark.parametrize("name", ["float_fn", "float_star", "main_rrt_nobias"])
+def test_batched_planners_match_oracle(name):
+    """64 planners with their own start/goal and stream: every tree equals the CPU oracle's."""
+    case = K.case_by_name(name)
+    rng = np.random.default_rng(5)
+    P = 64
+    (x0, x1), (y0, y1) = case["xy_range"]
+    starts, goals = [], []
+    while len(starts) < P:
+        s = (rng.uniform(x0, x1), rng.uniform(y0, y1)); t = (rng.uniform(x0, x1), rng.uniform(y0, y1))
+        if O.is_occupied(s, case["obstacles"], case["node_radius"]) or O.is_occupied(t, case["obstacles"], case["node_radius"]):
+            continue
+        starts.append(s); goals.append(t)
+    it = 300 if case["mode"] != "rrt" else case["iter_num"]
+    case = dict(case, iter_num=it)
+    b = make_batch(case, seeds=np.full(P, 77), stream_ids=np.arange(P), starts=starts, goals=goals, trace=False).run()
+    pls = b.planners()
+    for p in range(P):
+        prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0)
+        t = O.OracleTree(starts[p], it + 2)
+        st, _ = t.run(prm, case["obstacles"], goals[p], seed=77, stream_id=p)
+        assert pls[p]["status"] == st
+        assert_tree_equal(b.tree(p), t.export(), f"{name}[{p}]")
+        opl = t.planner()
+        for f in ("iter", "cursor", "attempts", "best_cost", "n_live", "n_rewired", "n_removed", "n_edge_checks",
+                  "n_edge_checks_ref", "solution_found"):
+            assert pls[p][f] == getattr(opl, f), (p, f)
+        assert np.array_equal(b.best_path(p), t.best_path())
+
+
+def test_tiny_capacity_forces_compactions():
+    """FN with the minimum slot capacity compacts constantly; results must not change."""
+    case, g = K.case_by_name("float_fn"), load_golden("float_fn")
+    words = philox_words(case["seed"], case["stream_id"], K.words_needed(case))
+    b = make_batch(case, words=words[None, :], capacity=case["max_nodes"] + 8).run()
+    check_against_golden(b, case, g)
+    assert b.planners()[0]["n_compactions"] > 50
+
+
+def test_resume_after_need_words():
+    case, g = K.case_by_name("main_fn"), load_golden("main_fn")
+    words = philox_words(case["seed"], case["stream_id"], K.words_needed(case))
+    n, calls = 600, 0
+    b = make_batch(case, words=words[None, :n])
+    import torch
+    while True:
+        b.run(); calls += 1
+        st = int(b.planners()[0]["status"])
+        if st != S.ST_NEED_WORDS:
+            break
+        n += 900
+        b.words = torch.from_numpy(np.ascontiguousarray(words[None, :n]).view(np.int32)).to(b.device)
+        b.prm.words_per_planner = n
+    assert calls > 3
+    check_against_golden(b, case, g)
