@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — RRT* tree extensions/s and edge collision checks/s on N B200s (see DESIGN.md "Measurement").
+
+A *step* is one complete run of the workload's planners owned by this rank: every tree is re-initialised
+to its root and grown for `iter_num` successful iterations (sample -> occupancy -> nearest visible ->
+steer -> insert -> near set -> collision checks -> choose-parent -> rewire -> goal / best-path bookkeeping).
+Weak scaling: every rank owns `--planners` planners (global planner index = rank * planners + i, so a
+planner's problem and tree do not depend on the sharding); after its planners finish, a rank takes part in
+one NCCL all_gather of the per-planner result records and one broadcast of the globally best path.
+
+  value        extensions/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e          the same metric through rrtfnd_plan_host(): HOST buffers in, HOST buffers out, copies timed
+  roofline     algorithmic bytes of the fused planner kernel (16 B per node visited by the nearest / near-set
+               scans + 12 B per parent-chain hop + 32 B per inserted node) / its CUDA-event duration, against
+               the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle port (oracle/rrt_oracle.c) on all host cores, bounded sample of the same workload
+
+`--impl reference` times that CPU port instead of the GPU path (the reference itself is Python and cannot
+travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rrt_star_tree_extensions_per_sec"
+UNIT = "extensions/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3"])
+    ap.add_argument("--planners", type=int, default=0, help="planners per GPU (0 = workload default)")
+    ap.add_argument("--iters", type=int, default=0, help="iterations per planner (0 = workload default)")
+    ap.add_argument("--launch", type=int, default=0)
+    ap.add_argument("--near-cap", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# default planners per GPU: config 3 is 16,384 planners over 8 GPUs = 2,048 per GPU (weak scaling unit)
+DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 2048}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_workload(args):
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    w = W.WORKLOADS[args.workload]()
+    if args.iters:
+        w["iter_num"] = args.iters
+    P = args.planners or DEFAULT_PLANNERS[args.workload]
+    return w, P
+
+
+def oracle_params(w, flags):
+    from rrt_star_fnd_algorithm_b200 import _structs as S
+    p = S.Params()
+    p.mode = {"rrt": 0, "star": 1, "fn": 2}[w["mode"]]
+    p.iter_num, p.max_nodes, p.capacity = w["iter_num"], w["max_nodes"], w["iter_num"] + 2
+    p.n_obst, p.near_cap, p.finish_cap, p.path_cap = len(w["obstacles"]), 4096, 4096, 4096
+    p.stream_mode, p.flags = S.STREAM_PHILOX, flags
+    p.step_length, p.radius, p.node_radius, p.bias = w["step_length"], w["radius"], w["node_radius"], w["bias"]
+    (p.x_lo, p.x_hi), (p.y_lo, p.y_hi) = w["xy_range"]
+    return p
+
+
+def cpu_port_run(w, first, count, iters, threads):
+    """Time the CPU oracle port on `count` planners x `iters` iterations. Returns (ext/s, edge/s, seconds, records)."""
+    import oracle as O
+    from rrt_star_fnd_algorithm_b200 import _structs as S
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    ww = dict(w, iter_num=iters)
+    s, g, seeds, sids = W.planner_problems(ww, first, count)
+    prm = oracle_params(ww, S.FLAG_EVAL_CHOOSE_PARENT)
+    sg = np.concatenate([s, g], 1)
+    t0 = time.perf_counter()
+    out, bad = O.run_batch(prm, sg, np.stack([seeds, sids], 1), ww["obstacles"], n_threads=threads)
+    dt = time.perf_counter() - t0
+    return out["iter"].sum() / dt, out["n_edge_checks"].sum() / dt, dt, out
+
+
+def size_cpu_sample(w, budget_s, cores):
+    """(planners, iterations) of a CPU sample that takes roughly budget_s on `cores` threads."""
+    cpu_port_run(w, 0, 1, 20, 1)                          # load / build the checker outside the calibration
+    cal_it = min(w["iter_num"], 1000)
+    _, _, dt, _ = cpu_port_run(w, 0, cores, cal_it, cores)
+    # per-iteration cost of RRT* grows ~linearly with tree size (time ~ it^2); FN saturates at the node cap
+    expo = 2.0 if w["mode"] == "star" else 1.0
+    full = dt * (w["iter_num"] / cal_it) ** expo            # estimated seconds for `cores` planners at full length
+    if full <= budget_s:
+        return cores * int(max(1, min(64, budget_s // max(full, 1e-3)))), w["iter_num"]
+    iters = int(max(cal_it, cal_it * (budget_s / max(dt, 1e-3)) ** (1.0 / expo)))
+    return cores, min(iters, w["iter_num"])
+
+
+def cpu_baseline(w, budget_s):
+    """Bounded sample of the same workload on all host cores (C port of the reference algorithm)."""
+    cores = len(os.sched_getaffinity(0))
+    count, iters = size_cpu_sample(w, budget_s, cores)
+    ext, edge, dt, _ = cpu_port_run(w, 0, count, iters, cores)
+    return {"value": ext, "unit": UNIT, "cores": cores, "kind": "port",
+            "edge_checks_per_sec": edge, "seconds": dt,
+            "sample": f"{count} planners (global index 0..{count - 1}) x {iters} of {w['iter_num']} iterations of workload "
+                      f"{w['name']} on {cores} host threads, C port of the reference algorithm (oracle/rrt_oracle.c)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, P = load_workload(args)
+    cores = len(os.sched_getaffinity(0))
+    # bounded sample per step, sized so that warmup + steps stay within a few minutes
+    count, iters = size_cpu_sample(w, 150.0 / max(1, args.steps + args.warmup), cores)
+    for _ in range(args.warmup):
+        cpu_port_run(w, 0, count, iters, cores)
+    t0 = time.perf_counter()
+    ext_total, edge_total = 0, 0
+    for _ in range(args.steps):
+        _, _, _, out = cpu_port_run(w, 0, count, iters, cores)
+        ext_total += int(out["iter"].sum()); edge_total += int(out["n_edge_checks"].sum())
+    dt = time.perf_counter() - t0
+    val = ext_total / dt
+    sample = (f"{count} planners x {iters} of {w['iter_num']} iterations of workload {w['name']} per step on {cores} host "
+              f"threads, C port of the reference algorithm (the Python reference cannot travel to the GPU box)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: {w['mode']} planners, {len(w['obstacles'])} circular obstacles, "
+                                   f"{iters} of {w['iter_num']} iterations (bounded CPU sample)", "planners_per_step": count},
+            "edge_checks_per_sec": edge_total / dt,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from rrt_star_fnd_algorithm_b200 import _abi, workloads as W
+    from rrt_star_fnd_algorithm_b200 import _structs as S
+    from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
+    from rrt_star_fnd_algorithm_b200.parallel import gather_results
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, P = load_workload(args)
+    first = rank * P
+    starts, goals, seeds, sids = W.planner_problems(w, first, P)
+    kw = dict(obstacles=w["obstacles"], xy_range=w["xy_range"], iter_num=w["iter_num"], step_length=w["step_length"],
+              radius=w["radius"], node_radius=w["node_radius"], bias=w["bias"], max_nodes=w["max_nodes"],
+              near_cap=args.near_cap, launch=args.launch)
+    b = PlannerBatch(w["mode"], starts=starts, goals=goals, seeds=seeds, stream_ids=sids, device=dev, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kern_ms = []
+
+    def step(timed):
+        b.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.run()
+        e1.record()
+        if world > 1:
+            gather_results(b, dist.group.WORLD)     # all_gather of the records + broadcast of the best path
+        if timed:
+            kern_ms.append((e0, e1))
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    clk = clocks.stop() if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+
+    pl = b.planners()
+    b.check_status()
+    stats = torch.tensor([pl["iter"].sum(), pl["n_edge_checks"].sum(), pl["n_edge_checks_ref"].sum(),
+                          pl["n_circle_tests"].sum(), pl["attempts"].sum(), pl["n_scan_nodes"].sum(),
+                          pl["n_chain_hops"].sum(), pl["solution_found"].sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats)
+    ext, edges, edges_ref, circles, attempts, scan_nodes, hops, solved = [float(v) for v in stats.tolist()]
+    # the counters are totals of ONE step (state is re-initialised each step); the timed region holds `steps` of them
+    rate = args.steps / (ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused planner kernel (rank 0's launches; algorithmic bytes)
+    k_ms = float(np.mean([a.elapsed_time(c) for a, c in kern_ms]))
+    alg_bytes = 16.0 * pl["n_scan_nodes"].sum() + 12.0 * pl["n_chain_hops"].sum() + 32.0 * pl["iter"].sum()
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (k_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{args.workload}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "plan_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src,
+                "note": "trees of resident planners are L1/L2/shared-memory resident, so DRAM traffic is far below "
+                        "the algorithmic bytes; the kernel is FP64-issue / latency bound (see profiles/)"}
+
+    # ---- e2e through the host-buffer C ABI (pinned host memory, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, w, P, first, b, dev)
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline(w, args.cpu_seconds)
+
+    # parity spot check against the CPU oracle (not timed): planner 0 of this rank
+    parity = spot_check(w, first, b)
+
+    line = {
+        "metric": METRIC, "value": ext * rate,
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['mode']} x {P} planners per GPU ({P * world} total), "
+                               f"{len(w['obstacles'])} circular obstacles, {w['iter_num']} iterations each",
+                   "planners_per_gpu": P, "iter_num": w["iter_num"], "l2": "per-step working set "
+                   f"{P * b.prm.capacity * 32 / 1e6:.0f} MB of tree state is re-initialised every step (larger than L2 "
+                   "for the default size; no explicit flush)", "launch": args.launch, "near_cap": args.near_cap},
+        "edge_checks_per_sec": edges * rate,
+        "edge_checks_ref_equiv_per_sec": edges_ref * rate,
+        "circle_tests_per_sec": circles * rate,
+        "attempts_per_sec": attempts * rate,
+        "solved_planners": solved, "gpu_launches": 2 * args.steps,
+        "roofline": roofline, "clocks": clk, "parity_spot_check": parity,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, w, P, first, b, dev):
+    """Same workload through rrtfnd_plan_host: host inputs -> device -> run -> trees + results back to host."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from rrt_star_fnd_algorithm_b200 import _abi, workloads as W
+    from rrt_star_fnd_algorithm_b200._structs import PLANNER_BYTES
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    starts, goals, seeds, sids = W.planner_problems(w, first, P)
+    prm = b.prm
+    Cn = prm.capacity
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    sg = pin((P, 4), torch.float64); sg.copy_(torch.from_numpy(np.concatenate([starts, goals], 1)))
+    sd = pin((P, 2), torch.int64); sd.copy_(torch.from_numpy(np.stack([seeds, sids], 1).astype(np.int64)))
+    ob = pin((max(prm.n_obst, 1), 3), torch.float64); ob[:prm.n_obst].copy_(torch.from_numpy(np.asarray(w["obstacles"], np.float64)))
+    o_pl = pin((P, PLANNER_BYTES), torch.uint8)
+    o_x, o_y, o_e = pin((P, Cn), torch.float64), pin((P, Cn), torch.float64), pin((P, Cn), torch.float64)
+    o_par, o_nc, o_id = pin((P, Cn), torch.int32), pin((P, Cn), torch.int32), pin((P, Cn), torch.int32)
+    o_bp = pin((P, prm.path_cap), torch.int32)
+    h2d = sg.numel() * 8 + sd.numel() * 8 + prm.n_obst * 24
+    d2h = o_pl.numel() + 3 * o_x.numel() * 8 + 3 * o_par.numel() * 4 + o_bp.numel() * 4
+
+    def call():
+        rc = _abi.lib.rrtfnd_plan_host(C.byref(prm), P, sg.data_ptr(), sd.data_ptr(), ob.data_ptr(), None,
+                                       o_pl.data_ptr(), o_x.data_ptr(), o_y.data_ptr(), o_e.data_ptr(),
+                                       o_par.data_ptr(), o_nc.data_ptr(), o_id.data_ptr(), o_bp.data_ptr(), dev.index)
+        _abi.check(rc, "rrtfnd_plan_host")
+
+    call()  # warm-up (allocator, module load)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        call()           # synchronous: returns after the device->host copies have completed
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    from rrt_star_fnd_algorithm_b200._structs import PLANNER_DTYPE
+    pl = o_pl.numpy().reshape(-1).view(PLANNER_DTYPE)
+    ext = torch.tensor([float(pl["iter"].sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ext)
+    return {"value": float(ext.item()) * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": n, "ms_per_step": dt / n * 1e3,
+            "api": "rrtfnd_plan_host (C ABI, pinned host buffers; whole trees + planner records + best paths copied back)"}
+
+
+def spot_check(w, first, b):
+    """Planner 0 of this rank vs the CPU oracle on the same Philox stream (bit-exact tree comparison)."""
+    try:
+        import oracle as O
+        from rrt_star_fnd_algorithm_b200 import _structs as S
+        from rrt_star_fnd_algorithm_b200 import workloads as W
+        s, g, seeds, sids = W.planner_problems(w, first, 1)
+        t = O.OracleTree(s[0], w["iter_num"] + 2)
+        t.run(oracle_params(w, 0), w["obstacles"], g[0], seed=int(seeds[0]), stream_id=int(sids[0]))
+        got, want = b.tree(0), t.export()
+        ok = all(np.array_equal(got[k], want[k]) for k in want)
+        ok = ok and float(b.planners()[0]["best_cost"]) == t.planner().best_cost
+        return "bit-exact vs oracle (planner 0)" if ok else "MISMATCH vs oracle (planner 0)"
+    except Exception as e:  # the bench number does not depend on the checker
+        return f"not checked: {type(e).__name__}: {e}"
+
+
+if __name__ == "__main__":
+    main()

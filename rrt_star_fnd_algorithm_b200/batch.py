@@ -42,7 +42,7 @@ class PlannerBatch:
     def __init__(self, mode, *, starts, goals, obstacles, xy_range, iter_num, step_length, radius=0.0,
                  node_radius=1.0, bias=0.0, max_nodes=200, seeds=None, stream_ids=None, words=None,
                  capacity=None, near_cap=512, finish_cap=1024, path_cap=1024, trace=False,
-                 eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None):
+                 eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None, launch=0):
         if not torch.cuda.is_available():
             raise RuntimeError("PlannerBatch needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -63,6 +63,7 @@ class PlannerBatch:
             (FLAG_TRACE if trace else 0)
         prm.trace_cap = int(iter_num) + 1 if trace else 0
         prm.max_attempts = int(max_attempts)
+        prm.reserved = int(launch)   # explicit launch geometry (threads + 1000*layout), 0 = automatic
         prm.step_length, prm.radius, prm.node_radius, prm.bias = float(step_length), float(radius or 0.0), \
             float(node_radius), float(bias)
         (prm.x_lo, prm.x_hi), (prm.y_lo, prm.y_hi) = [(float(a), float(b)) for a, b in xy_range]

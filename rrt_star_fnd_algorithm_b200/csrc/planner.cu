@@ -51,13 +51,13 @@ struct SmemPlan {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline SmemPlan plan_smem(const rrtfnd_params_t& prm, int nt, bool tree_in_smem) {
+__host__ __device__ inline SmemPlan plan_smem(const rrtfnd_params_t& prm, int nt, bool tree_in_smem, bool obst_in_smem = true) {
     SmemPlan s;
     size_t o = 0;
     const size_t C = (size_t)prm.capacity;
     s.off_x = o; o += tree_in_smem ? align_up(C * 8, 16) : 0;
     s.off_y = o; o += tree_in_smem ? align_up(C * 8, 16) : 0;
-    s.off_obst = o; o += align_up((size_t)prm.n_obst * 8, 16) * 4;          // ox | oy | r | K
+    s.off_obst = o; o += obst_in_smem ? align_up((size_t)prm.n_obst * 8, 16) * 4 : 0;   // ox | oy | r | K
     s.bm_words = (int)((C + nt) / 32 + 1);
     s.off_bm = o; o += align_up((size_t)s.bm_words * 4, 16);
     s.off_cdpl = o; o += align_up((size_t)prm.near_cap * 8, 16);
@@ -87,7 +87,10 @@ __device__ __forceinline__ double chain_walk(const int32_t* __restrict__ parent,
     return acc;
 }
 
-template <int NT, bool kTreeInSmem>
+// kTreeInSmem: x[]/y[] of the planner staged in shared memory (else streamed from HBM/L2 through L1).
+// kObstInSmem: obstacle table staged per CTA as SoA (else read as 32-byte rows through L1; the table is shared
+//              by every planner, so with many small CTAs per SM one L1-resident copy serves them all).
+template <int NT, bool kTreeInSmem, bool kObstInSmem>
 __global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NW = NT / 32;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, con
     const int p = blockIdx.x;
     const int C = prm.capacity;
     const int M = prm.n_obst;
-    const SmemPlan sp = plan_smem(prm, NT, kTreeInSmem);
+    const SmemPlan sp = plan_smem(prm, NT, kTreeInSmem, kObstInSmem);
 
     // per-planner global arrays
     double* __restrict__ GX = bt.x + (size_t)p * C;
@@ -116,6 +119,11 @@ __global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, con
     double* so_y = so_x + ostride;
     double* so_r = so_y + ostride;
     double* so_K = so_r + ostride;
+    const double2* __restrict__ gob = reinterpret_cast<const double2*>(bt.obst);
+    auto load_obst = [&](int j, double& ox, double& oy, double& orad, double& oK) {
+        if (kObstInSmem) { ox = so_x[j]; oy = so_y[j]; orad = so_r[j]; oK = so_K[j]; }
+        else { const double2 a = __ldg(gob + 2 * j), b = __ldg(gob + 2 * j + 1); ox = a.x; oy = a.y; orad = b.x; oK = b.y; }
+    };
     uint32_t* bm = reinterpret_cast<uint32_t*>(smem + sp.off_bm);
     int* cslot = reinterpret_cast<int*>(smem + sp.off_cslot);
     double* cdpl = reinterpret_cast<double*>(smem + sp.off_cdpl);
@@ -145,9 +153,11 @@ __global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, con
         rng.seed = PL->seed; rng.stream = PL->stream_id; rng.cursor = PL->cursor;
         rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0;
     }
-    for (int j = tid; j < M; j += NT) {
-        so_x[j] = bt.obst[4 * j + 0]; so_y[j] = bt.obst[4 * j + 1];
-        so_r[j] = bt.obst[4 * j + 2]; so_K[j] = bt.obst[4 * j + 3];
+    if (kObstInSmem) {
+        for (int j = tid; j < M; j += NT) {
+            so_x[j] = bt.obst[4 * j + 0]; so_y[j] = bt.obst[4 * j + 1];
+            so_r[j] = bt.obst[4 * j + 2]; so_K[j] = bt.obst[4 * j + 3];
+        }
     }
     __syncthreads();
     if (kTreeInSmem) {
@@ -246,7 +256,11 @@ __global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, con
         // ================================================================ B. Map.is_occupied_c (src/map.py:38-47)
         {
             bool occ = false;
-            for (int j = tid; j < M; j += NT) occ |= point_in_inflated(qx, qy, so_x[j], so_y[j], so_r[j], prm.node_radius);
+            for (int j = tid; j < M; j += NT) {
+                double ox, oy, orad, oK;
+                load_obst(j, ox, oy, orad, oK);
+                occ |= point_in_inflated(qx, qy, ox, oy, orad, prm.node_radius);
+            }
             if (__syncthreads_or(occ)) continue;                         // src/algorithm.py:39-40
         }
 
@@ -284,7 +298,11 @@ __global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, con
                 // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692)
                 const Seg sg = make_seg(qx, qy, sx[bs], sy[bs]);
                 bool hit = false;
-                for (int j = tid; j < M; j += NT) hit |= seg_hits_circle(sg, so_x[j], so_y[j], so_r[j], so_K[j]);
+                for (int j = tid; j < M; j += NT) {
+                    double ox, oy, orad, oK;
+                    load_obst(j, ox, oy, orad, oK);
+                    hit |= seg_hits_circle(sg, ox, oy, orad, oK);
+                }
                 if (tid == 0) { ++c.n_edge_checks; ++c.n_edge_checks_ref; c.n_circle_tests += M; c.n_scan_nodes += c.n_live; }
                 if (!__syncthreads_or(hit)) { near_slot = bs; break; }
                 prev_d = bd; prev_s = bs;
@@ -400,7 +418,11 @@ __global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, con
             for (; j0 < M; j0 += 32) {
                 const int j = j0 + lane;
                 bool h = false;
-                if (j < M) h = seg_hits_circle(sg, so_x[j], so_y[j], so_r[j], so_K[j]);
+                if (j < M) {
+                    double ox, oy, orad, oK;
+                    load_obst(j, ox, oy, orad, oK);
+                    h = seg_hits_circle(sg, ox, oy, orad, oK);
+                }
                 if (__any_sync(kFull, h)) { hit = true; j0 += 32; break; }
             }
             if (lane == 0) {
@@ -651,17 +673,57 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
     PL->solution_found = 0; PL->n_compactions = 0;
 }
 
-constexpr int kPlanThreads = 256;
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <bool kTreeInSmem>
+template <int NT, bool kTreeInSmem, bool kObstInSmem>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
-    const SmemPlan sp = plan_smem(*prm, kPlanThreads, kTreeInSmem);
-    auto kern = plan_kernel<kPlanThreads, kTreeInSmem>;
+    const SmemPlan sp = plan_smem(*prm, NT, kTreeInSmem, kObstInSmem);
+    auto kern = plan_kernel<NT, kTreeInSmem, kObstInSmem>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
     if (e != cudaSuccess) return (int)e;
-    kern<<<bt->n_planners, kPlanThreads, sp.total, st>>>(*prm, *bt);
+    kern<<<bt->n_planners, NT, sp.total, st>>>(*prm, *bt);
     return (int)cudaGetLastError();
+}
+
+// Launch geometry. prm->reserved encodes an explicit choice as threads + 1000 * layout
+// (layout 0: tree + obstacles in shared memory, 1: obstacles only, 2: neither); 0 = automatic.
+struct PlanCfg { int nt; int layout; };
+
+static PlanCfg choose_cfg(const rrtfnd_params_t& prm, int n_planners) {
+    if (prm.reserved > 0) return PlanCfg{prm.reserved % 1000, prm.reserved / 1000};
+    // Batches that can fill the GPU several CTAs deep run light CTAs (tree streamed through L1/L2, obstacle table
+    // L1-resident): occupancy hides the parent-chain latency. Small batches keep one fat CTA per planner with
+    // the coordinates in shared memory (lowest latency per tree).
+    if (n_planners >= 296 && plan_smem(prm, 128, false, false).total <= 24 * 1024) return PlanCfg{128, 2};
+    if (plan_smem(prm, 256, true, true).total <= kMaxSmem) return PlanCfg{256, 0};
+    if (plan_smem(prm, 256, false, true).total <= kMaxSmem) return PlanCfg{256, 1};
+    return PlanCfg{256, 2};
+}
+
+static size_t cfg_smem(const rrtfnd_params_t& prm, PlanCfg c) {
+    return plan_smem(prm, c.nt, c.layout == 0, c.layout <= 1).total;
+}
+
+template <int NT>
+static int launch_nt(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, int layout, cudaStream_t st) {
+    switch (layout) {
+        case 0: return launch_plan<NT, true, true>(prm, bt, st);
+        case 1: return launch_plan<NT, false, true>(prm, bt, st);
+        case 2: return launch_plan<NT, false, false>(prm, bt, st);
+        default: return RRTFND_E_BADARG;
+    }
+}
+
+static int launch_cfg(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, PlanCfg c, cudaStream_t st) {
+    if (cfg_smem(*prm, c) > kMaxSmem) return RRTFND_E_SMEM;
+    switch (c.nt) {
+        case 32: return launch_nt<32>(prm, bt, c.layout, st);
+        case 64: return launch_nt<64>(prm, bt, c.layout, st);
+        case 128: return launch_nt<128>(prm, bt, c.layout, st);
+        case 256: return launch_nt<256>(prm, bt, c.layout, st);
+        case 512: return launch_nt<512>(prm, bt, c.layout, st);
+        default: return RRTFND_E_BADARG;
+    }
 }
 
 }  // namespace rrtfnd
@@ -680,11 +742,8 @@ static int check_params(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
 
 extern "C" int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm) {
     if (!prm) return RRTFND_E_BADARG;
-    const SmemPlan a = plan_smem(*prm, kPlanThreads, true);
-    if (a.total <= kMaxSmem) return (int64_t)a.total;
-    const SmemPlan b = plan_smem(*prm, kPlanThreads, false);
-    if (b.total <= kMaxSmem) return (int64_t)b.total;
-    return RRTFND_E_SMEM;
+    const size_t b = cfg_smem(*prm, choose_cfg(*prm, 1 << 20));
+    return b <= kMaxSmem ? (int64_t)b : (int64_t)RRTFND_E_SMEM;
 }
 
 extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, void* stream) {
@@ -694,10 +753,7 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     if (!(q.flags & RRTFND_FLAG_TRACE)) q.trace_cap = 0;
     rrtfnd_batch_t b = *bt;
     if (!(q.flags & RRTFND_FLAG_TRACE)) b.trace = nullptr;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (plan_smem(q, kPlanThreads, true).total <= kMaxSmem) return launch_plan<true>(&q, &b, st);
-    if (plan_smem(q, kPlanThreads, false).total <= kMaxSmem) return launch_plan<false>(&q, &b, st);
-    return RRTFND_E_SMEM;
+    return launch_cfg(&q, &b, choose_cfg(q, b.n_planners), (cudaStream_t)stream);
 }
 
 extern "C" int rrtfnd_init_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, void* stream) {

@@ -1,0 +1,74 @@
+"""Synthetic workloads of BASELINE.json / SURVEY.md §8(d): maps, per-planner start/goal pairs and stream keys.
+
+Everything is a pure function of (workload name, global planner index), so a planner's problem — and
+therefore its tree — does not depend on how planners are sharded over GPUs.
+"""
+import numpy as np
+
+
+def _circles(seed, n, lo, hi, rmin, rmax, keep_clear=(), node_radius=0.0):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        c = rng.uniform(lo, hi, 2)
+        r = rng.uniform(rmin, rmax)
+        if any(np.hypot(c[0] - p[0], c[1] - p[1]) < node_radius + r for p in keep_clear):
+            continue
+        out.append((float(c[0]), float(c[1]), float(r)))
+    return out
+
+
+def _occupied(p, obst, node_radius):
+    ob = np.asarray(obst)
+    return bool((np.hypot(p[0] - ob[:, 0], p[1] - ob[:, 1]) < node_radius + ob[:, 2] + 1e-9).any())
+
+
+def c1():
+    """Config 1: RRT* on the reconstructed src/main.py map (9 cylinders), 2,000 iterations, one planner."""
+    obst = [(float(x), float(y), 15.0) for x in (-110, 0, 110) for y in (-110, 0, 110)]
+    return dict(name="c1", mode="star", obstacles=obst, xy_range=[[-210.0, 210.0], [-210.0, 210.0]], iter_num=2000,
+                step_length=25.0, radius=50.0, node_radius=20.0, bias=0.01, max_nodes=0,
+                start=(144.65717764052022, 108.34084923492702), goal=(-33.35993605104511, -101.2549648769554),
+                seed_base=1, planners=1)
+
+
+def c2():
+    """Config 2: RRT*-FN, 1,000-node cap, 100x100 map, 200 circles, 4,096 planners sharing start/goal."""
+    start, goal = (5.0, 5.0), (95.0, 95.0)
+    obst = _circles(2, 200, 2, 98, 0.5, 2.0, keep_clear=(start, goal), node_radius=1.0)
+    return dict(name="c2", mode="fn", obstacles=obst, xy_range=[[0.0, 100.0], [0.0, 100.0]], iter_num=5000,
+                step_length=3.0, radius=6.0, node_radius=1.0, bias=0.01, max_nodes=1000, start=start, goal=goal,
+                seed_base=1000, planners=4096)
+
+
+def c3():
+    """Config 3: RRT*, 200x200 map, 500 circles, 16,384 planners with random start/goal, 5,000 iterations."""
+    obst = _circles(3, 500, 0, 200, 1.0, 4.0)
+    return dict(name="c3", mode="star", obstacles=obst, xy_range=[[0.0, 200.0], [0.0, 200.0]], iter_num=5000,
+                step_length=5.0, radius=10.0, node_radius=2.0, bias=0.02, max_nodes=0, start=None, goal=None,
+                seed_base=3000, planners=16384)
+
+
+WORKLOADS = {"c1": c1, "c2": c2, "c3": c3}
+
+
+def planner_problems(w, first, count):
+    """starts [count,2], goals [count,2], seeds [count], stream_ids [count] for global planners first..first+count-1."""
+    starts = np.zeros((count, 2))
+    goals = np.zeros((count, 2))
+    for i in range(count):
+        g = first + i
+        if w["start"] is not None:
+            starts[i], goals[i] = w["start"], w["goal"]
+            continue
+        rng = np.random.default_rng([w["seed_base"], g])
+        (x0, x1), (y0, y1) = w["xy_range"]
+        pts = []
+        while len(pts) < 2:
+            p = (rng.uniform(x0, x1), rng.uniform(y0, y1))
+            if not _occupied(p, w["obstacles"], w["node_radius"]):
+                pts.append(p)
+        starts[i], goals[i] = pts
+    seeds = np.full(count, w["seed_base"], dtype=np.uint64)
+    stream_ids = np.arange(first, first + count, dtype=np.uint64)
+    return starts, goals, seeds, stream_ids

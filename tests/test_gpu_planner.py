@@ -113,3 +113,12 @@ def test_resume_after_need_words():
         b.prm.words_per_planner = n
     assert calls > 3
     check_against_golden(b, case, g)
+
+
+@pytest.mark.parametrize("launch", [32 + 2000, 64 + 2000, 128 + 2000, 64 + 1000, 128 + 0, 512 + 0, 256 + 1000])
+@pytest.mark.parametrize("name", ["dense_fn", "int_star"])
+def test_every_launch_geometry_gives_the_same_tree(name, launch):
+    """threads-per-planner and the shared-memory layout are performance knobs only."""
+    case, g = K.case_by_name(name), load_golden(name)
+    b = make_batch(case, seeds=[case["seed"]], stream_ids=[case["stream_id"]], launch=launch, near_cap=128).run()
+    check_against_golden(b, case, g)
