@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--planners", type=int, default=0, help="planners per GPU (0 = workload default)")
     ap.add_argument("--iters", type=int, default=0, help="iterations per planner (0 = workload default)")
     ap.add_argument("--launch", type=int, default=0)
-    ap.add_argument("--near-cap", type=int, default=256)
+    ap.add_argument("--near-cap", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -343,15 +343,15 @@ def run_e2e(args, w, P, first, b, dev):
     sd = pin((P, 2), torch.int64); sd.copy_(torch.from_numpy(np.stack([seeds, sids], 1).astype(np.int64)))
     ob = pin((max(prm.n_obst, 1), 3), torch.float64); ob[:prm.n_obst].copy_(torch.from_numpy(np.asarray(w["obstacles"], np.float64)))
     o_pl = pin((P, PLANNER_BYTES), torch.uint8)
-    o_x, o_y, o_e = pin((P, Cn), torch.float64), pin((P, Cn), torch.float64), pin((P, Cn), torch.float64)
+    o_xy, o_e = pin((P, Cn, 2), torch.float64), pin((P, Cn), torch.float64)
     o_par, o_nc, o_id = pin((P, Cn), torch.int32), pin((P, Cn), torch.int32), pin((P, Cn), torch.int32)
     o_bp = pin((P, prm.path_cap), torch.int32)
     h2d = sg.numel() * 8 + sd.numel() * 8 + prm.n_obst * 24
-    d2h = o_pl.numel() + 3 * o_x.numel() * 8 + 3 * o_par.numel() * 4 + o_bp.numel() * 4
+    d2h = o_pl.numel() + o_xy.numel() * 8 + o_e.numel() * 8 + 3 * o_par.numel() * 4 + o_bp.numel() * 4
 
     def call():
         rc = _abi.lib.rrtfnd_plan_host(C.byref(prm), P, sg.data_ptr(), sd.data_ptr(), ob.data_ptr(), None,
-                                       o_pl.data_ptr(), o_x.data_ptr(), o_y.data_ptr(), o_e.data_ptr(),
+                                       o_pl.data_ptr(), o_xy.data_ptr(), o_e.data_ptr(),
                                        o_par.data_ptr(), o_nc.data_ptr(), o_id.data_ptr(), o_bp.data_ptr(), dev.index)
         _abi.check(rc, "rrtfnd_plan_host")
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RRTFND_ABI_VERSION 1
+#define RRTFND_ABI_VERSION 2
 
 /* planner kinds: src/algorithm.py:55 (RRT), :98 (RRT_star), :190 (RRT_star_FN) */
 #define RRTFND_MODE_RRT 0
@@ -48,7 +48,7 @@ extern "C" {
 #define RRTFND_ST_NEED_WORDS 2     /* word buffer exhausted at an attempt boundary; refill and call again */
 #define RRTFND_ST_ATTEMPT_CAP 3    /* max_attempts reached (reference would still be looping, src/algorithm.py:74-75) */
 #define RRTFND_ST_CAPACITY (-1)    /* node capacity exhausted */
-#define RRTFND_ST_NEAR_CAP (-2)    /* near-set larger than near_cap */
+#define RRTFND_ST_NEAR_CAP (-2)    /* reserved (v1: near-set larger than near_cap); never returned by ABI v2 */
 #define RRTFND_ST_FINISH_CAP (-3)  /* more goal-reaching nodes than finish_cap */
 #define RRTFND_ST_PATH_CAP (-4)    /* best path longer than path_cap */
 #define RRTFND_ST_DUPLICATE (-5)   /* steered point coincides with an existing vertex (src/graph.py:54-56 corner) */
@@ -66,7 +66,7 @@ typedef struct rrtfnd_params {
     int32_t max_nodes;     /* RRT*-FN node cap (src/algorithm.py:233) */
     int32_t capacity;      /* node slots per planner */
     int32_t n_obst;        /* circles in the obstacle table */
-    int32_t near_cap;      /* max near-set size handled */
+    int32_t near_cap;      /* re-parented nodes of one rewire_kdtree call kept in shared memory (more spill to nflags; a performance knob) */
     int32_t finish_cap;    /* max goal-reaching nodes tracked (finish_nodes_of_path, :116) */
     int32_t path_cap;      /* max ids stored for best_path["path"] */
     int32_t stream_mode;   /* RRTFND_STREAM_* */
@@ -120,29 +120,60 @@ typedef struct rrtfnd_trace {
     double cp_cost;     /* cost in that returned edge */
 } rrtfnd_trace_t;
 
+/* Uniform grid over the circular obstacles, used to cull circle tests without changing a single boolean
+ * (DESIGN.md "Obstacle grid": a circle is listed in every cell its box, inflated by r + margin, overlaps; the
+ * margin bounds the rounding error of the reference's own quadratic for |slope| <= slope_max and
+ * |coordinates| <= coord_max; other segments fall back to the full table). nx == 0 disables culling.
+ * cell(v) = min(max((int)floor((v - v0) * inv_cell), 0), n - 1) on both the host builder and the device. */
+typedef struct rrtfnd_obst_grid {
+    double x0, y0, inv_cell;
+    double slope_max;           /* segments with |Line.dir| above this (or vertical / NaN) test every circle */
+    double coord_max;           /* bound on |coordinate| and radius the margin was derived for */
+    double margin;              /* inflation used for seg_* lists (informational) */
+    int32_t nx, ny;
+    const int32_t* seg_start;   /* [nx*ny + 1] CSR offsets into seg_items (row-major cells, x fastest) */
+    const int32_t* seg_items;   /* obstacle indices for through_obstacle (src/algorithm.py:581-591) */
+    const int32_t* pt_start;    /* [nx*ny + 1] CSR offsets into pt_items */
+    const int32_t* pt_items;    /* obstacle indices for Map.is_occupied_c (src/map.py:38-47), inflated by node_radius */
+} rrtfnd_obst_grid_t;
+
 /* Device-resident batch of P independent planners, structure-of-arrays, fixed capacity. */
 typedef struct rrtfnd_batch {
     int32_t n_planners;
     int32_t reserved;
     rrtfnd_planner_t* planners; /* [P] */
-    double* x;                  /* [P][capacity] node x; NaN in a tombstone slot */
-    double* y;                  /* [P][capacity] */
+    double* xy;                 /* [P][capacity][2] node position (x, y); NaN in a tombstone slot */
     double* ecost;              /* [P][capacity] edge cost to parent (Graph.cost, src/graph.py:29) */
     int32_t* parent;            /* [P][capacity] parent SLOT, -1 = none */
     int32_t* nchild;            /* [P][capacity] len(Graph.children[id]) */
     int32_t* id;                /* [P][capacity] reference node id, -1 = tombstone; ascending in slot order */
+    uint8_t* nflags;            /* [P][capacity] scratch: bit 0 = some goal-reaching node descends from this node */
     int32_t* finish;            /* [P][finish_cap] slots of goal-reaching nodes, in discovery order */
     int32_t* best_path;         /* [P][path_cap] ids leaf -> root (best_path["path"]) */
     const double* obst;         /* [n_obst][4]: ox, oy, r, K = ((-(r*r)) + ox*ox) + oy*oy */
     const uint32_t* words;      /* [P][words_per_planner] or NULL */
     rrtfnd_trace_t* trace;      /* [P][trace_cap] or NULL */
+    rrtfnd_obst_grid_t grid;    /* optional culling grid over obst */
 } rrtfnd_batch_t;
 
 /* ---- library info ------------------------------------------------------------------------ */
 int rrtfnd_abi_version(void);
 const char* rrtfnd_status_string(int status);
-/* dynamic shared memory (bytes) the fused planner kernel needs for these parameters; <0 = does not fit */
+/* dynamic shared memory (bytes) per planner the fused planner kernel needs for these parameters; <0 = does not fit */
 int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm);
+
+/* ---- obstacle grid (host side, no CUDA calls) ------------------------------------------------- */
+
+/* Build the culling grid for obst_host [M][3] (ox, oy, r) over the box [lo_x, hi_x] x [lo_y, hi_y] that
+ * bounds every coordinate the planners can produce (xy_range, starts, goals). cell <= 0 picks
+ * sqrt(area / M). Two-call pattern: with seg_items_host == NULL only the sizes are returned in
+ * n_items_out[0] (seg) and n_items_out[1] (pt) and grid_out->nx/ny are set; otherwise the CSR arrays are
+ * filled (seg_start_host / pt_start_host hold nx*ny + 1 entries). Pointers inside grid_out are left NULL:
+ * the caller uploads the four arrays and stores the device pointers. */
+int rrtfnd_obst_grid_build_host(const double* obst_host, int32_t n_obst, double node_radius, double lo_x,
+                                double hi_x, double lo_y, double hi_y, double cell, rrtfnd_obst_grid_t* grid_out,
+                                int32_t* seg_start_host, int32_t* seg_items_host, int32_t* pt_start_host,
+                                int32_t* pt_items_host, int64_t* n_items_out);
 
 /* ---- stateless batched operators (device pointers) ------------------------------------------ */
 
@@ -157,9 +188,19 @@ int rrtfnd_edges_vs_circles(const double* p1x, const double* p1y, const double* 
 int rrtfnd_points_occupied(const double* px, const double* py, int64_t n_points, const double* obst,
                            int32_t n_obst, double node_radius, uint8_t* out_occ, void* stream);
 
+/* The same two predicates evaluated the way the fused planner does: circles culled through `grid` (host struct
+ * holding device pointers). Results are identical to the un-culled operators above by construction; the parity
+ * tests compare them on adversarial inputs. */
+int rrtfnd_edges_vs_circles_grid(const double* p1x, const double* p1y, const double* p2x, const double* p2y,
+                                 int64_t n_edges, const double* obst, int32_t n_obst, const rrtfnd_obst_grid_t* grid,
+                                 uint8_t* out_hit, void* stream);
+int rrtfnd_points_occupied_grid(const double* px, const double* py, int64_t n_points, const double* obst,
+                                int32_t n_obst, const rrtfnd_obst_grid_t* grid, double node_radius, uint8_t* out_occ,
+                                void* stream);
+
 /* nearest_node_kdtree (src/algorithm.py:666-699) for one query per planner: the slot of the nearest node
  * (plain d2, lowest id on ties) whose segment Line(q, node) is collision free; -1 if none is visible,
- * -2 if q coincides exactly with a vertex (:676-678). q is [P][2]. */
+ * -2 if q coincides exactly with a vertex (:676-678). q is [P][2]. Tests every circle (no grid). */
 int rrtfnd_nearest_visible(const rrtfnd_batch_t* batch, int32_t capacity, const double* q, int32_t n_obst,
                            int32_t* out_slot, int32_t* out_rounds, void* stream);
 
@@ -177,7 +218,7 @@ int rrtfnd_chain_cost(const rrtfnd_batch_t* batch, int32_t capacity, const int32
 /* Advance every planner of the batch until iter == prm->iter_num (or a status other than RUNNING).
  * Replaces the loops of RRT / RRT_star / RRT_star_FN (src/algorithm.py:71-94, :118-186, :214-265) with
  * new_node (:36-51), choose_parent_kdtree (:822-852), rewire_kdtree (:882-910), forced_removal (:800-819),
- * check_solution (:749-760), find_path (:778-797) fused into one persistent CTA per planner. Resumable. */
+ * check_solution (:749-760), find_path (:778-797) fused into one persistent warp per planner. Resumable. */
 int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, void* stream);
 
 /* Initialise planner p's tree to the single root node `start` (Graph.__init__, src/graph.py:25-32) and
@@ -203,10 +244,11 @@ int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch
 /* Plan P independent problems given HOST buffers; allocates device memory, copies in, runs to completion,
  * copies results back. starts_goals_host is [P][4] (sx, sy, gx, gy); seeds_host is [P][2] (seed, stream_id);
  * obst_host is [M][3] (ox, oy, r). Outputs (all host, may be NULL to skip): planners_host [P];
- * tree arrays [P][capacity] x, y, ecost, parent (slot), nchild, id; best_path_host [P][path_cap]. */
+ * tree arrays xy [P][capacity][2], ecost, parent (slot), nchild, id [P][capacity]; best_path_host
+ * [P][path_cap]. The obstacle grid is built inside the call. */
 int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t n_planners, const double* starts_goals_host,
                      const uint64_t* seeds_host, const double* obst_host, const uint32_t* words_host,
-                     rrtfnd_planner_t* planners_host, double* x_host, double* y_host, double* ecost_host,
+                     rrtfnd_planner_t* planners_host, double* xy_host, double* ecost_host,
                      int32_t* parent_host, int32_t* nchild_host, int32_t* id_host, int32_t* best_path_host,
                      int32_t device);
 

@@ -24,10 +24,10 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "rrt_oracle.c")
-    hdr = os.path.join(_HERE, "..", "include", "rrtfnd.h")
+    srcs = [os.path.join(_HERE, "rrt_oracle.c"), os.path.join(_HERE, "cull_probe.c"),
+            os.path.join(_HERE, "..", "include", "rrtfnd.h")]
     stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -60,6 +60,8 @@ def lib():
     L.orc_near_set.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, vp]
     L.orc_run.argtypes = [vp, C.POINTER(Params), vp, C.c_double, C.c_double, vp, C.c_int64, C.c_uint64,
                           C.c_uint64, vp]
+    L.orc_cull_probe.restype = C.c_int64
+    L.orc_cull_probe.argtypes = [C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int64)]
     L.orc_run_batch.argtypes = [C.POINTER(Params), C.c_int, vp, vp, vp, vp, C.c_int]
     _lib = L
     return L
@@ -166,3 +168,11 @@ def run_batch(prm: Params, starts_goals, seeds, obstacles, n_threads=1):
     out = np.zeros(len(sg), dtype=PLANNER_DTYPE)
     bad = lib().orc_run_batch(C.byref(prm), len(sg), _ptr(sg), _ptr(sd), _ptr(ob), _ptr(out), int(n_threads))
     return out, bad
+
+
+def cull_probe(seed, n_trials, coord_max, slope_max, margin, scale=1.0):
+    """Adversarial check of the grid-culling rule (oracle/cull_probe.c): (hits, valid pairs)."""
+    nv = C.c_int64(0)
+    h = lib().orc_cull_probe(int(seed), int(n_trials), float(coord_max), float(slope_max), float(margin), float(scale),
+                             C.byref(nv))
+    return int(h), int(nv.value)

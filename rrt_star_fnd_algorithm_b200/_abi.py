@@ -3,15 +3,15 @@ or cannot be loaded, importing this module raises."""
 import ctypes as C
 import os
 
-from ._structs import ABI_VERSION, Batch, Params, Planner
+from ._structs import ABI_VERSION, Batch, ObstGrid, Params, Planner
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librrtfnd.so")
 
 # every symbol include/rrtfnd.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [
-    "rrtfnd_abi_version", "rrtfnd_status_string", "rrtfnd_plan_smem_bytes",
-    "rrtfnd_edges_vs_circles", "rrtfnd_points_occupied", "rrtfnd_nearest_visible", "rrtfnd_near_set",
+    "rrtfnd_abi_version", "rrtfnd_status_string", "rrtfnd_plan_smem_bytes", "rrtfnd_obst_grid_build_host",
+    "rrtfnd_edges_vs_circles", "rrtfnd_points_occupied", "rrtfnd_edges_vs_circles_grid", "rrtfnd_points_occupied_grid", "rrtfnd_nearest_visible", "rrtfnd_near_set",
     "rrtfnd_chain_cost", "rrtfnd_plan_batch", "rrtfnd_init_batch",
     "rrtfnd_fnd_select_branch", "rrtfnd_fnd_valid_path", "rrtfnd_fnd_reconnect",
     "rrtfnd_plan_host",
@@ -37,6 +37,8 @@ def _load():
     lib.rrtfnd_plan_smem_bytes.argtypes = [PP]
     lib.rrtfnd_edges_vs_circles.argtypes = [vp, vp, vp, vp, i64, vp, i32, vp, vp]
     lib.rrtfnd_points_occupied.argtypes = [vp, vp, i64, vp, i32, dbl, vp, vp]
+    lib.rrtfnd_edges_vs_circles_grid.argtypes = [vp, vp, vp, vp, i64, vp, i32, C.POINTER(ObstGrid), vp, vp]
+    lib.rrtfnd_points_occupied_grid.argtypes = [vp, vp, i64, vp, i32, C.POINTER(ObstGrid), dbl, vp, vp]
     lib.rrtfnd_nearest_visible.argtypes = [PB, i32, vp, i32, vp, vp, vp]
     lib.rrtfnd_near_set.argtypes = [PB, i32, vp, dbl, i32, vp, vp, vp]
     lib.rrtfnd_chain_cost.argtypes = [PB, i32, vp, vp, i64, vp, vp]
@@ -45,7 +47,8 @@ def _load():
     lib.rrtfnd_fnd_select_branch.argtypes = [PP, PB, vp, vp]
     lib.rrtfnd_fnd_valid_path.argtypes = [PP, PB, vp, vp]
     lib.rrtfnd_fnd_reconnect.argtypes = [PP, PB, vp, dbl, vp, vp]
-    lib.rrtfnd_plan_host.argtypes = [PP, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
+    lib.rrtfnd_plan_host.argtypes = [PP, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
+    lib.rrtfnd_obst_grid_build_host.argtypes = [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, C.POINTER(ObstGrid), vp, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here = the library does not match the header
         if name not in ("rrtfnd_status_string", "rrtfnd_plan_smem_bytes", "rrtfnd_abi_version"):

@@ -1,7 +1,7 @@
 """ctypes mirrors of the structs in include/rrtfnd.h (kept field-for-field in the same order)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MODE_RRT, MODE_STAR, MODE_FN = 0, 1, 2
 STREAM_WORDS, STREAM_PHILOX = 0, 1
@@ -12,7 +12,7 @@ ST_CAPACITY, ST_NEAR_CAP, ST_FINISH_CAP, ST_PATH_CAP, ST_DUPLICATE, ST_NO_CHILDL
 
 STATUS_NAMES = {
     ST_RUNNING: "running", ST_DONE: "done", ST_NEED_WORDS: "need-words", ST_ATTEMPT_CAP: "attempt-cap",
-    ST_CAPACITY: "node capacity exhausted", ST_NEAR_CAP: "near-set larger than near_cap",
+    ST_CAPACITY: "node capacity exhausted", ST_NEAR_CAP: "more nodes rewired in one iteration than near_cap",
     ST_FINISH_CAP: "finish list full", ST_PATH_CAP: "best path longer than path_cap",
     ST_DUPLICATE: "steered point coincides with an existing vertex",
     ST_NO_CHILDLESS: "forced_removal has no removable childless node",
@@ -54,14 +54,24 @@ class Trace(C.Structure):
     ]
 
 
+class ObstGrid(C.Structure):
+    _fields_ = [
+        ("x0", C.c_double), ("y0", C.c_double), ("inv_cell", C.c_double),
+        ("slope_max", C.c_double), ("coord_max", C.c_double), ("margin", C.c_double),
+        ("nx", C.c_int32), ("ny", C.c_int32),
+        ("seg_start", C.c_void_p), ("seg_items", C.c_void_p), ("pt_start", C.c_void_p), ("pt_items", C.c_void_p),
+    ]
+
+
 class Batch(C.Structure):
     _fields_ = [
         ("n_planners", C.c_int32), ("reserved", C.c_int32),
         ("planners", C.c_void_p),
-        ("x", C.c_void_p), ("y", C.c_void_p), ("ecost", C.c_void_p),
-        ("parent", C.c_void_p), ("nchild", C.c_void_p), ("id", C.c_void_p),
+        ("xy", C.c_void_p), ("ecost", C.c_void_p),
+        ("parent", C.c_void_p), ("nchild", C.c_void_p), ("id", C.c_void_p), ("nflags", C.c_void_p),
         ("finish", C.c_void_p), ("best_path", C.c_void_p),
         ("obst", C.c_void_p), ("words", C.c_void_p), ("trace", C.c_void_p),
+        ("grid", ObstGrid),
     ]
 
 

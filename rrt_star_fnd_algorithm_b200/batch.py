@@ -8,7 +8,7 @@ import torch
 
 from . import _abi
 from ._structs import (
-    Batch, Params, PLANNER_BYTES, PLANNER_DTYPE, TRACE_BYTES, TRACE_DTYPE,
+    Batch, ObstGrid, Params, PLANNER_BYTES, PLANNER_DTYPE, TRACE_BYTES, TRACE_DTYPE,
     MODE_RRT, MODE_STAR, MODE_FN, STREAM_WORDS, STREAM_PHILOX, FLAG_EVAL_CHOOSE_PARENT, FLAG_TRACE,
     ST_DONE, ST_RUNNING, ST_NEED_WORDS, STATUS_NAMES,
 )
@@ -33,6 +33,26 @@ def obstacle_table(obstacles) -> np.ndarray:
     return np.asarray(rows, dtype=np.float64).reshape(-1, 4)
 
 
+def build_obstacle_grid(obstacles3: np.ndarray, node_radius: float, bounds, cell: float = 0.0):
+    """Host-side culling grid (rrtfnd_obst_grid_build_host): returns (ObstGrid without pointers, 4 int32 arrays).
+
+    `bounds` = (lo_x, hi_x, lo_y, hi_y) must contain every coordinate the planners can produce."""
+    ob = np.ascontiguousarray(obstacles3, dtype=np.float64).reshape(-1, 3)
+    g = ObstGrid()
+    cnt = (C.c_int64 * 2)()
+    args = (ob.ctypes.data, len(ob), float(node_radius), float(bounds[0]), float(bounds[1]), float(bounds[2]),
+            float(bounds[3]), float(cell), C.byref(g))
+    _abi.check(_abi.lib.rrtfnd_obst_grid_build_host(*args, None, None, None, None, cnt), "rrtfnd_obst_grid_build_host")
+    if g.nx == 0:
+        return g, None
+    nc = g.nx * g.ny
+    arrs = [np.zeros(nc + 1, np.int32), np.zeros(max(int(cnt[0]), 1), np.int32),
+            np.zeros(nc + 1, np.int32), np.zeros(max(int(cnt[1]), 1), np.int32)]
+    _abi.check(_abi.lib.rrtfnd_obst_grid_build_host(*args, *[a.ctypes.data for a in arrs], cnt),
+               "rrtfnd_obst_grid_build_host")
+    return g, arrs
+
+
 def fn_capacity(max_nodes: int) -> int:
     """Slots for an RRT*-FN planner: the cap, the transient extra node, and tombstone slack between compactions."""
     return int(max_nodes) + 2 + max(256, int(max_nodes) // 4)
@@ -41,8 +61,9 @@ def fn_capacity(max_nodes: int) -> int:
 class PlannerBatch:
     def __init__(self, mode, *, starts, goals, obstacles, xy_range, iter_num, step_length, radius=0.0,
                  node_radius=1.0, bias=0.0, max_nodes=200, seeds=None, stream_ids=None, words=None,
-                 capacity=None, near_cap=512, finish_cap=1024, path_cap=1024, trace=False,
-                 eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None, launch=0):
+                 capacity=None, near_cap=64, finish_cap=1024, path_cap=1024, trace=False,
+                 eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None, launch=0,
+                 grid=True, grid_cell=0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("PlannerBatch needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -63,7 +84,7 @@ class PlannerBatch:
             (FLAG_TRACE if trace else 0)
         prm.trace_cap = int(iter_num) + 1 if trace else 0
         prm.max_attempts = int(max_attempts)
-        prm.reserved = int(launch)   # explicit launch geometry (threads + 1000*layout), 0 = automatic
+        prm.reserved = int(launch)   # planners (warps) per CTA: 1, 2, 4, 8; 0 = automatic
         prm.step_length, prm.radius, prm.node_radius, prm.bias = float(step_length), float(radius or 0.0), \
             float(node_radius), float(bias)
         (prm.x_lo, prm.x_hi), (prm.y_lo, prm.y_hi) = [(float(a), float(b)) for a, b in xy_range]
@@ -84,15 +105,26 @@ class PlannerBatch:
             pl["stream_id"] = np.asarray(stream_ids if stream_ids is not None else np.zeros(P), dtype=np.uint64)
         self.planners_t = torch.from_numpy(pl.view(np.uint8).reshape(P, PLANNER_BYTES).copy()).to(dev)
         Cn = prm.capacity
-        self.x = torch.empty((P, Cn), dtype=torch.float64, device=dev)
-        self.y = torch.empty((P, Cn), dtype=torch.float64, device=dev)
+        self.xy = torch.empty((P, Cn, 2), dtype=torch.float64, device=dev)
         self.ecost = torch.empty((P, Cn), dtype=torch.float64, device=dev)
         self.parent = torch.empty((P, Cn), dtype=torch.int32, device=dev)
         self.nchild = torch.empty((P, Cn), dtype=torch.int32, device=dev)
         self.id = torch.empty((P, Cn), dtype=torch.int32, device=dev)
+        self.nflags = torch.zeros((P, Cn), dtype=torch.uint8, device=dev)
         self.finish = torch.empty((P, prm.finish_cap), dtype=torch.int32, device=dev)
         self.best_path_t = torch.empty((P, prm.path_cap), dtype=torch.int32, device=dev)
         self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(dev)
+        # culling grid over the obstacles; its box bounds the sampling range and every start / goal
+        self.grid = ObstGrid()
+        self._grid_t = None
+        if grid and len(self.obst_host):
+            pts = np.concatenate([starts, goals, np.asarray(xy_range, dtype=np.float64).T])
+            bounds = (pts[:, 0].min(), pts[:, 0].max(), pts[:, 1].min(), pts[:, 1].max())
+            g, arrs = build_obstacle_grid(self.obst_host[:, :3], prm.node_radius, bounds, grid_cell)
+            if arrs is not None:
+                self._grid_t = [torch.from_numpy(a).to(dev) for a in arrs]
+                g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in self._grid_t]
+                self.grid = g
         self.trace_t = torch.zeros((P, max(prm.trace_cap, 1) * TRACE_BYTES), dtype=torch.uint8, device=dev) if trace else None
         self._initialised = False
         smem = _abi.lib.rrtfnd_plan_smem_bytes(C.byref(prm))
@@ -105,8 +137,10 @@ class PlannerBatch:
         b = Batch()
         b.n_planners = self.P
         b.planners = self.planners_t.data_ptr()
-        b.x, b.y, b.ecost = self.x.data_ptr(), self.y.data_ptr(), self.ecost.data_ptr()
+        b.xy, b.ecost = self.xy.data_ptr(), self.ecost.data_ptr()
         b.parent, b.nchild, b.id = self.parent.data_ptr(), self.nchild.data_ptr(), self.id.data_ptr()
+        b.nflags = self.nflags.data_ptr()
+        b.grid = self.grid
         b.finish, b.best_path = self.finish.data_ptr(), self.best_path_t.data_ptr()
         b.obst = self.obst.data_ptr()
         b.words = self.words.data_ptr() if self.words is not None else None
@@ -150,7 +184,8 @@ class PlannerBatch:
         live = ids >= 0
         par_slot = self.parent[p, :n].cpu().numpy()
         parent = np.where(par_slot >= 0, ids[np.clip(par_slot, 0, None)], -1).astype(np.int32)
-        return dict(ids=ids[live].copy(), x=self.x[p, :n].cpu().numpy()[live], y=self.y[p, :n].cpu().numpy()[live],
+        xy = self.xy[p, :n].cpu().numpy()
+        return dict(ids=ids[live].copy(), x=xy[live, 0].copy(), y=xy[live, 1].copy(),
                     parent=parent[live], cost=self.ecost[p, :n].cpu().numpy()[live],
                     nchild=self.nchild[p, :n].cpu().numpy()[live])
 

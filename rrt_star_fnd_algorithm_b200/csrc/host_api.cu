@@ -6,11 +6,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
 #include <vector>
 
 #include "../../include/rrtfnd.h"
+#include "grid.cuh"
 
 namespace {
 
@@ -24,9 +26,59 @@ struct DevBuf {
 
 }  // namespace
 
+// ---- obstacle grid builder (pure host code) --------------------------------------------------------------
+extern "C" int rrtfnd_obst_grid_build_host(const double* obst_host, int32_t M, double node_radius, double lo_x,
+                                           double hi_x, double lo_y, double hi_y, double cell,
+                                           rrtfnd_obst_grid_t* g, int32_t* seg_start_host, int32_t* seg_items_host,
+                                           int32_t* pt_start_host, int32_t* pt_items_host, int64_t* n_items_out) {
+    if (!g || M < 0 || (M > 0 && !obst_host) || !(hi_x > lo_x) || !(hi_y > lo_y) || !n_items_out) return RRTFND_E_BADARG;
+    memset(g, 0, sizeof *g);
+    n_items_out[0] = n_items_out[1] = 0;
+    if (M == 0) return 0;                                       // nx == 0: culling disabled
+    double S = fmax(fmax(fabs(lo_x), fabs(hi_x)), fmax(fabs(lo_y), fabs(hi_y)));
+    for (int j = 0; j < M; ++j)
+        for (int c = 0; c < 3; ++c) S = fmax(S, fabs(obst_host[3 * j + c]));
+    if (!(S < 1e100)) return RRTFND_E_BADARG;
+    const double slope_max = 256.0;
+    const double margin = rrtfnd::grid_seg_margin(S, slope_max);
+    const double w = hi_x - lo_x, h = hi_y - lo_y;
+    if (!(cell > 0.0)) cell = sqrt(w * h / (double)M);
+    cell = fmax(cell, fmax(w, h) / 512.0);
+    const int nx = (int)fmin(512.0, fmax(1.0, ceil(w / cell))), ny = (int)fmin(512.0, fmax(1.0, ceil(h / cell)));
+    g->x0 = lo_x; g->y0 = lo_y; g->inv_cell = 1.0 / cell;
+    g->slope_max = slope_max; g->coord_max = S; g->margin = margin; g->nx = nx; g->ny = ny;
+    const size_t ncells = (size_t)nx * ny;
+    std::vector<int32_t> cnt_s(ncells + 1, 0), cnt_p(ncells + 1, 0);
+    struct Box { int x0, x1, y0, y1; };
+    std::vector<Box> bs((size_t)M), bp((size_t)M);
+    for (int j = 0; j < M; ++j) {
+        const double ox = obst_host[3 * j], oy = obst_host[3 * j + 1], r = obst_host[3 * j + 2];
+        // segments: inflate by r + margin; points: by r + node_radius (Map.is_occupied_c); both with relative slack
+        const double Rs = (fabs(r) + margin) * 1.000000001, Rp = (fabs(r) + fabs(node_radius)) * 1.000000001;
+        bs[j] = Box{rrtfnd::grid_cell(ox - Rs, g->x0, g->inv_cell, nx), rrtfnd::grid_cell(ox + Rs, g->x0, g->inv_cell, nx),
+                    rrtfnd::grid_cell(oy - Rs, g->y0, g->inv_cell, ny), rrtfnd::grid_cell(oy + Rs, g->y0, g->inv_cell, ny)};
+        bp[j] = Box{rrtfnd::grid_cell(ox - Rp, g->x0, g->inv_cell, nx), rrtfnd::grid_cell(ox + Rp, g->x0, g->inv_cell, nx),
+                    rrtfnd::grid_cell(oy - Rp, g->y0, g->inv_cell, ny), rrtfnd::grid_cell(oy + Rp, g->y0, g->inv_cell, ny)};
+        for (int cy = bs[j].y0; cy <= bs[j].y1; ++cy) for (int cx = bs[j].x0; cx <= bs[j].x1; ++cx) ++cnt_s[(size_t)cy * nx + cx + 1];
+        for (int cy = bp[j].y0; cy <= bp[j].y1; ++cy) for (int cx = bp[j].x0; cx <= bp[j].x1; ++cx) ++cnt_p[(size_t)cy * nx + cx + 1];
+    }
+    for (size_t c = 0; c < ncells; ++c) { cnt_s[c + 1] += cnt_s[c]; cnt_p[c + 1] += cnt_p[c]; }
+    n_items_out[0] = cnt_s[ncells]; n_items_out[1] = cnt_p[ncells];
+    if (!seg_items_host) return 0;                              // sizing call
+    if (!seg_start_host || !pt_start_host || !pt_items_host) return RRTFND_E_BADARG;
+    memcpy(seg_start_host, cnt_s.data(), (ncells + 1) * sizeof(int32_t));
+    memcpy(pt_start_host, cnt_p.data(), (ncells + 1) * sizeof(int32_t));
+    std::vector<int32_t> fs(cnt_s.begin(), cnt_s.end() - 1), fp(cnt_p.begin(), cnt_p.end() - 1);
+    for (int j = 0; j < M; ++j) {                               // ascending obstacle index inside every cell
+        for (int cy = bs[j].y0; cy <= bs[j].y1; ++cy) for (int cx = bs[j].x0; cx <= bs[j].x1; ++cx) seg_items_host[fs[(size_t)cy * nx + cx]++] = j;
+        for (int cy = bp[j].y0; cy <= bp[j].y1; ++cy) for (int cx = bp[j].x0; cx <= bp[j].x1; ++cx) pt_items_host[fp[(size_t)cy * nx + cx]++] = j;
+    }
+    return 0;
+}
+
 extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const double* starts_goals_host,
                                 const uint64_t* seeds_host, const double* obst_host, const uint32_t* words_host,
-                                rrtfnd_planner_t* planners_host, double* x_host, double* y_host, double* ecost_host,
+                                rrtfnd_planner_t* planners_host, double* xy_host, double* ecost_host,
                                 int32_t* parent_host, int32_t* nchild_host, int32_t* id_host, int32_t* best_path_host,
                                 int32_t device) {
     if (!prm || P <= 0 || !starts_goals_host || !seeds_host || (prm->n_obst > 0 && !obst_host)) return RRTFND_E_BADARG;
@@ -52,10 +104,32 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         ob[4 * j] = ox; ob[4 * j + 1] = oy; ob[4 * j + 2] = r; ob[4 * j + 3] = t + y2;
     }
 
-    DevBuf d_pl, d_x, d_y, d_e, d_par, d_nc, d_id, d_fin, d_bp, d_ob, d_w;
+    // culling grid over the box that bounds xy_range and every start / goal
+    double lo_x = prm->x_lo, hi_x = prm->x_hi, lo_y = prm->y_lo, hi_y = prm->y_hi;
+    for (int p = 0; p < P; ++p) {
+        lo_x = fmin(lo_x, fmin(pl[p].start_x, pl[p].goal_x)); hi_x = fmax(hi_x, fmax(pl[p].start_x, pl[p].goal_x));
+        lo_y = fmin(lo_y, fmin(pl[p].start_y, pl[p].goal_y)); hi_y = fmax(hi_y, fmax(pl[p].start_y, pl[p].goal_y));
+    }
+    rrtfnd_obst_grid_t grid;
+    memset(&grid, 0, sizeof grid);
+    std::vector<int32_t> g_ss, g_si, g_ps, g_pi;
+    if (M > 0 && hi_x > lo_x && hi_y > lo_y) {
+        int64_t cnt[2];
+        int grc = rrtfnd_obst_grid_build_host(obst_host, (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, 0, 0, 0, 0, cnt);
+        if (grc) return grc;
+        const size_t ncells = (size_t)grid.nx * grid.ny;
+        g_ss.resize(ncells + 1); g_ps.resize(ncells + 1); g_si.resize((size_t)cnt[0] + 1); g_pi.resize((size_t)cnt[1] + 1);
+        grc = rrtfnd_obst_grid_build_host(obst_host, (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, g_ss.data(),
+                                          g_si.data(), g_ps.data(), g_pi.data(), cnt);
+        if (grc) return grc;
+    }
+
+    DevBuf d_pl, d_xy, d_e, d_par, d_nc, d_id, d_fl, d_fin, d_bp, d_ob, d_w, d_gss, d_gsi, d_gps, d_gpi;
     CK(d_pl.alloc((size_t)P * sizeof(rrtfnd_planner_t)));
-    CK(d_x.alloc(n * 8)); CK(d_y.alloc(n * 8)); CK(d_e.alloc(n * 8));
-    CK(d_par.alloc(n * 4)); CK(d_nc.alloc(n * 4)); CK(d_id.alloc(n * 4));
+    CK(d_xy.alloc(n * 16)); CK(d_e.alloc(n * 8));
+    CK(d_par.alloc(n * 4)); CK(d_nc.alloc(n * 4)); CK(d_id.alloc(n * 4)); CK(d_fl.alloc(n));
+    CK(d_gss.alloc(g_ss.size() * 4)); CK(d_gsi.alloc(g_si.size() * 4));
+    CK(d_gps.alloc(g_ps.size() * 4)); CK(d_gpi.alloc(g_pi.size() * 4));
     CK(d_fin.alloc((size_t)P * prm->finish_cap * 4)); CK(d_bp.alloc((size_t)P * prm->path_cap * 4));
     CK(d_ob.alloc(ob.size() * 8));
     cudaStream_t st;
@@ -64,6 +138,14 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
     do {
         if ((rc = (int)cudaMemcpyAsync(d_pl.p, pl.data(), (size_t)P * sizeof(rrtfnd_planner_t), cudaMemcpyHostToDevice, st))) break;
         if ((rc = (int)cudaMemcpyAsync(d_ob.p, ob.data(), ob.size() * 8, cudaMemcpyHostToDevice, st))) break;
+        if (grid.nx > 0) {
+            if ((rc = (int)cudaMemcpyAsync(d_gss.p, g_ss.data(), g_ss.size() * 4, cudaMemcpyHostToDevice, st))) break;
+            if ((rc = (int)cudaMemcpyAsync(d_gsi.p, g_si.data(), g_si.size() * 4, cudaMemcpyHostToDevice, st))) break;
+            if ((rc = (int)cudaMemcpyAsync(d_gps.p, g_ps.data(), g_ps.size() * 4, cudaMemcpyHostToDevice, st))) break;
+            if ((rc = (int)cudaMemcpyAsync(d_gpi.p, g_pi.data(), g_pi.size() * 4, cudaMemcpyHostToDevice, st))) break;
+            grid.seg_start = (const int32_t*)d_gss.p; grid.seg_items = (const int32_t*)d_gsi.p;
+            grid.pt_start = (const int32_t*)d_gps.p; grid.pt_items = (const int32_t*)d_gpi.p;
+        }
         if (prm->stream_mode == RRTFND_STREAM_WORDS) {
             const size_t wb = (size_t)P * (size_t)prm->words_per_planner * 4;
             if ((rc = (int)d_w.alloc(wb))) break;
@@ -72,8 +154,9 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         rrtfnd_batch_t bt;
         memset(&bt, 0, sizeof bt);
         bt.n_planners = P; bt.planners = (rrtfnd_planner_t*)d_pl.p;
-        bt.x = (double*)d_x.p; bt.y = (double*)d_y.p; bt.ecost = (double*)d_e.p;
-        bt.parent = (int32_t*)d_par.p; bt.nchild = (int32_t*)d_nc.p; bt.id = (int32_t*)d_id.p;
+        bt.xy = (double*)d_xy.p; bt.ecost = (double*)d_e.p;
+        bt.parent = (int32_t*)d_par.p; bt.nchild = (int32_t*)d_nc.p; bt.id = (int32_t*)d_id.p; bt.nflags = (uint8_t*)d_fl.p;
+        bt.grid = grid;
         bt.finish = (int32_t*)d_fin.p; bt.best_path = (int32_t*)d_bp.p; bt.obst = (const double*)d_ob.p;
         bt.words = (const uint32_t*)d_w.p; bt.trace = nullptr;
         rrtfnd_params_t q = *prm;
@@ -81,8 +164,7 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         if ((rc = rrtfnd_init_batch(&q, &bt, st))) break;
         if ((rc = rrtfnd_plan_batch(&q, &bt, st))) break;
         if (planners_host && (rc = (int)cudaMemcpyAsync(planners_host, d_pl.p, (size_t)P * sizeof(rrtfnd_planner_t), cudaMemcpyDeviceToHost, st))) break;
-        if (x_host && (rc = (int)cudaMemcpyAsync(x_host, d_x.p, n * 8, cudaMemcpyDeviceToHost, st))) break;
-        if (y_host && (rc = (int)cudaMemcpyAsync(y_host, d_y.p, n * 8, cudaMemcpyDeviceToHost, st))) break;
+        if (xy_host && (rc = (int)cudaMemcpyAsync(xy_host, d_xy.p, n * 16, cudaMemcpyDeviceToHost, st))) break;
         if (ecost_host && (rc = (int)cudaMemcpyAsync(ecost_host, d_e.p, n * 8, cudaMemcpyDeviceToHost, st))) break;
         if (parent_host && (rc = (int)cudaMemcpyAsync(parent_host, d_par.p, n * 4, cudaMemcpyDeviceToHost, st))) break;
         if (nchild_host && (rc = (int)cudaMemcpyAsync(nchild_host, d_nc.p, n * 4, cudaMemcpyDeviceToHost, st))) break;

@@ -12,6 +12,7 @@
 
 #include "../../include/rrtfnd.h"
 #include "arith.cuh"
+#include "cull.cuh"
 
 namespace rrtfnd {
 
@@ -90,6 +91,34 @@ __global__ void __launch_bounds__(256) points_occupied_kernel(const double* __re
     }
 }
 
+// The culled forms used inside the fused planner, as stand-alone kernels: one LANE per edge / one warp per point.
+__global__ void __launch_bounds__(128) edges_vs_circles_grid_kernel(const double* __restrict__ p1x, const double* __restrict__ p1y,
+                                                                    const double* __restrict__ p2x, const double* __restrict__ p2y,
+                                                                    long long n_edges, const double* __restrict__ obst, int M,
+                                                                    const rrtfnd_obst_grid_t grid, uint8_t* __restrict__ out_hit) {
+    const Obst ob = make_obst(obst, M, grid);
+    long long tests = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
+        const double ay = p1y[e], by = p2y[e];
+        const Seg sg = make_seg(p1x[e], ay, p2x[e], by);
+        out_hit[e] = seg_blocked_lane(ob, sg, ay, by, tests) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(128) points_occupied_grid_kernel(const double* __restrict__ px, const double* __restrict__ py,
+                                                                   long long n_points, const double* __restrict__ obst, int M,
+                                                                   const rrtfnd_obst_grid_t grid, double node_radius,
+                                                                   uint8_t* __restrict__ out) {
+    const Obst ob = make_obst(obst, M, grid);
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long tests = 0;
+    for (long long e = warp0; e < n_points; e += nwarps) {
+        const bool occ = point_occupied_warp(ob, px[e], py[e], node_radius, lane, tests);
+        if (lane == 0) out[e] = occ ? 1 : 0;
+    }
+}
+
 template <int NT>
 __device__ __forceinline__ void block_argmin(double& bd, int& bs, double* red_d, int* red_s) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,7 +138,7 @@ __device__ __forceinline__ void block_argmin(double& bd, int& bs, double* red_d,
 }
 
 // One CTA per planner: repeated (d2, slot) argmin passes over x[], y[] (double2-vectorised, coalesced)
-// until the candidate's segment to q is collision free.
+// until the candidate's segment to q is collision free. Tests every circle (the un-culled cross-check of planner.cu).
 template <int NT>
 __global__ void __launch_bounds__(NT) nearest_visible_kernel(const rrtfnd_batch_t bt, int C, const double* __restrict__ q,
                                                              int M, int* __restrict__ out_slot, int* __restrict__ out_rounds) {
@@ -117,39 +146,26 @@ __global__ void __launch_bounds__(NT) nearest_visible_kernel(const rrtfnd_batch_
     __shared__ double red_d[32];
     __shared__ int red_s[32];
     const int p = blockIdx.x, tid = threadIdx.x;
-    const double* __restrict__ X = bt.x + (size_t)p * C;
-    const double* __restrict__ Y = bt.y + (size_t)p * C;
+    const double2* __restrict__ XY = reinterpret_cast<const double2*>(bt.xy) + (size_t)p * C;
     const int n_slots = bt.planners[p].n_slots, n_live = bt.planners[p].n_live;
     const double qx = q[2 * p], qy = q[2 * p + 1];
     stage_obstacles(bt.obst, 0, min(M, kObstTile), ox, oy, orr, oK);   // M <= kObstTile enforced by the host wrapper
     __syncthreads();
     double prev_d = -1.0; int prev_s = -1, result = -1, rounds = 0;
-    const bool aligned = ((((size_t)p * C) & 1) == 0);
     for (int round = 0; round < n_live; ++round) {
         double bd = CUDART_INF; int bs = 0x7fffffff; bool exact = false;
-        auto visit = [&](double x, double y, int s) {
-            const double d = dist2(x, y, qx, qy);
-            if (x == qx && y == qy) exact = true;
+        for (int s = tid; s < n_slots; s += NT) {                        // one coalesced 16-byte load per node
+            const double2 v = XY[s];
+            const double d = dist2(v.x, v.y, qx, qy);
+            if (v.x == qx && v.y == qy) exact = true;
             if ((d > prev_d || (d == prev_d && s > prev_s)) && d < bd) { bd = d; bs = s; }
-        };
-        if (aligned) {
-            const int n2 = n_slots >> 1;
-            const double2* X2 = reinterpret_cast<const double2*>(X);
-            const double2* Y2 = reinterpret_cast<const double2*>(Y);
-            for (int i = tid; i < n2; i += NT) {
-                const double2 vx = X2[i], vy = Y2[i];
-                visit(vx.x, vy.x, 2 * i);
-                visit(vx.y, vy.y, 2 * i + 1);
-            }
-            if ((n_slots & 1) && tid == 0) visit(X[n_slots - 1], Y[n_slots - 1], n_slots - 1);
-        } else {
-            for (int s = tid; s < n_slots; s += NT) visit(X[s], Y[s], s);
         }
         if (round == 0 && __syncthreads_or(exact)) { result = -2; break; }
         block_argmin<NT>(bd, bs, red_d, red_s);
         if (bs == 0x7fffffff) break;
         ++rounds;
-        const Seg sg = make_seg(qx, qy, X[bs], Y[bs]);
+        const double2 nb = XY[bs];
+        const Seg sg = make_seg(qx, qy, nb.x, nb.y);
         bool hit = false;
         for (int j = tid; j < M; j += NT) hit |= seg_hits_circle(sg, ox[j], oy[j], orr[j], oK[j]);
         if (!__syncthreads_or(hit)) { result = bs; break; }
@@ -165,8 +181,7 @@ __global__ void __launch_bounds__(NT) near_set_kernel(const rrtfnd_batch_t bt, i
     __shared__ int warp_cnt[NT / 32];
     __shared__ int running;
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* __restrict__ X = bt.x + (size_t)p * C;
-    const double* __restrict__ Y = bt.y + (size_t)p * C;
+    const double2* __restrict__ XY = reinterpret_cast<const double2*>(bt.xy) + (size_t)p * C;
     const int n_slots = bt.planners[p].n_slots;
     const double qx = q[2 * p], qy = q[2 * p + 1];
     const double r2 = dmul(radius, radius);
@@ -176,7 +191,7 @@ __global__ void __launch_bounds__(NT) near_set_kernel(const rrtfnd_batch_t bt, i
     for (int base = 0; base < n_slots; base += NT) {
         const int s = base + tid;
         bool in = false;
-        if (s < n_slots) in = dist2(X[s], Y[s], qx, qy) <= r2;
+        if (s < n_slots) { const double2 v = XY[s]; in = dist2(v.x, v.y, qx, qy) <= r2; }
         const unsigned b = __ballot_sync(kFullMask, in);
         if (lane == 0) warp_cnt[warp] = __popc(b);
         __syncthreads();
@@ -231,7 +246,7 @@ extern "C" const char* rrtfnd_status_string(int st) {
         case RRTFND_ST_NEED_WORDS: return "need-words";
         case RRTFND_ST_ATTEMPT_CAP: return "attempt-cap";
         case RRTFND_ST_CAPACITY: return "node capacity exhausted";
-        case RRTFND_ST_NEAR_CAP: return "near-set larger than near_cap";
+        case RRTFND_ST_NEAR_CAP: return "more nodes rewired in one iteration than near_cap";
         case RRTFND_ST_FINISH_CAP: return "finish list full";
         case RRTFND_ST_PATH_CAP: return "best path longer than path_cap";
         case RRTFND_ST_DUPLICATE: return "steered point coincides with an existing vertex";
@@ -254,6 +269,36 @@ extern "C" int rrtfnd_edges_vs_circles(const double* p1x, const double* p1y, con
     const long long cap = (long long)sm_count() * 8;     // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     edges_vs_circles_kernel<<<(int)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(p1x, p1y, p2x, p2y, n_edges, obst, n_obst, out_hit);
+    return (int)cudaGetLastError();
+}
+
+static int check_grid(const rrtfnd_obst_grid_t* g) {
+    if (!g) return RRTFND_E_BADARG;
+    if (g->nx > 0 && (g->ny <= 0 || !g->seg_start || !g->seg_items || !g->pt_start || !g->pt_items)) return RRTFND_E_BADARG;
+    return 0;
+}
+
+extern "C" int rrtfnd_edges_vs_circles_grid(const double* p1x, const double* p1y, const double* p2x, const double* p2y,
+                                            int64_t n_edges, const double* obst, int32_t n_obst,
+                                            const rrtfnd_obst_grid_t* grid, uint8_t* out_hit, void* stream) {
+    if (n_edges < 0 || n_obst < 0 || check_grid(grid) || (n_edges > 0 && (!p1x || !p1y || !p2x || !p2y || !out_hit))) return RRTFND_E_BADARG;
+    if (n_edges == 0) return 0;
+    long long blocks = (n_edges + 127) / 128;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    edges_vs_circles_grid_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(p1x, p1y, p2x, p2y, n_edges, obst, n_obst, *grid, out_hit);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rrtfnd_points_occupied_grid(const double* px, const double* py, int64_t n_points, const double* obst,
+                                           int32_t n_obst, const rrtfnd_obst_grid_t* grid, double node_radius,
+                                           uint8_t* out_occ, void* stream) {
+    if (n_points < 0 || n_obst < 0 || check_grid(grid) || (n_points > 0 && (!px || !py || !out_occ))) return RRTFND_E_BADARG;
+    if (n_points == 0) return 0;
+    long long blocks = (n_points + 3) / 4;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    points_occupied_grid_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(px, py, n_points, obst, n_obst, *grid, node_radius, out_occ);
     return (int)cudaGetLastError();
 }
 

@@ -1,81 +1,69 @@
-// planner.cu — fused persistent planner kernel: one CTA grows one tree from sample to best-path bookkeeping.
+// planner.cu — fused persistent planner kernel: one WARP grows one tree from sample to best-path bookkeeping.
 //
 // Replaces the Python loops of RRT / RRT_star / RRT_star_FN (src/algorithm.py:54-265) together with
 // new_node (:36-51), nearest_node_kdtree (:666-699), steer (:731-746), choose_parent_kdtree (:822-852),
 // rewire_kdtree (:882-910), forced_removal (:800-819), check_solution (:749-760), find_path (:778-797)
 // and the Graph bookkeeping of src/graph.py:34-87.
 //
-// Layout. Node coordinates of the planner live in shared memory (x[], y[] fp64, the two arrays every
-// nearest / near-set scan streams) and are mirrored to HBM on insert; parent[], ecost[], nchild[], id[]
-// stay in HBM/L1 (touched only by chain walks and commits). The obstacle table is staged once per CTA as
-// SoA in shared memory. Slots are kept in ascending-id order: inserts append, FN removals leave a
-// tombstone (x = y = NaN so every scan predicate is false, nchild = id = -1) and a stable compaction runs
-// only when the slot array is full.
+// Execution model. Planners are independent and strictly sequential inside (iteration i+1 needs the tree of
+// iteration i), and after obstacle culling one iteration is a few thousand fp64 operations plus several
+// latency-bound pointer chases. So a planner gets one warp, not a CTA: no block barriers, reductions are
+// warp votes / redux, warp-uniform values live in registers of every lane, and the SM hides one planner's
+// latency (parent-chain walks, div / sqrt chains) behind the other 16-64 planners resident on it. A batch larger
+// than the resident-warp count streams through the hardware block scheduler.
 //
-// The grid has one CTA per planner; the hardware block scheduler is the work queue (planners are
-// independent and never communicate), so a batch larger than the resident-CTA count streams through.
+// Layout (HBM, per planner, fixed capacity, slots in ascending-id order): xy[] (double2, the array every
+// nearest / near-set scan streams with one coalesced 16-byte load per lane), ecost[], parent[], nchild[], id[],
+// nflags[]. Inserts append; FN removals leave a tombstone (x = y = NaN so every scan predicate is false,
+// nchild = id = -1) and a stable in-place compaction runs only when the slot array is full. The obstacle table
+// and its culling grid (grid.cuh) are shared by all planners and stay L1 resident.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/rrtfnd.h"
 #include "arith.cuh"
+#include "cull.cuh"
+#include "grid.cuh"
 #include "rng.cuh"
 
 namespace rrtfnd {
 
 constexpr int kReserveWords = 64;   // must equal RESERVE_WORDS in _structs.py / ORC_RESERVE_WORDS
-constexpr unsigned kFull = 0xffffffffu;
-
-struct Ctl {
-    double qx, qy;          // current sample
-    double px, py;          // new node position
-    double e0;              // cost_new_near = calc_distance(q_new, q_near)
-    double cost_new;        // Graph.get_cost(id_new)
-    double best_cost;
-    double gx, gy;
-    long long attempts, n_edge_checks, n_edge_checks_ref, n_circle_tests, n_scan_nodes, n_chain_hops;
-    int n_slots, n_live, last_id, iter, root_slot, n_finish, best_len, status;
-    int n_rewired, n_removed, solution_found, n_compactions;
-    int best_leaf_slot;     // slot of best_path["path"][0], -1 if none
-    int go, need_compact, near_slot, new_slot, k, reached, rewired_iter, dup, pick;
-    int cp_parent_id;
-    double cp_cost;
-    int removed_id;
-};
-
-struct SmemPlan {
-    size_t off_x, off_y, off_obst, off_bm, off_cslot, off_cdpl, off_ccost, off_chit, off_red_d, off_red_s,
-        off_map, off_ctl, total;
-    int bm_words;
-};
+constexpr int kStage = 64;          // near-set slots staged per warp between chunk flushes
+constexpr int kIntMax = 0x7fffffff;
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline int bitmap_words(const rrtfnd_params_t& prm) { return prm.capacity / 32 + 1; }
 
-__host__ __device__ inline SmemPlan plan_smem(const rrtfnd_params_t& prm, int nt, bool tree_in_smem, bool obst_in_smem = true) {
-    SmemPlan s;
-    size_t o = 0;
-    const size_t C = (size_t)prm.capacity;
-    s.off_x = o; o += tree_in_smem ? align_up(C * 8, 16) : 0;
-    s.off_y = o; o += tree_in_smem ? align_up(C * 8, 16) : 0;
-    s.off_obst = o; o += obst_in_smem ? align_up((size_t)prm.n_obst * 8, 16) * 4 : 0;   // ox | oy | r | K
-    s.bm_words = (int)((C + nt) / 32 + 1);
-    s.off_bm = o; o += align_up((size_t)s.bm_words * 4, 16);
-    s.off_cdpl = o; o += align_up((size_t)prm.near_cap * 8, 16);
-    s.off_ccost = o; o += align_up((size_t)prm.near_cap * 8, 16);
-    s.off_cslot = o; o += align_up((size_t)prm.near_cap * 4, 16);
-    s.off_chit = o; o += align_up((size_t)prm.near_cap * 4, 16);
-    s.off_red_d = o; o += align_up((size_t)2 * 32 * 8, 16);
-    s.off_red_s = o; o += align_up((size_t)2 * 32 * 4, 16);
-    s.off_map = o; o += (prm.mode == RRTFND_MODE_FN) ? align_up(C * 4, 16) : 0;
-    s.off_ctl = o; o += align_up(sizeof(Ctl), 16);
-    s.total = o;
-    return s;
+// shared memory of one warp: stage[kStage] | rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | (FN only) live bitmap + its prefix counts
+__host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm) {
+    size_t o = kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
+    if (prm.mode == RRTFND_MODE_FN) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
+    return o;
+}
+
+// ------------------------------------------------------------------------------------ warp helpers
+
+// (value, index) argmin over the warp for NON-NEGATIVE doubles (their bit patterns order like unsigned integers),
+// lowest index on equal values. Three redux instructions instead of a five-step shuffle tree.
+__device__ __forceinline__ void warp_argmin(double& bd, int& bs) {
+    const unsigned hi = (unsigned)__double2hiint(bd), lo = (unsigned)__double2loint(bd);
+    const unsigned mh = __reduce_min_sync(kFull, hi);
+    const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
+    bs = __reduce_min_sync(kFull, (hi == mh && lo == ml) ? bs : kIntMax);
+    bd = __hiloint2double((int)mh, (int)ml);
+}
+
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
 }
 
 // Leaf -> root sequential sum of edge costs (Graph.get_cost, src/graph.py:41-46). `acc` is the running
 // value to start from (0 for get_cost; the new node's own edge cost when walking from its parent).
-__device__ __forceinline__ double chain_walk(const int32_t* __restrict__ parent, const double* __restrict__ ecost,
-                                             int slot, double acc, long long& hops) {
+__device__ __forceinline__ double chain_walk(const int32_t* parent, const double* ecost, int slot, double acc,
+                                             long long& hops) {
     int n = slot;
     int p = parent[n];
     while (p >= 0) {
@@ -87,573 +75,504 @@ __device__ __forceinline__ double chain_walk(const int32_t* __restrict__ parent,
     return acc;
 }
 
-// kTreeInSmem: x[]/y[] of the planner staged in shared memory (else streamed from HBM/L2 through L1).
-// kObstInSmem: obstacle table staged per CTA as SoA (else read as 32-byte rows through L1; the table is shared
-//              by every planner, so with many small CTAs per SM one L1-resident copy serves them all).
-template <int NT, bool kTreeInSmem, bool kObstInSmem>
-__global__ void __launch_bounds__(NT) plan_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) {
+// find_path's cost (src/algorithm.py:787-792): like get_cost but the walk ends at the planner's root slot
+__device__ __forceinline__ double path_cost(const int32_t* parent, const double* ecost, int from, int root, long long& hops) {
+    double cost = 0.0;
+    int n = from;
+    while (n != root && n >= 0) { cost = dadd(cost, ecost[n]); n = parent[n]; ++hops; }
+    return cost;
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NW = NT / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int p = blockIdx.x;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int p = blockIdx.x * WPB + wib;
+    if (p >= bt.n_planners) return;                       // whole warp leaves; warps never synchronise with each other
     const int C = prm.capacity;
-    const int M = prm.n_obst;
-    const SmemPlan sp = plan_smem(prm, NT, kTreeInSmem, kObstInSmem);
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     // per-planner global arrays
-    double* __restrict__ GX = bt.x + (size_t)p * C;
-    double* __restrict__ GY = bt.y + (size_t)p * C;
-    double* __restrict__ ECOST = bt.ecost + (size_t)p * C;
-    int32_t* __restrict__ PARENT = bt.parent + (size_t)p * C;
-    int32_t* __restrict__ NCHILD = bt.nchild + (size_t)p * C;
-    int32_t* __restrict__ ID = bt.id + (size_t)p * C;
-    int32_t* __restrict__ FINISH = bt.finish + (size_t)p * prm.finish_cap;
-    int32_t* __restrict__ BPATH = bt.best_path + (size_t)p * prm.path_cap;
-    rrtfnd_planner_t* __restrict__ PL = bt.planners + p;
-    rrtfnd_trace_t* __restrict__ TRACE = bt.trace ? bt.trace + (size_t)p * prm.trace_cap : nullptr;
+    double2* XY = reinterpret_cast<double2*>(bt.xy) + (size_t)p * C;
+    double* ECOST = bt.ecost + (size_t)p * C;
+    int32_t* PARENT = bt.parent + (size_t)p * C;
+    int32_t* NCHILD = bt.nchild + (size_t)p * C;
+    int32_t* ID = bt.id + (size_t)p * C;
+    uint8_t* NFLAG = bt.nflags + (size_t)p * C;
+    int32_t* FINISH = bt.finish + (size_t)p * prm.finish_cap;
+    int32_t* BPATH = bt.best_path + (size_t)p * prm.path_cap;
+    rrtfnd_planner_t* PL = bt.planners + p;
+    rrtfnd_trace_t* TRACE = bt.trace ? bt.trace + (size_t)p * prm.trace_cap : nullptr;
 
-    double* sx = kTreeInSmem ? reinterpret_cast<double*>(smem + sp.off_x) : GX;
-    double* sy = kTreeInSmem ? reinterpret_cast<double*>(smem + sp.off_y) : GY;
-    const size_t ostride = align_up((size_t)M * 8, 16) / 8;
-    double* so_x = reinterpret_cast<double*>(smem + sp.off_obst);
-    double* so_y = so_x + ostride;
-    double* so_r = so_y + ostride;
-    double* so_K = so_r + ostride;
-    const double2* __restrict__ gob = reinterpret_cast<const double2*>(bt.obst);
-    auto load_obst = [&](int j, double& ox, double& oy, double& orad, double& oK) {
-        if (kObstInSmem) { ox = so_x[j]; oy = so_y[j]; orad = so_r[j]; oK = so_K[j]; }
-        else { const double2 a = __ldg(gob + 2 * j), b = __ldg(gob + 2 * j + 1); ox = a.x; oy = a.y; orad = b.x; oK = b.y; }
-    };
-    uint32_t* bm = reinterpret_cast<uint32_t*>(smem + sp.off_bm);
-    int* cslot = reinterpret_cast<int*>(smem + sp.off_cslot);
-    double* cdpl = reinterpret_cast<double*>(smem + sp.off_cdpl);
-    double* ccost = reinterpret_cast<double*>(smem + sp.off_ccost);
-    int* chit = reinterpret_cast<int*>(smem + sp.off_chit);
-    double* red_d = reinterpret_cast<double*>(smem + sp.off_red_d);
-    int* red_s = reinterpret_cast<int*>(smem + sp.off_red_s);
-    int* smap = reinterpret_cast<int*>(smem + sp.off_map);
-    Ctl& c = *reinterpret_cast<Ctl*>(smem + sp.off_ctl);
+    // per-warp shared memory
+    unsigned char* ws = smem + (size_t)wib * warp_smem_bytes(prm);
+    int* stage = reinterpret_cast<int*>(ws);
+    int* rwlist = stage + kStage;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(ws + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16));
+    uint32_t* pre = bm + align_up((size_t)bitmap_words(prm) * 4, 16) / 4;
 
-    // ---- load planner state
-    WordSrc rng;  // meaningful in thread 0 only
-    if (tid == 0) {
-        c.gx = PL->goal_x; c.gy = PL->goal_y;
-        c.best_cost = PL->best_cost;
-        c.attempts = PL->attempts; c.n_edge_checks = PL->n_edge_checks; c.n_edge_checks_ref = PL->n_edge_checks_ref;
-        c.n_circle_tests = PL->n_circle_tests; c.n_scan_nodes = PL->n_scan_nodes; c.n_chain_hops = PL->n_chain_hops;
-        c.n_slots = PL->n_slots; c.n_live = PL->n_live; c.last_id = PL->last_id; c.iter = PL->iter;
-        c.root_slot = PL->root_slot; c.n_finish = PL->n_finish; c.best_len = PL->best_len;
-        c.status = RRTFND_ST_RUNNING;
-        c.n_rewired = PL->n_rewired; c.n_removed = PL->n_removed; c.solution_found = PL->solution_found;
-        c.n_compactions = PL->n_compactions;
-        c.best_leaf_slot = -1;
-        rng.mode = prm.stream_mode;
-        rng.words = bt.words ? bt.words + (size_t)p * prm.words_per_planner : nullptr;
-        rng.n_words = prm.words_per_planner;
-        rng.seed = PL->seed; rng.stream = PL->stream_id; rng.cursor = PL->cursor;
-        rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0;
-    }
-    if (kObstInSmem) {
-        for (int j = tid; j < M; j += NT) {
-            so_x[j] = bt.obst[4 * j + 0]; so_y[j] = bt.obst[4 * j + 1];
-            so_r[j] = bt.obst[4 * j + 2]; so_K[j] = bt.obst[4 * j + 3];
-        }
-    }
-    __syncthreads();
-    if (kTreeInSmem) {
-        for (int s = tid; s < c.n_slots; s += NT) { sx[s] = GX[s]; sy[s] = GY[s]; }
-    }
-    if (tid == 0 && c.best_len > 0) {
-        // slot of the cached best path's leaf (ids ascend with slots: binary search)
+    const Obst ob = make_obst(bt.obst, prm.n_obst, bt.grid);
+
+    // ---- planner state: warp-uniform, replicated in the registers of every lane
+    const double gx = PL->goal_x, gy = PL->goal_y;
+    double best_cost = PL->best_cost;
+    long long attempts = PL->attempts, n_edge_checks = PL->n_edge_checks, n_edge_checks_ref = PL->n_edge_checks_ref;
+    long long n_scan_nodes = PL->n_scan_nodes;
+    int n_slots = PL->n_slots, n_live = PL->n_live, last_id = PL->last_id, iter = PL->iter, root_slot = PL->root_slot;
+    int n_finish = PL->n_finish, best_len = PL->best_len, status = RRTFND_ST_RUNNING;
+    int n_rewired = PL->n_rewired, n_removed = PL->n_removed, solution_found = PL->solution_found;
+    int n_compactions = PL->n_compactions;
+    long long my_hops = 0, my_tests = 0;     // per-lane counters, summed at the end
+
+    WordSrc rng;                              // identical in every lane
+    rng.mode = prm.stream_mode;
+    rng.words = bt.words ? bt.words + (size_t)p * prm.words_per_planner : nullptr;
+    rng.n_words = prm.words_per_planner;
+    rng.seed = PL->seed; rng.stream = PL->stream_id; rng.cursor = PL->cursor;
+    rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0;
+
+    // slot of the cached best path's leaf (ids ascend with slots: binary search around tombstones)
+    int best_leaf_slot = -1;
+    if (best_len > 0) {
         const int leaf_id = BPATH[0];
-        int lo = 0, hi = c.n_slots - 1, found = -1;
-        while (lo <= hi) {  // tombstones carry id -1: fall back to a linear probe around them
+        int lo = 0, hi = n_slots - 1;
+        while (lo <= hi) {
             const int mid = (lo + hi) >> 1;
             int m2 = mid;
             while (m2 <= hi && ID[m2] < 0) ++m2;
             if (m2 > hi) { hi = mid - 1; continue; }
-            if (ID[m2] == leaf_id) { found = m2; break; }
-            if (ID[m2] < leaf_id) lo = m2 + 1; else hi = mid - 1;
+            const int v = ID[m2];
+            if (v == leaf_id) { best_leaf_slot = m2; break; }
+            if (v < leaf_id) lo = m2 + 1; else hi = mid - 1;
         }
-        c.best_leaf_slot = found;
     }
-    __syncthreads();
+    // childless live nodes (forced_removal draws among them); kept incrementally afterwards
+    int n_childless = 0;
+    if (prm.mode == RRTFND_MODE_FN) {
+        for (int base = 0; base < n_slots; base += 32) {
+            const int s = base + lane;
+            n_childless += __popc(__ballot_sync(kFull, s < n_slots && NCHILD[s] == 0));
+        }
+    }
 
-    long long my_hops = 0, my_tests = 0;   // per-thread counters, merged at the end
     const double r2 = dmul(prm.radius, prm.radius);
     const double goal_thresh = dmul(2.0, prm.node_radius);
+    const bool eval_cp = (prm.flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
+    const bool commit_cp = (prm.flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) != 0;
+    const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
 
     for (;;) {
-        // ================================================================ A. attempt header (thread 0)
-        if (tid == 0) {
-            c.go = 1; c.need_compact = 0;
-            if (c.iter >= prm.iter_num) { c.status = RRTFND_ST_DONE; c.go = 0; }
-            else if (prm.max_attempts > 0 && c.attempts >= prm.max_attempts) { c.status = RRTFND_ST_ATTEMPT_CAP; c.go = 0; }
-            else if (prm.stream_mode == RRTFND_STREAM_WORDS &&
-                     (long long)rng.cursor + kReserveWords > prm.words_per_planner) { c.status = RRTFND_ST_NEED_WORDS; c.go = 0; }
-            else if (c.n_slots >= C) {
-                if (c.n_live < c.n_slots) c.need_compact = 1;
-                else { c.status = RRTFND_ST_CAPACITY; c.go = 0; }
-            }
-            if (c.go) {
-                ++c.attempts;
-                // Graph.random_node (src/graph.py:96-98)
-                if (next_random(rng) < prm.bias) { c.qx = c.gx; c.qy = c.gy; }
-                else {
-                    c.qx = dadd(prm.x_lo, dmul(dsub(prm.x_hi, prm.x_lo), next_random(rng)));
-                    c.qy = dadd(prm.y_lo, dmul(dsub(prm.y_hi, prm.y_lo), next_random(rng)));
-                }
-            }
+        // ================================================================ A. attempt header
+        if (iter >= prm.iter_num) { status = RRTFND_ST_DONE; break; }
+        if (prm.max_attempts > 0 && attempts >= prm.max_attempts) { status = RRTFND_ST_ATTEMPT_CAP; break; }
+        if (prm.stream_mode == RRTFND_STREAM_WORDS && (long long)rng.cursor + kReserveWords > prm.words_per_planner) {
+            status = RRTFND_ST_NEED_WORDS; break;
         }
-        __syncthreads();
-        if (!c.go) break;
-
-        // ================================================================ A'. stable compaction (FN, rare)
-        if (c.need_compact) {
-            const int n_slots = c.n_slots;
-            if (warp == 0) {
-                int running = 0;
-                for (int base = 0; base < n_slots; base += 32) {
-                    const int s = base + lane;
-                    const bool alive = s < n_slots && ID[s] >= 0;
-                    const unsigned b = __ballot_sync(kFull, alive);
-                    if (s < n_slots) smap[s] = alive ? running + __popc(b & ((1u << lane) - 1u)) : -1;
-                    running += __popc(b);
-                }
+        if (n_slots >= C) {
+            if (n_live >= n_slots) { status = RRTFND_ST_CAPACITY; break; }
+            // ---- A'. stable in-place compaction (FN only; rare)
+            const int nwords = (n_slots + 31) >> 5;
+            for (int w = 0; w < nwords; ++w) {
+                const int s = w * 32 + lane;
+                const unsigned b = __ballot_sync(kFull, s < n_slots && ID[s] >= 0);
+                if (lane == 0) bm[w] = b;
             }
-            __syncthreads();
-            for (int base = 0; base < n_slots; base += NT) {
-                const int s = base + tid;
-                const bool alive = s < n_slots && smap[s] >= 0;
-                double vx = 0, vy = 0, ve = 0; int vp = -1, vn = 0, vi = -1;
+            __syncwarp();
+            if (lane == 0) { int run = 0; for (int w = 0; w < nwords; ++w) { pre[w] = run; run += __popc(bm[w]); } }
+            __syncwarp();
+            auto rank = [&](int s) { return (int)pre[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31)) - 1u)); };
+            for (int base = 0; base < n_slots; base += 32) {
+                const int s = base + lane;
+                const bool alive = s < n_slots && ((bm[s >> 5] >> (s & 31)) & 1u);
+                double2 v = nan2; double ve = 0; int vp = -1, vn = 0, vi = -1; uint8_t vf = 0;
                 if (alive) {
-                    vx = sx[s]; vy = sy[s]; ve = ECOST[s]; vp = PARENT[s]; vn = NCHILD[s]; vi = ID[s];
-                    if (vp >= 0) vp = smap[vp];
+                    v = XY[s]; ve = ECOST[s]; vp = PARENT[s]; vn = NCHILD[s]; vi = ID[s]; vf = NFLAG[s];
+                    if (vp >= 0) vp = rank(vp);
                 }
-                __syncthreads();
+                __syncwarp();   // the whole row is read before any of it is overwritten (destinations are <= sources)
                 if (alive) {
-                    const int d = smap[s];
-                    sx[d] = vx; sy[d] = vy;
-                    if (kTreeInSmem) { GX[d] = vx; GY[d] = vy; }
-                    ECOST[d] = ve; PARENT[d] = vp; NCHILD[d] = vn; ID[d] = vi;
+                    const int d = rank(s);
+                    XY[d] = v; ECOST[d] = ve; PARENT[d] = vp; NCHILD[d] = vn; ID[d] = vi; NFLAG[d] = vf;
                 }
-                __syncthreads();
+                __syncwarp();
             }
-            for (int f = tid; f < c.n_finish; f += NT) FINISH[f] = smap[FINISH[f]];
-            __syncthreads();
-            if (tid == 0) {
-                c.root_slot = smap[c.root_slot];
-                if (c.best_leaf_slot >= 0) c.best_leaf_slot = smap[c.best_leaf_slot];
-                c.n_slots = c.n_live;
-                ++c.n_compactions;
-            }
-            __syncthreads();
+            for (int f = lane; f < n_finish; f += 32) FINISH[f] = rank(FINISH[f]);
+            root_slot = rank(root_slot);
+            if (best_leaf_slot >= 0) best_leaf_slot = rank(best_leaf_slot);
+            n_slots = n_live;
+            ++n_compactions;
+            __syncwarp();
         }
-
-        const double qx = c.qx, qy = c.qy;
-        const int n_slots = c.n_slots;
+        ++attempts;
+        // Graph.random_node (src/graph.py:96-98)
+        double qx, qy;
+        if (next_random(rng) < prm.bias) { qx = gx; qy = gy; }
+        else {
+            qx = dadd(prm.x_lo, dmul(dsub(prm.x_hi, prm.x_lo), next_random(rng)));
+            qy = dadd(prm.y_lo, dmul(dsub(prm.y_hi, prm.y_lo), next_random(rng)));
+        }
 
         // ================================================================ B. Map.is_occupied_c (src/map.py:38-47)
-        {
-            bool occ = false;
-            for (int j = tid; j < M; j += NT) {
-                double ox, oy, orad, oK;
-                load_obst(j, ox, oy, orad, oK);
-                occ |= point_in_inflated(qx, qy, ox, oy, orad, prm.node_radius);
-            }
-            if (__syncthreads_or(occ)) continue;                         // src/algorithm.py:39-40
-        }
+        if (point_occupied_warp(ob, qx, qy, prm.node_radius, lane, my_tests)) continue;   // src/algorithm.py:39-40
 
         // ================================================================ C. nearest visible node (:666-699)
         int near_slot = -1;
         {
             double prev_d = -1.0; int prev_s = -1;
             bool reject = false;
-            for (int round = 0; round < c.n_live; ++round) {
-                double bd = CUDART_INF; int bs = 0x7fffffff; bool exact = false;
-                for (int s = tid; s < n_slots; s += NT) {
-                    const double x = sx[s], y = sy[s];
-                    const double d = dist2(x, y, qx, qy);
-                    if (round == 0 && x == qx && y == qy) exact = true;           // G.id_vertex[vertex] hit (:676-678)
-                    const bool after_prev = d > prev_d || (d == prev_d && s > prev_s);
-                    if (after_prev && d < bd) { bd = d; bs = s; }
-                }
+            for (int round = 0; round < n_live; ++round) {
+                double bd = CUDART_INF; int bs = kIntMax;
+                for (int base = 0; base < n_slots; base += 128) {
+                    double2 v[4];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double od = __shfl_xor_sync(kFull, bd, off);
-                    const int os = __shfl_xor_sync(kFull, bs, off);
-                    if (key_less(od, os, bd, bs)) { bd = od; bs = os; }
-                }
-                const int par = round & 1;
-                if (lane == 0) { red_d[par * 32 + warp] = bd; red_s[par * 32 + warp] = bs; }
-                if (round == 0) { if (__syncthreads_or(exact)) { reject = true; break; } }
-                else __syncthreads();
-                bd = red_d[par * 32]; bs = red_s[par * 32];
+                    for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
 #pragma unroll
-                for (int w = 1; w < NW; ++w) {
-                    const double od = red_d[par * 32 + w]; const int os = red_s[par * 32 + w];
-                    if (key_less(od, os, bd, bs)) { bd = od; bs = os; }
+                    for (int u = 0; u < 4; ++u) {
+                        const int s = base + 32 * u + lane;
+                        const double d = dist2(v[u].x, v[u].y, qx, qy);                 // NaN for tombstones / padding
+                        const bool after_prev = d > prev_d || (d == prev_d && s > prev_s);  // always true in round 0
+                        if (after_prev && d < bd) { bd = d; bs = s; }
+                    }
                 }
-                if (bs == 0x7fffffff) break;                                      // nothing left
+                warp_argmin(bd, bs);
+                if (bs == kIntMax) break;                                         // nothing left
+                if (round == 0 && bd == 0.0) {                                    // G.id_vertex[vertex] hit (:676-678)
+                    const double2 e = XY[bs];
+                    bool exact = (e.x == qx && e.y == qy);
+                    if (!exact) {   // d2 underflowed to 0 without equality: look for a truly identical vertex
+                        for (int s = lane; s < n_slots; s += 32) { const double2 t = XY[s]; exact |= (t.x == qx && t.y == qy); }
+                        exact = __any_sync(kFull, exact);
+                    }
+                    if (exact) { reject = true; break; }
+                }
+                ++n_edge_checks; ++n_edge_checks_ref; n_scan_nodes += n_live;
                 // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692)
-                const Seg sg = make_seg(qx, qy, sx[bs], sy[bs]);
-                bool hit = false;
-                for (int j = tid; j < M; j += NT) {
-                    double ox, oy, orad, oK;
-                    load_obst(j, ox, oy, orad, oK);
-                    hit |= seg_hits_circle(sg, ox, oy, orad, oK);
-                }
-                if (tid == 0) { ++c.n_edge_checks; ++c.n_edge_checks_ref; c.n_circle_tests += M; c.n_scan_nodes += c.n_live; }
-                if (!__syncthreads_or(hit)) { near_slot = bs; break; }
+                const double2 nb = XY[bs];
+                const Seg sg = make_seg(qx, qy, nb.x, nb.y);
+                if (!seg_blocked_warp(ob, sg, qy, nb.y, lane, my_tests)) { near_slot = bs; break; }
                 prev_d = bd; prev_s = bs;
             }
             if (reject || near_slot < 0) continue;                               // :45-46
         }
 
-        // ================================================================ D. steer + insert (thread 0)
-        if (tid == 0) {
-            const double nx = sx[near_slot], ny = sy[near_slot];
-            const double d = dist_fma(qx, qy, nx, ny);                            // steer (:739)
-            const double ux = ddiv(dsub(qx, nx), d), uy = ddiv(dsub(qy, ny), d);
-            const double tx = dadd(nx, dmul(ux, prm.step_length)), ty = dadd(ny, dmul(uy, prm.step_length));
-            double px = qx, py = qy;
+        // ================================================================ D. steer + insert (every lane computes, lane 0 stores)
+        const double2 nb = XY[near_slot];
+        double px = qx, py = qy;
+        {
+            const double d = dist_fma(qx, qy, nb.x, nb.y);                        // steer (:739)
+            const double ux = ddiv(dsub(qx, nb.x), d), uy = ddiv(dsub(qy, nb.y), d);
+            const double tx = dadd(nb.x, dmul(ux, prm.step_length)), ty = dadd(nb.y, dmul(uy, prm.step_length));
             if (d > prm.step_length) { px = tx; py = ty; }
-            const int slot = c.n_slots++;
-            const int id = ++c.last_id;                                           // Graph.add_vertex (src/graph.py:57-61)
-            ++c.n_live;
-            const double e0 = dist_fma(px, py, nx, ny);                           // :49
-            sx[slot] = px; sy[slot] = py;
-            if (kTreeInSmem) { GX[slot] = px; GY[slot] = py; }
-            ID[slot] = id; PARENT[slot] = near_slot; ECOST[slot] = e0; NCHILD[slot] = 0;  // :141-142
-            c.px = px; c.py = py; c.e0 = e0; c.near_slot = near_slot; c.new_slot = slot;
-            c.reached = dist_fma(px, py, c.gx, c.gy) < goal_thresh;               // check_solution (:757-758)
-            c.k = 0; c.rewired_iter = 0; c.dup = 0; c.removed_id = -1; c.cp_parent_id = -1; c.cp_cost = 0.0;
-            if (prm.mode == RRTFND_MODE_RRT) {
+        }
+        const int new_slot = n_slots++;
+        const int id_new = ++last_id;                                            // Graph.add_vertex (src/graph.py:57-61)
+        ++n_live;
+        const double e0 = dist_fma(px, py, nb.x, nb.y);                          // :49
+        const bool reached = dist_fma(px, py, gx, gy) < goal_thresh;             // check_solution (:757-758)
+        if (lane == 0) {
+            XY[new_slot] = make_double2(px, py);
+            ID[new_slot] = id_new; PARENT[new_slot] = near_slot; ECOST[new_slot] = e0;   // :141-142
+            NCHILD[new_slot] = 0; NFLAG[new_slot] = 0;
+        }
+        __syncwarp();
+
+        if (prm.mode == RRTFND_MODE_RRT) {
+            int L = 0; double cost = 0.0;
+            if (lane == 0) {
                 NCHILD[near_slot] += 1;                                           // add_edge (:76)
-                if (c.reached) {                                                  // :78-81, break before iter += 1
-                    double cost = 0.0; int n = slot, L = 0;
-                    while (n != c.root_slot && n >= 0) {
+                if (reached) {                                                    // :78-81, break before iter += 1
+                    int n = new_slot;
+                    while (n != root_slot && n >= 0) {
                         if (L < prm.path_cap) BPATH[L] = ID[n];
                         ++L; cost = dadd(cost, ECOST[n]); n = PARENT[n]; ++my_hops;
                     }
-                    if (L < prm.path_cap) BPATH[L] = ID[c.root_slot];
+                    if (L < prm.path_cap) BPATH[L] = ID[root_slot];
                     ++L;
-                    c.best_len = L; c.best_cost = cost; c.best_leaf_slot = slot; c.solution_found = 1;
-                    c.status = L > prm.path_cap ? RRTFND_ST_PATH_CAP : RRTFND_ST_DONE;
-                    c.go = 0;
                 }
-                if (TRACE && c.iter < prm.trace_cap) {
-                    rrtfnd_trace_t t; t.id_new = id; t.id_near = ID[near_slot]; t.n_near = 0; t.n_rewired = 0;
+                if (TRACE && iter < prm.trace_cap) {
+                    rrtfnd_trace_t t; t.id_new = id_new; t.id_near = ID[near_slot]; t.n_near = 0; t.n_rewired = 0;
                     t.removed_id = -1; t.cp_parent = -1; t.cp_cost = 0.0;
-                    TRACE[c.iter] = t;
+                    TRACE[iter] = t;
                 }
-                if (c.go) ++c.iter;
             }
-        }
-        __syncthreads();
-        if (prm.mode == RRTFND_MODE_RRT) { if (!c.go) break; continue; }
-
-        const double px = c.px, py = c.py;
-        const int new_slot = c.new_slot;
-        const int n_slots2 = c.n_slots;
-
-        // ================================================================ E. near set (query_ball_point, :837 / :893)
-        {
-            bool dup = false;
-            for (int base = 0; base < n_slots2; base += NT) {
-                const int s = base + tid;
-                bool in = false;
-                if (s < n_slots2 && s != new_slot) {
-                    const double x = sx[s], y = sy[s];
-                    in = dist2(x, y, px, py) <= r2;
-                    dup |= (x == px && y == py);
-                }
-                const unsigned b = __ballot_sync(kFull, in);
-                if (lane == 0) bm[(base >> 5) + warp] = b;
-            }
-            if (__syncthreads_or(dup)) {                                          // src/graph.py:54-56 corner (B9)
-                if (tid == 0) c.status = RRTFND_ST_DUPLICATE;
+            __syncwarp();
+            if (reached) {
+                best_len = __shfl_sync(kFull, L, 0); best_cost = __shfl_sync(kFull, cost, 0);
+                best_leaf_slot = new_slot; solution_found = 1;
+                status = best_len > prm.path_cap ? RRTFND_ST_PATH_CAP : RRTFND_ST_DONE;
                 break;
             }
-            if (warp == 0) {                                                      // bitmap -> ascending slot list
-                const int nwords = (n_slots2 + 31) >> 5;
-                int count = 0;
-                for (int w0 = 0; w0 < nwords; w0 += 32) {
-                    uint32_t w = (w0 + lane < nwords) ? bm[w0 + lane] : 0u;
-                    const int n = __popc(w);
-                    int incl = n;
+            ++iter;
+            continue;
+        }
+
+        // ================================================================ E. near set -> collision, costs, choose-parent, rewire
+        // The ball (query_ball_point, :837 / :893) is produced in ascending slot order by the scan and handed to the
+        // lanes in chunks of up to 32 candidates: lane i owns candidate i (its own segment test, its own parent-chain
+        // walk). In the first chunk lane 31 walks the new node's chain (Graph.get_cost(id_new)). Rewire decisions are
+        // taken against the pre-rewire tree and committed after the scan.
+        int n_rw = 0, k_total = 0;
+        int cp_slot = near_slot; double cp_cost = e0;
+        bool dup = false;
+        double cost_new = 0.0;
+        const int n_pass = commit_cp ? 2 : 1;          // committing choose-parent needs its result before any rewire decision
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const bool do_cp = eval_cp && pass == 0;
+            const bool do_rw = pass == n_pass - 1;
+            const int walk_from = PARENT[new_slot];
+            const double walk_acc = ECOST[new_slot];
+            double cp_cn = 0.0;
+            bool first = true;
+            int count = 0;
+            k_total = 0;
+
+            auto process = [&](int n) {
+                int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
+                if (lane < n) {
+                    s = stage[lane];
+                    const double2 v = XY[s];
+                    dpl = dist_plain(v.x, v.y, px, py);                           // :842 / :899
+                    if (dpl == 0.0 && v.x == px && v.y == py) dup = true;         // src/graph.py:54-56 corner (B9)
+                    const Seg sg = make_seg(v.x, v.y, px, py);                    // Line(node, q_new): p1 = node (:846 / :903)
+                    hit = seg_blocked_lane(ob, sg, v.y, py, my_tests);
+                    if (!hit) cc = chain_walk(PARENT, ECOST, s, 0.0, my_hops);   // Graph.get_cost(id) (:848 / :905)
+                } else if (first && lane == 31) {
+                    cc = chain_walk(PARENT, ECOST, walk_from, walk_acc, my_hops); // Graph.get_cost(id_new)
+                }
+                __syncwarp();
+                if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; }
+                if (do_cp) {
+                    // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
+                    unsigned open = __ballot_sync(kFull, lane < n && !hit);
+                    while (open) {
+                        const int i = __ffs(open) - 1;
+                        open &= open - 1;
+                        const double ci = __shfl_sync(kFull, cc, i), di = __shfl_sync(kFull, dpl, i);
+                        if (cp_cn > dadd(ci, di)) {
+                            cp_slot = __shfl_sync(kFull, s, i); cp_cost = di;
+                            // G.cost[id_new] = cost, parent untouched: the chain is still id_near's (:849)
+                            cp_cn = chain_walk(PARENT, ECOST, near_slot, di, my_hops);
+                        }
+                    }
+                }
+                if (do_rw) {
+                    const bool rw = lane < n && !hit && cc > dadd(cost_new, dpl);   // :905, strict
+                    const unsigned m = __ballot_sync(kFull, rw);
+                    if (m) {   // remember the decision: short list in shared memory, overflow as a per-node flag bit
+                        const int pos = n_rw + __popc(m & lt_mask);
+                        if (rw) { if (pos < prm.near_cap) rwlist[pos] = s; else NFLAG[s] |= 2; }
+                        n_rw += __popc(m);
+                    }
+                }
+                first = false;
+                __syncwarp();
+            };
+
+            for (int base = 0; base < n_slots; base += 128) {
+                double2 v[4];
 #pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const int v = __shfl_up_sync(kFull, incl, off);
-                        if (lane >= off) incl += v;
-                    }
-                    int pos = count + incl - n;
-                    while (w) {
-                        const int bit = __ffs(w) - 1;
-                        w &= w - 1;
-                        if (pos < prm.near_cap) cslot[pos] = ((w0 + lane) << 5) + bit;
-                        ++pos;
-                    }
-                    count += __shfl_sync(kFull, incl, 31);
-                }
-                if (lane == 0) {
-                    c.k = count;
-                    c.n_scan_nodes += c.n_live;
-                    c.n_edge_checks += count;
-                    c.n_edge_checks_ref += 2 * (long long)count + 2;   // each candidate twice + Line(q_new,q_new) twice
-                }
-            }
-            __syncthreads();
-            if (c.k > prm.near_cap) { if (tid == 0) c.status = RRTFND_ST_NEAR_CAP; break; }
-        }
-        const int k = c.k;
-
-        // ---- E1. collision of Line(node, q_new) per candidate (:846-847 / :903-904): one warp per edge
-        for (int ci = warp; ci < k; ci += NW) {
-            const int s = cslot[ci];
-            const double x = sx[s], y = sy[s];
-            const Seg sg = make_seg(x, y, px, py);                                // p1 = node, p2 = q_new
-            bool hit = false;
-            int j0 = 0;
-            for (; j0 < M; j0 += 32) {
-                const int j = j0 + lane;
-                bool h = false;
-                if (j < M) {
-                    double ox, oy, orad, oK;
-                    load_obst(j, ox, oy, orad, oK);
-                    h = seg_hits_circle(sg, ox, oy, orad, oK);
-                }
-                if (__any_sync(kFull, h)) { hit = true; j0 += 32; break; }
-            }
-            if (lane == 0) {
-                chit[ci] = hit ? 1 : 0;
-                cdpl[ci] = dist_plain(x, y, px, py);                              // :842 / :899
-                my_tests += (j0 < M ? j0 : M);
-            }
-        }
-        // ---- E2. Graph.get_cost per candidate (src/graph.py:34-46): one lane per chain
-        for (int ci = tid; ci < k; ci += NT) ccost[ci] = chain_walk(PARENT, ECOST, cslot[ci], 0.0, my_hops);
-        if (tid == NT - 1) c.cost_new = chain_walk(PARENT, ECOST, c.near_slot, c.e0, my_hops);  // get_cost(id_new)
-        __syncthreads();
-
-        // ---- E3. choose_parent_kdtree's RETURNED edge (:845-852); dropped by the planners (:146, :224)
-        if (prm.flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) {
-            if (tid == 0) {
-                int bp = c.near_slot; double bc = c.e0; double cn = c.cost_new;
-                for (int ci = 0; ci < k; ++ci) {
-                    if (chit[ci]) continue;
-                    if (cn > dadd(ccost[ci], cdpl[ci])) {
-                        bp = cslot[ci]; bc = cdpl[ci];
-                        // G.cost[id_new] = cost, parent untouched: the chain is still id_near's (:849)
-                        cn = chain_walk(PARENT, ECOST, c.near_slot, bc, my_hops);
+                for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int s = base + 32 * u + lane;
+                    const bool in = dist2(v[u].x, v[u].y, px, py) <= r2 && s != new_slot;
+                    const unsigned m = __ballot_sync(kFull, in);
+                    if (m) {
+                        if (in) stage[count + __popc(m & lt_mask)] = s;
+                        count += __popc(m); k_total += __popc(m);
+                        const int cap = first ? 31 : 32;
+                        if (count >= cap) {
+                            __syncwarp();
+                            process(cap);
+                            const int rem = count - cap;                           // < 32
+                            const int t = lane < rem ? stage[cap + lane] : 0;
+                            __syncwarp();
+                            if (lane < rem) stage[lane] = t;
+                            count = rem;
+                        }
                     }
                 }
-                c.cp_parent_id = ID[bp]; c.cp_cost = bc;
-                if (prm.flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) {   // EXTENSION (not the shipped behaviour)
-                    PARENT[new_slot] = bp; ECOST[new_slot] = bc;
-                    c.cost_new = chain_walk(PARENT, ECOST, bp, bc, my_hops);
-                }
             }
-            __syncthreads();
-        }
+            if (count > 0) { __syncwarp(); process(count); }
 
-        // ---- E4. rewire_kdtree (:902-910): decide against the snapshot, then commit
+            if (pass == 0 && commit_cp && k_total > 0) {   // EXTENSION (not the shipped behaviour): adopt the returned edge
+                if (lane == 0) { PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost; }
+                __syncwarp();
+            }
+        }
+        if (__any_sync(kFull, dup)) { status = RRTFND_ST_DUPLICATE; break; }
+        n_scan_nodes += n_live;
+        n_edge_checks += k_total;
+        n_edge_checks_ref += 2 * (long long)k_total + 2;   // each candidate twice + Line(q_new, q_new) twice
+
+        // ---- E4. commit: rewire_kdtree's re-parenting (:906-910) and G.add_edge(*best_edge) (:148), serial on lane 0
+        bool need_refresh = false;
         {
-            const double cost_new = c.cost_new;
-            int n_rw = 0;
-            for (int ci = tid; ci < k; ci += NT) {
-                if (chit[ci]) continue;
-                if (ccost[ci] > dadd(cost_new, cdpl[ci])) {
-                    const int s = cslot[ci];
-                    atomicSub(&NCHILD[PARENT[s]], 1);
+            int d_childless = 0, flagged = 0;
+            if (lane == 0) {
+                auto reparent = [&](int s) {
+                    const int oldp = PARENT[s];
+                    if (--NCHILD[oldp] == 0) ++d_childless;
+                    const double2 v = XY[s];
                     PARENT[s] = new_slot;
-                    ECOST[s] = cdpl[ci];
-                    ++n_rw;
+                    ECOST[s] = dist_plain(v.x, v.y, px, py);
+                    flagged |= NFLAG[s] & 1;
+                };
+                const int n_list = n_rw < prm.near_cap ? n_rw : prm.near_cap;
+                for (int i = 0; i < n_list; ++i) reparent(rwlist[i]);
+                if (n_rw > n_list) {          // more re-parented nodes than the list holds (rare): find the flagged rest
+                    for (int s = 0; s < new_slot; ++s)
+                        if (NFLAG[s] & 2) { NFLAG[s] &= (uint8_t)~2; reparent(s); }
+                }
+                NCHILD[new_slot] = n_rw;
+                if (n_rw == 0) ++d_childless;
+                if (NCHILD[PARENT[new_slot]]++ == 0) --d_childless;
+                if (flagged) {   // the moved subtree holds a goal-reaching node: mark its new ancestors
+                    int n = new_slot;
+                    while (n >= 0 && !(NFLAG[n] & 1)) { NFLAG[n] |= 1; n = PARENT[n]; }
                 }
             }
-            if (n_rw) { atomicAdd(&NCHILD[new_slot], n_rw); atomicAdd(&c.rewired_iter, n_rw); }
-            if (tid == 0) atomicAdd(&NCHILD[PARENT[new_slot]], 1);                // G.add_edge(*best_edge) (:148)
+            __syncwarp();
+            n_childless += __shfl_sync(kFull, d_childless, 0);
+            need_refresh = __shfl_sync(kFull, flagged, 0) != 0;
+            n_rewired += n_rw;
         }
-        __syncthreads();
+
+        const int cp_parent_id = eval_cp ? ID[cp_slot] : -1;   // read before forced_removal can delete that node
 
         // ================================================================ F. forced_removal (:233-237, :800-819)
-        if (prm.mode == RRTFND_MODE_FN && c.n_live > prm.max_nodes) {
-            for (int base = 0; base < n_slots2; base += NT) {
-                const int s = base + tid;
-                const bool childless = s < n_slots2 && NCHILD[s] == 0;             // tombstones hold -1
-                const unsigned b = __ballot_sync(kFull, childless);
-                if (lane == 0) bm[(base >> 5) + warp] = b;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                const int nwords = (n_slots2 + 31) >> 5;
-                int total = 0;
-                for (int w0 = lane; w0 < nwords; w0 += 32) total += __popc(bm[w0]);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
-                const int leaf = c.best_leaf_slot;
-                int n_ok = total - (NCHILD[new_slot] == 0 ? 1 : 0);
-                if (leaf >= 0 && leaf != new_slot && NCHILD[leaf] == 0) --n_ok;
-                int pick = -1;
-                if (n_ok <= 0) { if (lane == 0) c.status = RRTFND_ST_NO_CHILDLESS; }
-                else {
-                    for (;;) {
-                        uint32_t r = 0; int bad = 0;
-                        if (lane == 0) { r = next_randbelow(rng, (uint32_t)total); bad = rng.exhausted; }   // random.choice (:813/:816)
-                        r = __shfl_sync(kFull, r, 0); bad = __shfl_sync(kFull, bad, 0);
-                        if (bad) { if (lane == 0) c.status = RRTFND_ST_STREAM_EXHAUSTED; break; }
-                        // r-th set bit of the bitmap, in ascending slot order
-                        int seen = 0; pick = -1;
-                        for (int w0 = 0; w0 < nwords && pick < 0; w0 += 32) {
-                            const uint32_t w = (w0 + lane < nwords) ? bm[w0 + lane] : 0u;
-                            const int n = __popc(w);
-                            int incl = n;
-#pragma unroll
-                            for (int off = 1; off < 32; off <<= 1) {
-                                const int v = __shfl_up_sync(kFull, incl, off);
-                                if (lane >= off) incl += v;
-                            }
-                            const int excl = seen + incl - n;
-                            const bool mine = (int)r >= excl && (int)r < excl + n;
-                            const unsigned who = __ballot_sync(kFull, mine);
-                            if (who) {
-                                const int src = __ffs(who) - 1;
-                                int cand = -1;
-                                if (lane == src) cand = ((w0 + lane) << 5) + (__fns(w, 0, (int)r - excl + 1));
-                                pick = __shfl_sync(kFull, cand, src);
-                            }
-                            seen += __shfl_sync(kFull, incl, 31);
-                        }
-                        if (pick != new_slot && pick != leaf) break;              // :815
-                    }
+        int removed_id = -1;
+        if (prm.mode == RRTFND_MODE_FN && n_live > prm.max_nodes) {
+            const int leaf = best_leaf_slot;
+            const int total = n_childless;
+            int n_ok = total - (NCHILD[new_slot] == 0 ? 1 : 0);
+            if (leaf >= 0 && leaf != new_slot && NCHILD[leaf] == 0) --n_ok;
+            if (n_ok <= 0) { status = RRTFND_ST_NO_CHILDLESS; break; }
+            int pick = -1;
+            for (;;) {
+                const uint32_t r = next_randbelow(rng, (uint32_t)total);          // random.choice (:813 / :816)
+                if (rng.exhausted) { status = RRTFND_ST_STREAM_EXHAUSTED; break; }
+                // r-th childless node in ascending slot order (tombstones hold nchild = -1)
+                int running = 0; pick = -1;
+                for (int base = 0; base < n_slots; base += 32) {
+                    const int s = base + lane;
+                    const unsigned m = __ballot_sync(kFull, s < n_slots && NCHILD[s] == 0);
+                    const int c = __popc(m);
+                    if ((int)r < running + c) { pick = base + (int)__fns(m, 0, (int)r - running + 1); break; }
+                    running += c;
                 }
-                if (lane == 0) { c.pick = (c.status == RRTFND_ST_RUNNING) ? pick : -1; c.k = 0; }
+                if (pick != new_slot && pick != leaf) break;                      // :815
             }
-            __syncthreads();
-            if (c.status != RRTFND_ST_RUNNING) break;
-            const int pick = c.pick;
+            if (status != RRTFND_ST_RUNNING) break;
             // finish_nodes_of_path.remove(id_removed) (:235-236), order preserving
             int fpos = -1;
-            for (int f = tid; f < c.n_finish; f += NT) if (FINISH[f] == pick) fpos = f;
-            if (fpos >= 0) c.k = fpos + 1;      // c.k doubles as a mailbox (zeroed above; candidates are done)
-            __syncthreads();
-            if (c.k > 0) {
-                const int f0 = c.k - 1;
-                // shift left by one, chunked so reads precede writes
-                for (int base = f0; base < c.n_finish - 1; base += NT) {
-                    const int f = base + tid;
-                    int v = 0; const bool ok = f < c.n_finish - 1;
-                    if (ok) v = FINISH[f + 1];
-                    __syncthreads();
+            for (int base = 0; base < n_finish; base += 32) {
+                const int f = base + lane;
+                const unsigned m = __ballot_sync(kFull, f < n_finish && FINISH[f] == pick);
+                if (m) { fpos = base + __ffs(m) - 1; break; }
+            }
+            if (fpos >= 0) {
+                for (int base = fpos; base < n_finish - 1; base += 32) {
+                    const int f = base + lane;
+                    const bool ok = f < n_finish - 1;
+                    const int v = ok ? FINISH[f + 1] : 0;
+                    __syncwarp();
                     if (ok) FINISH[f] = v;
-                    __syncthreads();
+                    __syncwarp();
                 }
+                --n_finish;
             }
-            if (tid == 0) {                                                       // Graph.remove_vertex (src/graph.py:64-77)
-                if (c.k > 0) --c.n_finish;
+            int d_childless = -1;                                                 // the removed node was childless
+            removed_id = ID[pick];
+            __syncwarp();
+            if (lane == 0) {                                                      // Graph.remove_vertex (src/graph.py:64-77)
                 const int par = PARENT[pick];
-                if (par >= 0) NCHILD[par] -= 1;
-                c.removed_id = ID[pick];
+                if (par >= 0 && --NCHILD[par] == 0) ++d_childless;
                 ID[pick] = -1; NCHILD[pick] = -1; PARENT[pick] = -1;
-                const double qnan = CUDART_NAN;
-                sx[pick] = qnan; sy[pick] = qnan;
-                if (kTreeInSmem) { GX[pick] = qnan; GY[pick] = qnan; }
-                --c.n_live; ++c.n_removed;
+                XY[pick] = nan2;
             }
-            __syncthreads();
+            __syncwarp();
+            n_childless += __shfl_sync(kFull, d_childless, 0);
+            --n_live; ++n_removed;
         }
 
         // ================================================================ G. goal test and best path (:155-170, :240-251)
-        if (c.reached) {
-            if (tid == 0) {
-                if (c.n_finish >= prm.finish_cap) c.status = RRTFND_ST_FINISH_CAP;
-                else {
-                    FINISH[c.n_finish++] = new_slot;
-                    c.solution_found = 1;
-                    if (prm.mode == RRTFND_MODE_STAR) {                           // unconditional overwrite (:160-161)
-                        double cost = 0.0; int n = new_slot, L = 0;
-                        while (n != c.root_slot && n >= 0) {
-                            if (L < prm.path_cap) BPATH[L] = ID[n];
-                            ++L; cost = dadd(cost, ECOST[n]); n = PARENT[n]; ++my_hops;
-                        }
-                        if (L < prm.path_cap) BPATH[L] = ID[c.root_slot];
-                        ++L;
-                        c.best_len = L; c.best_cost = cost; c.best_leaf_slot = new_slot;
-                        if (L > prm.path_cap) c.status = RRTFND_ST_PATH_CAP;
+        if (reached) {
+            if (n_finish >= prm.finish_cap) { status = RRTFND_ST_FINISH_CAP; break; }
+            int L = 0; double cost = 0.0;
+            if (lane == 0) {
+                FINISH[n_finish] = new_slot;
+                int n = new_slot;                                                 // mark the ancestors of the new finish node
+                while (n >= 0 && !(NFLAG[n] & 1)) { NFLAG[n] |= 1; n = PARENT[n]; }
+                if (prm.mode == RRTFND_MODE_STAR) {                               // unconditional overwrite (:160-161)
+                    n = new_slot;
+                    while (n != root_slot && n >= 0) {
+                        if (L < prm.path_cap) BPATH[L] = ID[n];
+                        ++L; cost = dadd(cost, ECOST[n]); n = PARENT[n]; ++my_hops;
                     }
+                    if (L < prm.path_cap) BPATH[L] = ID[root_slot];
+                    ++L;
                 }
             }
-            __syncthreads();
-            if (c.status != RRTFND_ST_RUNNING) break;
+            __syncwarp();
+            ++n_finish;
+            solution_found = 1;
+            if (prm.mode == RRTFND_MODE_STAR) {
+                best_len = __shfl_sync(kFull, L, 0); best_cost = __shfl_sync(kFull, cost, 0); best_leaf_slot = new_slot;
+                if (best_len > prm.path_cap) { status = RRTFND_ST_PATH_CAP; break; }
+            }
         }
-        // Path costs only change through a rewire, and the list only grows through a new finish node, so the
-        // reference's per-iteration refresh (:166-170) can only have an effect in those two cases.
-        if (c.reached || c.rewired_iter > 0) {
-            const int nf = c.n_finish;
-            if (nf > 0) {
-                double bd = CUDART_INF; int bf = 0x7fffffff;
-                for (int f = tid; f < nf; f += NT) {
-                    // find_path's running sum starts at 0 and adds leaf -> root (:787-792)
-                    double cost = 0.0; int n = FINISH[f];
-                    while (n != c.root_slot && n >= 0) { cost = dadd(cost, ECOST[n]); n = PARENT[n]; ++my_hops; }
-                    if (cost < bd) { bd = cost; bf = f; }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double od = __shfl_xor_sync(kFull, bd, off);
-                    const int of = __shfl_xor_sync(kFull, bf, off);
-                    if (key_less(od, of, bd, bf)) { bd = od; bf = of; }
-                }
-                if (lane == 0) { red_d[warp] = bd; red_s[warp] = bf; }
-                __syncthreads();
-                if (tid == 0) {
-                    for (int w = 1; w < NW; ++w)
-                        if (key_less(red_d[w], red_s[w], bd, bf)) { bd = red_d[w]; bf = red_s[w]; }
-                    if (bd < c.best_cost) {                                       // strict (:168, :249)
-                        int n = FINISH[bf], L = 0;
-                        const int leaf = n;
-                        while (n != c.root_slot && n >= 0) {
-                            if (L < prm.path_cap) BPATH[L] = ID[n];
-                            ++L; n = PARENT[n]; ++my_hops;
-                        }
-                        if (L < prm.path_cap) BPATH[L] = ID[c.root_slot];
-                        ++L;
-                        c.best_len = L; c.best_cost = bd; c.best_leaf_slot = leaf;
-                        if (L > prm.path_cap) c.status = RRTFND_ST_PATH_CAP;
+        // The reference recomputes every finish node's path each iteration and keeps a strictly cheaper one
+        // (:166-170, :247-251). A path cost only changes when a node with a goal-reaching descendant is rewired, and
+        // the list only grows through a new finish node, so those are the only iterations in which it can have an effect.
+        if ((reached || need_refresh) && n_finish > 0) {
+            double bd = CUDART_INF; int bf = kIntMax;
+            for (int f = lane; f < n_finish; f += 32) {
+                const double cost = path_cost(PARENT, ECOST, FINISH[f], root_slot, my_hops);
+                if (cost < bd) { bd = cost; bf = f; }
+            }
+            __syncwarp();
+            warp_argmin(bd, bf);
+            if (bd < best_cost) {                                                 // strict (:168, :249)
+                const int leaf = FINISH[bf];
+                int L = 0;
+                if (lane == 0) {
+                    int n = leaf;
+                    while (n != root_slot && n >= 0) {
+                        if (L < prm.path_cap) BPATH[L] = ID[n];
+                        ++L; n = PARENT[n]; ++my_hops;
                     }
+                    if (L < prm.path_cap) BPATH[L] = ID[root_slot];
+                    ++L;
                 }
-                __syncthreads();
-                if (c.status != RRTFND_ST_RUNNING) break;
+                __syncwarp();
+                best_len = __shfl_sync(kFull, L, 0); best_cost = bd; best_leaf_slot = leaf;
+                if (best_len > prm.path_cap) { status = RRTFND_ST_PATH_CAP; break; }
             }
         }
 
         // ================================================================ H. end of iteration
-        if (tid == 0) {
-            c.n_rewired += c.rewired_iter;
-            if (TRACE && c.iter < prm.trace_cap) {
-                rrtfnd_trace_t t;
-                t.id_new = c.last_id; t.id_near = ID[c.near_slot]; t.n_near = k; t.n_rewired = c.rewired_iter;
-                t.removed_id = c.removed_id; t.cp_parent = c.cp_parent_id; t.cp_cost = c.cp_cost;
-                TRACE[c.iter] = t;
-            }
-            ++c.iter;                                                             // :173 / :254
+        if (TRACE && iter < prm.trace_cap && lane == 0) {
+            rrtfnd_trace_t t;
+            t.id_new = id_new; t.id_near = ID[near_slot]; t.n_near = k_total; t.n_rewired = n_rw;
+            t.removed_id = removed_id;
+            t.cp_parent = cp_parent_id; t.cp_cost = eval_cp ? cp_cost : 0.0;
+            TRACE[iter] = t;
         }
-        // the next header's __syncthreads orders these writes before anyone reads them
+        ++iter;                                                                   // :173 / :254
     }
 
     // ---- write back
-    __syncthreads();
-    if (my_hops) atomicAdd((unsigned long long*)&c.n_chain_hops, (unsigned long long)my_hops);
-    if (my_tests) atomicAdd((unsigned long long*)&c.n_circle_tests, (unsigned long long)my_tests);
-    __syncthreads();
-    if (tid == 0) {
-        PL->best_cost = c.best_cost; PL->cursor = rng.cursor; PL->attempts = c.attempts;
-        PL->n_edge_checks = c.n_edge_checks; PL->n_edge_checks_ref = c.n_edge_checks_ref;
-        PL->n_circle_tests = c.n_circle_tests; PL->n_scan_nodes = c.n_scan_nodes; PL->n_chain_hops = c.n_chain_hops;
-        PL->n_slots = c.n_slots; PL->n_live = c.n_live; PL->last_id = c.last_id; PL->iter = c.iter;
-        PL->root_slot = c.root_slot; PL->n_finish = c.n_finish; PL->best_len = c.best_len; PL->status = c.status;
-        PL->n_rewired = c.n_rewired; PL->n_removed = c.n_removed; PL->solution_found = c.solution_found;
-        PL->n_compactions = c.n_compactions;
+    __syncwarp();
+    const long long hops = warp_sum(my_hops), tests = warp_sum(my_tests);
+    if (lane == 0) {
+        PL->best_cost = best_cost; PL->cursor = rng.cursor; PL->attempts = attempts;
+        PL->n_edge_checks = n_edge_checks; PL->n_edge_checks_ref = n_edge_checks_ref;
+        PL->n_circle_tests += tests; PL->n_scan_nodes = n_scan_nodes; PL->n_chain_hops += hops;
+        PL->n_slots = n_slots; PL->n_live = n_live; PL->last_id = last_id; PL->iter = iter;
+        PL->root_slot = root_slot; PL->n_finish = n_finish; PL->best_len = best_len; PL->status = status;
+        PL->n_rewired = n_rewired; PL->n_removed = n_removed; PL->solution_found = solution_found;
+        PL->n_compactions = n_compactions;
     }
 }
 
@@ -663,8 +582,8 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
     if (p >= bt.n_planners) return;
     const size_t o = (size_t)p * prm.capacity;
     rrtfnd_planner_t* PL = bt.planners + p;
-    bt.x[o] = PL->start_x; bt.y[o] = PL->start_y; bt.ecost[o] = 0.0;
-    bt.parent[o] = -1; bt.nchild[o] = 0; bt.id[o] = 0;
+    bt.xy[2 * o] = PL->start_x; bt.xy[2 * o + 1] = PL->start_y; bt.ecost[o] = 0.0;
+    bt.parent[o] = -1; bt.nchild[o] = 0; bt.id[o] = 0; bt.nflags[o] = 0;
     PL->best_cost = CUDART_INF;
     PL->cursor = 0; PL->attempts = 0; PL->n_edge_checks = 0; PL->n_edge_checks_ref = 0; PL->n_circle_tests = 0;
     PL->n_scan_nodes = 0; PL->n_chain_hops = 0;
@@ -675,55 +594,25 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int NT, bool kTreeInSmem, bool kObstInSmem>
+template <int WPB>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
-    const SmemPlan sp = plan_smem(*prm, NT, kTreeInSmem, kObstInSmem);
-    auto kern = plan_kernel<NT, kTreeInSmem, kObstInSmem>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    const size_t bytes = warp_smem_bytes(*prm) * WPB;
+    if (bytes > kMaxSmem) return RRTFND_E_SMEM;
+    auto kern = plan_kernel<WPB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    kern<<<bt->n_planners, NT, sp.total, st>>>(*prm, *bt);
+    kern<<<(bt->n_planners + WPB - 1) / WPB, 32 * WPB, bytes, st>>>(*prm, *bt);
     return (int)cudaGetLastError();
 }
 
-// Launch geometry. prm->reserved encodes an explicit choice as threads + 1000 * layout
-// (layout 0: tree + obstacles in shared memory, 1: obstacles only, 2: neither); 0 = automatic.
-struct PlanCfg { int nt; int layout; };
-
-static PlanCfg choose_cfg(const rrtfnd_params_t& prm, int n_planners) {
-    if (prm.reserved > 0) return PlanCfg{prm.reserved % 1000, prm.reserved / 1000};
-    // Batches that can fill the GPU several CTAs deep run light CTAs (tree streamed through L1/L2, obstacle table
-    // L1-resident): occupancy hides the parent-chain latency. Small batches keep one fat CTA per planner with
-    // the coordinates in shared memory (lowest latency per tree).
-    if (n_planners >= 296 && plan_smem(prm, 128, false, false).total <= 24 * 1024) return PlanCfg{128, 2};
-    if (plan_smem(prm, 256, true, true).total <= kMaxSmem) return PlanCfg{256, 0};
-    if (plan_smem(prm, 256, false, true).total <= kMaxSmem) return PlanCfg{256, 1};
-    return PlanCfg{256, 2};
-}
-
-static size_t cfg_smem(const rrtfnd_params_t& prm, PlanCfg c) {
-    return plan_smem(prm, c.nt, c.layout == 0, c.layout <= 1).total;
-}
-
-template <int NT>
-static int launch_nt(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, int layout, cudaStream_t st) {
-    switch (layout) {
-        case 0: return launch_plan<NT, true, true>(prm, bt, st);
-        case 1: return launch_plan<NT, false, true>(prm, bt, st);
-        case 2: return launch_plan<NT, false, false>(prm, bt, st);
-        default: return RRTFND_E_BADARG;
-    }
-}
-
-static int launch_cfg(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, PlanCfg c, cudaStream_t st) {
-    if (cfg_smem(*prm, c) > kMaxSmem) return RRTFND_E_SMEM;
-    switch (c.nt) {
-        case 32: return launch_nt<32>(prm, bt, c.layout, st);
-        case 64: return launch_nt<64>(prm, bt, c.layout, st);
-        case 128: return launch_nt<128>(prm, bt, c.layout, st);
-        case 256: return launch_nt<256>(prm, bt, c.layout, st);
-        case 512: return launch_nt<512>(prm, bt, c.layout, st);
-        default: return RRTFND_E_BADARG;
-    }
+// Warps (= planners) per CTA. prm->reserved makes an explicit choice (1, 2, 4 or 8); 0 = automatic: one planner
+// per CTA spreads a small batch evenly over the SMs (an SM holds at most 32 CTAs), larger batches need more warps
+// per CTA to reach the SM's warp limit.
+static int choose_wpb(const rrtfnd_params_t& prm, int n_planners) {
+    if (prm.reserved == 1 || prm.reserved == 2 || prm.reserved == 4 || prm.reserved == 8) return prm.reserved;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return n_planners <= 32 * sms ? 1 : 2;
 }
 
 }  // namespace rrtfnd
@@ -737,12 +626,16 @@ static int check_params(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
     if (prm->near_cap < 1 || prm->finish_cap < 1 || prm->path_cap < 2) return RRTFND_E_BADARG;
     if (prm->stream_mode == RRTFND_STREAM_WORDS && !bt->words) return RRTFND_E_BADARG;
     if ((prm->flags & RRTFND_FLAG_TRACE) && (!bt->trace || prm->trace_cap < 1)) return RRTFND_E_BADARG;
+    if (!bt->planners || !bt->xy || !bt->ecost || !bt->parent || !bt->nchild || !bt->id || !bt->nflags || !bt->finish ||
+        !bt->best_path || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
+    if (bt->grid.nx > 0 && (!bt->grid.seg_start || !bt->grid.seg_items || !bt->grid.pt_start || !bt->grid.pt_items ||
+                            bt->grid.ny <= 0)) return RRTFND_E_BADARG;
     return 0;
 }
 
 extern "C" int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm) {
     if (!prm) return RRTFND_E_BADARG;
-    const size_t b = cfg_smem(*prm, choose_cfg(*prm, 1 << 20));
+    const size_t b = warp_smem_bytes(*prm);
     return b <= kMaxSmem ? (int64_t)b : (int64_t)RRTFND_E_SMEM;
 }
 
@@ -753,11 +646,18 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     if (!(q.flags & RRTFND_FLAG_TRACE)) q.trace_cap = 0;
     rrtfnd_batch_t b = *bt;
     if (!(q.flags & RRTFND_FLAG_TRACE)) b.trace = nullptr;
-    return launch_cfg(&q, &b, choose_cfg(q, b.n_planners), (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (choose_wpb(q, b.n_planners)) {
+        case 1: return launch_plan<1>(&q, &b, st);
+        case 2: return launch_plan<2>(&q, &b, st);
+        case 4: return launch_plan<4>(&q, &b, st);
+        case 8: return launch_plan<8>(&q, &b, st);
+        default: return RRTFND_E_BADARG;
+    }
 }
 
 extern "C" int rrtfnd_init_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, void* stream) {
-    if (!prm || !bt || bt->n_planners <= 0) return RRTFND_E_BADARG;
+    if (!prm || !bt || bt->n_planners <= 0 || !bt->planners || !bt->xy || !bt->nflags) return RRTFND_E_BADARG;
     const int nt = 128;
     init_kernel<<<(bt->n_planners + nt - 1) / nt, nt, 0, (cudaStream_t)stream>>>(*prm, *bt);
     return (int)cudaGetLastError();

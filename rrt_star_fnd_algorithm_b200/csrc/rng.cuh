@@ -18,7 +18,7 @@ struct WordSrc {
     const uint32_t* words;  // STREAM_WORDS buffer of this planner
     long long n_words;
     unsigned long long seed, stream, cursor, blk_idx;
-    uint32_t blk[4];
+    uint32_t b0, b1, b2, b3;   // cached Philox block (scalars: a dynamically indexed array would live in local memory)
     int mode;
     bool have_blk, exhausted;
 };
@@ -47,11 +47,14 @@ __device__ __forceinline__ uint32_t next_word(WordSrc& r) {
     }
     const unsigned long long b = i >> 2;
     if (!r.have_blk || b != r.blk_idx) {
-        philox4x32_10(b, r.stream, r.seed, r.blk);
+        uint32_t o[4];
+        philox4x32_10(b, r.stream, r.seed, o);
+        r.b0 = o[0]; r.b1 = o[1]; r.b2 = o[2]; r.b3 = o[3];
         r.blk_idx = b;
         r.have_blk = true;
     }
-    return r.blk[i & 3];
+    const unsigned k = (unsigned)i & 3u;
+    return k == 0 ? r.b0 : k == 1 ? r.b1 : k == 2 ? r.b2 : r.b3;
 }
 
 __device__ __forceinline__ double next_random(WordSrc& r) {

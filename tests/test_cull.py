@@ -1,0 +1,91 @@
+"""Obstacle-grid culling must not change a single boolean.
+
+CPU: adversarial probe of the culling rule itself (oracle/cull_probe.c) on the reference's predicate.
+GPU: the culled operators (what the fused planner runs) against the un-culled operators and the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+def seg_margin(coord_max, slope_max=256.0):
+    return 128.0 * (1.0 + slope_max) * coord_max / 2.0 ** 26      # grid_seg_margin in csrc/grid.cuh
+
+
+@pytest.mark.parametrize("coord_max", [16.0, 256.0, 1024.0, 8192.0])
+def test_no_culled_circle_ever_hits(coord_max):
+    hits, valid = O.cull_probe(11, 3_000_000, coord_max, 256.0, seg_margin(coord_max), scale=1.0)
+    assert valid > 2_000_000 and hits == 0
+    # a quarter of the margin is the bound derived in DESIGN.md (the shipped margin carries a 4x safety factor)
+    hits, _ = O.cull_probe(12, 3_000_000, coord_max, 256.0, seg_margin(coord_max), scale=0.25)
+    assert hits == 0
+
+
+def test_probe_is_adversarial():
+    """With (almost) no margin the same placements do produce hits, i.e. the probe looks in the right place."""
+    hits, valid = O.cull_probe(13, 3_000_000, 256.0, 256.0, seg_margin(256.0), scale=1e-6)
+    assert hits > 100
+
+
+# ----------------------------------------------------------------------------------------------------- GPU
+def _edges(rng, n, lo, hi, obst):
+    """Random segments: short and long, plus steep / vertical / endpoint-on-circle corner cases."""
+    p1 = rng.uniform(lo, hi, (n, 2))
+    L = np.exp(rng.uniform(np.log(1e-3), np.log(hi - lo), n))
+    th = rng.uniform(0, 2 * np.pi, n)
+    p2 = np.clip(p1 + L[:, None] * np.column_stack([np.cos(th), np.sin(th)]), lo, hi)
+    k = n // 10
+    p2[:k, 0] = p1[:k, 0]                                         # vertical (infinite-line quirk, all circles)
+    p2[k:2 * k, 0] = p1[k:2 * k, 0] + rng.uniform(-1e-6, 1e-6, k)  # steeper than slope_max: falls back to the table
+    ob = np.asarray(obst)
+    j = rng.integers(0, len(ob), k)
+    a = rng.uniform(0, 2 * np.pi, k)                              # an endpoint exactly on / just off a circle's rim
+    p1[2 * k:3 * k] = ob[j, :2] + (ob[j, 2] * (1 + rng.choice([0, 1e-15, -1e-15, 1e-9], k)))[:, None] * np.column_stack([np.cos(a), np.sin(a)])
+    return p1, p2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload", ["c2", "c3", "c1"])
+def test_culled_edge_and_point_operators_equal_the_full_ones(workload):
+    import torch
+    from rrt_star_fnd_algorithm_b200 import _abi, workloads as W
+    from rrt_star_fnd_algorithm_b200.batch import build_obstacle_grid, obstacle_table
+    w = W.WORKLOADS[workload]()
+    (x0, x1), (y0, y1) = w["xy_range"]
+    tab = obstacle_table(w["obstacles"])
+    g, arrs = build_obstacle_grid(tab[:, :3], w["node_radius"], (x0, x1, y0, y1))
+    dev = torch.device("cuda:0")
+    gt = [torch.from_numpy(a).to(dev) for a in arrs]
+    g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in gt]
+    rng = np.random.default_rng(3)
+    n = 400_000
+    p1, p2 = _edges(rng, n, x0, x1, w["obstacles"])
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tp = [d(p1[:, 0]), d(p1[:, 1]), d(p2[:, 0]), d(p2[:, 1])]
+    tob = d(tab)
+    full = torch.zeros(n, dtype=torch.uint8, device=dev)
+    cull = torch.full((n,), 7, dtype=torch.uint8, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    _abi.check(_abi.lib.rrtfnd_edges_vs_circles(*[ptr(t) for t in tp], n, ptr(tob), len(tab), ptr(full), None), "full")
+    _abi.check(_abi.lib.rrtfnd_edges_vs_circles_grid(*[ptr(t) for t in tp], n, ptr(tob), len(tab), C.byref(g), ptr(cull), None), "culled")
+    torch.cuda.synchronize()
+    full, cull = full.cpu().numpy(), cull.cpu().numpy()
+    assert 0.02 < full.mean() < 0.98
+    bad = np.flatnonzero(full != cull)
+    assert bad.size == 0, (bad[:5], p1[bad[:5]], p2[bad[:5]])
+    for i in rng.integers(0, n, 300):                             # and both equal the CPU oracle
+        assert bool(full[i]) == O.through_obstacle(p1[i], p2[i], w["obstacles"])
+    # points
+    pts = rng.uniform(x0, x1, (n, 2))
+    tx, ty = d(pts[:, 0]), d(pts[:, 1])
+    of = torch.zeros(n, dtype=torch.uint8, device=dev)
+    oc = torch.full((n,), 7, dtype=torch.uint8, device=dev)
+    _abi.check(_abi.lib.rrtfnd_points_occupied(ptr(tx), ptr(ty), n, ptr(tob), len(tab), w["node_radius"], ptr(of), None), "full")
+    _abi.check(_abi.lib.rrtfnd_points_occupied_grid(ptr(tx), ptr(ty), n, ptr(tob), len(tab), C.byref(g), w["node_radius"], ptr(oc), None), "culled")
+    torch.cuda.synchronize()
+    of, oc = of.cpu().numpy(), oc.cpu().numpy()
+    assert np.array_equal(of, oc)
+    for i in rng.integers(0, n, 300):
+        assert bool(of[i]) == O.is_occupied(pts[i], w["obstacles"], w["node_radius"])
