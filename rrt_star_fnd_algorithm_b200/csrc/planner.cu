@@ -216,43 +216,114 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
         if (point_occupied_warp(ob, qx, qy, prm.node_radius, lane, my_tests)) continue;   // src/algorithm.py:39-40
 
         // ================================================================ C. nearest visible node (:666-699)
+        // The reference asks the k-d tree for the 1st, 2nd, 3rd ... nearest node until one is visible. Round 0 here is
+        // that first query (plain argmin). If it is blocked, the remaining order is consumed in annuli of doubling
+        // squared radius: every node of an annulus is tested (one lane per segment) and the lowest (d2, slot) key among
+        // the visible ones is the node the reference would have stopped at, because everything in earlier annuli was
+        // blocked. A boxed-in sample therefore costs O(log N) scans instead of O(N).
         int near_slot = -1;
         {
-            double prev_d = -1.0; int prev_s = -1;
-            bool reject = false;
-            for (int round = 0; round < n_live; ++round) {
-                double bd = CUDART_INF; int bs = kIntMax;
-                for (int base = 0; base < n_slots; base += 128) {
-                    double2 v[4];
+            double bd = CUDART_INF; int bs = kIntMax;
+            for (int base = 0; base < n_slots; base += 128) {
+                double2 v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
+                for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int s = base + 32 * u + lane;
-                        const double d = dist2(v[u].x, v[u].y, qx, qy);                 // NaN for tombstones / padding
-                        const bool after_prev = d > prev_d || (d == prev_d && s > prev_s);  // always true in round 0
-                        if (after_prev && d < bd) { bd = d; bs = s; }
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    const double d = dist2(v[u].x, v[u].y, qx, qy);                     // NaN for tombstones / padding
+                    if (d < bd) { bd = d; bs = base + 32 * u + lane; }
                 }
-                warp_argmin(bd, bs);
-                if (bs == kIntMax) break;                                         // nothing left
-                if (round == 0 && bd == 0.0) {                                    // G.id_vertex[vertex] hit (:676-678)
-                    const double2 e = XY[bs];
-                    bool exact = (e.x == qx && e.y == qy);
-                    if (!exact) {   // d2 underflowed to 0 without equality: look for a truly identical vertex
-                        for (int s = lane; s < n_slots; s += 32) { const double2 t = XY[s]; exact |= (t.x == qx && t.y == qy); }
-                        exact = __any_sync(kFull, exact);
-                    }
-                    if (exact) { reject = true; break; }
+            }
+            warp_argmin(bd, bs);
+            n_scan_nodes += n_live;
+            if (bs == kIntMax) continue;                                          // empty tree (cannot happen)
+            if (bd == 0.0) {                                                      // G.id_vertex[vertex] hit (:676-678)
+                const double2 e = XY[bs];
+                bool exact = (e.x == qx && e.y == qy);
+                if (!exact) {   // d2 underflowed to 0 without equality: look for a truly identical vertex
+                    for (int s = lane; s < n_slots; s += 32) { const double2 t = XY[s]; exact |= (t.x == qx && t.y == qy); }
+                    exact = __any_sync(kFull, exact);
                 }
-                ++n_edge_checks; ++n_edge_checks_ref; n_scan_nodes += n_live;
-                // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692)
+                if (exact) continue;                                              // rejected at :45
+            }
+            // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692)
+            int rounds = 1;
+            {
                 const double2 nb = XY[bs];
                 const Seg sg = make_seg(qx, qy, nb.x, nb.y);
-                if (!seg_blocked_warp(ob, sg, qy, nb.y, lane, my_tests)) { near_slot = bs; break; }
-                prev_d = bd; prev_s = bs;
+                if (!seg_blocked_warp(ob, sg, qy, nb.y, lane, my_tests)) near_slot = bs;
             }
-            if (reject || near_slot < 0) continue;                               // :45-46
+            if (near_slot < 0 && n_live > 1) {
+                double lo_d = bd; int lo_s = bs;                                  // keys <= (lo_d, lo_s) are known to be blocked
+                double T = bd;
+                const double t_floor = dmul(dmul(prm.step_length, prm.step_length), 0.0625);
+                rounds = n_live;                                                  // if nothing is visible every node was tried
+                for (;;) {
+                    T = dadd(T, T);
+                    if (T < t_floor) T = t_floor;
+                    double vd = CUDART_INF; int vs = kIntMax;                      // this lane's best visible key
+                    bool beyond = false;
+                    int count = 0;
+                    auto test_chunk = [&](int n) {
+                        if (lane < n) {
+                            const int s = stage[lane];
+                            const double2 nb = XY[s];
+                            const Seg sg = make_seg(qx, qy, nb.x, nb.y);
+                            if (!seg_blocked_lane(ob, sg, qy, nb.y, my_tests)) {
+                                const double d = dist2(nb.x, nb.y, qx, qy);
+                                if (d < vd || (d == vd && s < vs)) { vd = d; vs = s; }
+                            }
+                        }
+                        __syncwarp();
+                    };
+                    for (int base = 0; base < n_slots; base += 128) {
+                        double2 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int s = base + 32 * u + lane;
+                            const double d = dist2(v[u].x, v[u].y, qx, qy);
+                            beyond |= d > T;
+                            const bool in = (d > lo_d || (d == lo_d && s > lo_s)) && d <= T;
+                            const unsigned m = __ballot_sync(kFull, in);
+                            if (m) {
+                                if (in) stage[count + __popc(m & lt_mask)] = s;
+                                count += __popc(m);
+                                if (count >= 32) {
+                                    __syncwarp();
+                                    test_chunk(32);
+                                    const int rem = count - 32;
+                                    const int t = lane < rem ? stage[32 + lane] : 0;
+                                    __syncwarp();
+                                    if (lane < rem) stage[lane] = t;
+                                    count = rem;
+                                }
+                            }
+                        }
+                    }
+                    if (count > 0) { __syncwarp(); test_chunk(count); }
+                    n_scan_nodes += n_live;
+                    warp_argmin(vd, vs);
+                    if (vs != kIntMax) {
+                        near_slot = vs;
+                        // the reference's query count = rank of the winner in (d2, slot) order
+                        int rank = 0;
+                        for (int base = 0; base < n_slots; base += 32) {
+                            const int s = base + lane;
+                            bool le = false;
+                            if (s < n_slots) { const double2 t = XY[s]; const double d = dist2(t.x, t.y, qx, qy); le = d < vd || (d == vd && s <= vs); }
+                            rank += __popc(__ballot_sync(kFull, le));
+                        }
+                        rounds = rank;
+                        break;
+                    }
+                    if (!__any_sync(kFull, beyond)) break;                        // every node tried, none visible
+                    lo_d = T; lo_s = kIntMax;
+                }
+            }
+            n_edge_checks += rounds; n_edge_checks_ref += rounds;
+            if (near_slot < 0) continue;                                          // :45-46
         }
 
         // ================================================================ D. steer + insert (every lane computes, lane 0 stores)
