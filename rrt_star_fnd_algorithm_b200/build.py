@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librrtfnd.so")
 SOURCES = ["planner.cu", "ops.cu", "fnd.cu", "host_api.cu"]
-HEADERS = ["arith.cuh", "rng.cuh", "grid.cuh", "cull.cuh", os.path.join("..", "..", "include", "rrtfnd.h")]
+HEADERS = ["arith.cuh", "rng.cuh", "grid.cuh", "cull.cuh", "stream.cuh", os.path.join("..", "..", "include", "rrtfnd.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -13,8 +13,11 @@ namespace rrtfnd {
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+// IEEE division and square root expand to long instruction sequences (reciprocal / rsqrt seed, Newton steps, exact
+// rounding fix-up). They are calls, not inline expansions, so that each exists once per kernel: the fused planner
+// has about twenty call sites and must fit the instruction cache (see profiles/).
+static __device__ __noinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+static __device__ __noinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
 
 // calc_distance (src/algorithm.py:954-961): np.linalg.norm(p - q) = sqrt(ddot(v, v)); OpenBLAS' ddot tail
 // loop is FMA-contracted, i.e. sqrt(fma(dy, dy, fl(dx*dx))).

@@ -1,6 +1,12 @@
 // cull.cuh — obstacle tests of the planners with grid culling (see grid.cuh for the exactness argument).
-//   seg_blocked_lane / seg_blocked_warp   through_obstacle      src/algorithm.py:581-591
-//   point_occupied_warp                   Map.is_occupied_c     src/map.py:38-47
+//   seg_blocked            through_obstacle      src/algorithm.py:581-591
+//   point_occupied_warp    Map.is_occupied_c     src/map.py:38-47
+//
+// Code size matters here: the fused planner keeps dozens of warps in different phases on one SM, so its
+// instruction footprint has to stay inside the instruction cache. The segment test (one division for the line,
+// two divisions and a square root per circle) therefore exists ONCE, not inlined, and serves both uses through a
+// (first, stride) pair: a lane testing its own segment walks its circles with (0, 1), a warp sharing one segment
+// splits them with (lane, 32).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,13 +19,30 @@ namespace rrtfnd {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// What a kernel needs to test obstacles: the table, the grid (pointer to the kernel's __grid_constant__ parameter or
+// to any other copy) and the cell-count limit above which a bounding box is cheaper to test against the whole table
+// (cells overlap, so their lists repeat circles).
 struct Obst {
-    const double2* tab;      // [M][2]: (ox, oy), (r, K)
-    rrtfnd_obst_grid_t g;
+    const double2* tab;               // [M][2]: (ox, oy), (r, K)
+    const rrtfnd_obst_grid_t* g;
     int M;
-    int full_cells;          // bounding boxes covering more cells than this test the whole table instead
-    bool use_grid;
+    int full_cells;                   // 0 = no grid
 };
+
+__device__ __forceinline__ Obst make_obst(const double* obst, int n_obst, const rrtfnd_obst_grid_t* grid) {
+    Obst ob;
+    ob.tab = reinterpret_cast<const double2*>(obst);
+    ob.g = grid;
+    ob.M = n_obst;
+    ob.full_cells = 0;
+    if (grid->nx > 0 && grid->seg_start != nullptr && n_obst > 0) {
+        const int ncells = grid->nx * grid->ny;
+        const int n_items = __ldg(grid->seg_start + ncells);
+        ob.full_cells = (int)(((long long)n_obst * ncells) / (n_items > 0 ? n_items : 1));
+        if (ob.full_cells < 1) ob.full_cells = 1;
+    }
+    return ob;
+}
 
 __device__ __forceinline__ void load_obst(const double2* __restrict__ tab, int j, double& ox, double& oy, double& r,
                                           double& K) {
@@ -27,106 +50,60 @@ __device__ __forceinline__ void load_obst(const double2* __restrict__ tab, int j
     ox = a.x; oy = a.y; r = b.x; K = b.y;
 }
 
-__device__ __forceinline__ bool seg_can_cull(const Obst& ob, const Seg& sg, double ya, double yb, int& cx0, int& cx1,
-                                             int& cy0, int& cy1) {
-    if (!ob.use_grid || sg.vertical || !(fabs(sg.m) <= ob.g.slope_max)) return false;
-    cx0 = grid_cell(sg.lo, ob.g.x0, ob.g.inv_cell, ob.g.nx);
-    cx1 = grid_cell(sg.hi, ob.g.x0, ob.g.inv_cell, ob.g.nx);
-    cy0 = grid_cell(ya < yb ? ya : yb, ob.g.y0, ob.g.inv_cell, ob.g.ny);
-    cy1 = grid_cell(ya < yb ? yb : ya, ob.g.y0, ob.g.inv_cell, ob.g.ny);
-    return (cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= ob.full_cells;
-}
-
-// through_obstacle for this LANE's own segment (lanes hold different segments; sequential over its circles)
-__device__ __forceinline__ bool seg_blocked_lane(const Obst& ob, const Seg& sg, double ya, double yb, long long& tests) {
-    int cx0, cx1, cy0, cy1;
-    double ox, oy, r, K;
-    if (seg_can_cull(ob, sg, ya, yb, cx0, cx1, cy0, cy1)) {
-        for (int cy = cy0; cy <= cy1; ++cy) {
-            int j = __ldg(ob.g.seg_start + cy * ob.g.nx + cx0);
-            const int e = __ldg(ob.g.seg_start + cy * ob.g.nx + cx1 + 1);
-            for (; j < e; ++j) {
-                load_obst(ob.tab, __ldg(ob.g.seg_items + j), ox, oy, r, K);
-                ++tests;
-                if (seg_hits_circle(sg, ox, oy, r, K)) return true;
-            }
-        }
-        return false;
+// through_obstacle(Line(p1, p2), obstacles) over the circles first, first + stride, ... of the candidate list.
+// Returns (circle tests performed << 1) | hit. Stops at the first hit.
+static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, const rrtfnd_obst_grid_t* __restrict__ g, int M,
+                                        int full_cells, double p1x, double p1y, double p2x, double p2y, int first,
+                                        int stride) {
+    const Seg sg = make_seg(p1x, p1y, p2x, p2y);
+    int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, nx = 0;
+    bool cull = false;
+    if (full_cells > 0 && !sg.vertical && fabs(sg.m) <= g->slope_max) {
+        const double x0 = g->x0, y0 = g->y0, inv = g->inv_cell;
+        nx = g->nx;
+        const int ny = g->ny;
+        cx0 = grid_cell(sg.lo, x0, inv, nx);
+        cx1 = grid_cell(sg.hi, x0, inv, nx);
+        cy0 = grid_cell(p1y < p2y ? p1y : p2y, y0, inv, ny);
+        cy1 = grid_cell(p1y < p2y ? p2y : p1y, y0, inv, ny);
+        cull = (cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= full_cells;
     }
-    for (int j = 0; j < ob.M; ++j) {
-        load_obst(ob.tab, j, ox, oy, r, K);
-        ++tests;
-        if (seg_hits_circle(sg, ox, oy, r, K)) return true;
-    }
-    return false;
-}
-
-// through_obstacle for ONE segment held by every lane (lanes stride over its circles)
-__device__ __forceinline__ bool seg_blocked_warp(const Obst& ob, const Seg& sg, double ya, double yb, int lane,
-                                                 long long& tests) {
-    int cx0, cx1, cy0, cy1;
-    double ox, oy, r, K;
-    bool hit = false;
-    if (seg_can_cull(ob, sg, ya, yb, cx0, cx1, cy0, cy1)) {
-        for (int cy = cy0; cy <= cy1; ++cy) {
-            const int b = __ldg(ob.g.seg_start + cy * ob.g.nx + cx0);
-            const int e = __ldg(ob.g.seg_start + cy * ob.g.nx + cx1 + 1);
-            for (int j = b + lane; j < e; j += 32) {
-                load_obst(ob.tab, __ldg(ob.g.seg_items + j), ox, oy, r, K);
-                ++tests;
-                hit |= seg_hits_circle(sg, ox, oy, r, K);
-            }
-        }
-    } else {
-        for (int j = lane; j < ob.M; j += 32) {
-            load_obst(ob.tab, j, ox, oy, r, K);
+    if (!cull) { cy0 = 0; cy1 = 0; }                       // one pseudo-row holding the whole table
+    const int32_t* __restrict__ start = g->seg_start;
+    const int32_t* __restrict__ items = g->seg_items;
+    int tests = 0;
+    for (int cy = cy0; cy <= cy1; ++cy) {
+        int j = cull ? __ldg(start + cy * nx + cx0) : 0;
+        const int e = cull ? __ldg(start + cy * nx + cx1 + 1) : M;
+        for (j += first; j < e; j += stride) {
+            double ox, oy, r, K;
+            load_obst(tab, cull ? __ldg(items + j) : j, ox, oy, r, K);
             ++tests;
-            hit |= seg_hits_circle(sg, ox, oy, r, K);
+            if (seg_hits_circle(sg, ox, oy, r, K)) return (tests << 1) | 1;
         }
     }
-    return __any_sync(kFull, hit);
+    return tests << 1;
 }
 
-// Map.is_occupied_c for ONE point held by every lane
+// Map.is_occupied_c for ONE point held by every lane of the warp
 __device__ __forceinline__ bool point_occupied_warp(const Obst& ob, double px, double py, double node_radius, int lane,
                                                     long long& tests) {
-    double ox, oy, r, K;
+    const bool cull = ob.full_cells > 0;
+    int j = 0, e = ob.M;
+    if (cull) {
+        const rrtfnd_obst_grid_t* g = ob.g;
+        const int c = grid_cell(py, g->y0, g->inv_cell, g->ny) * g->nx + grid_cell(px, g->x0, g->inv_cell, g->nx);
+        j = __ldg(g->pt_start + c);
+        e = __ldg(g->pt_start + c + 1);
+    }
     bool occ = false;
-    if (ob.use_grid) {
-        const int c = grid_cell(py, ob.g.y0, ob.g.inv_cell, ob.g.ny) * ob.g.nx + grid_cell(px, ob.g.x0, ob.g.inv_cell, ob.g.nx);
-        const int b = __ldg(ob.g.pt_start + c), e = __ldg(ob.g.pt_start + c + 1);
-        for (int j = b + lane; j < e; j += 32) {
-            load_obst(ob.tab, __ldg(ob.g.pt_items + j), ox, oy, r, K);
-            ++tests;
-            occ |= point_in_inflated(px, py, ox, oy, r, node_radius);
-        }
-    } else {
-        for (int j = lane; j < ob.M; j += 32) {
-            load_obst(ob.tab, j, ox, oy, r, K);
-            ++tests;
-            occ |= point_in_inflated(px, py, ox, oy, r, node_radius);
-        }
+    for (j += lane; j < e; j += 32) {
+        double ox, oy, r, K;
+        load_obst(ob.tab, cull ? __ldg(ob.g->pt_items + j) : j, ox, oy, r, K);
+        ++tests;
+        occ |= point_in_inflated(px, py, ox, oy, r, node_radius);
     }
     return __any_sync(kFull, occ);
-}
-
-
-// Obst for a kernel: obstacle table + grid; bounding boxes covering more cells than `full_cells` are cheaper to
-// test against the whole table (cells overlap, so their lists repeat circles).
-__device__ __forceinline__ Obst make_obst(const double* obst, int n_obst, const rrtfnd_obst_grid_t& grid) {
-    Obst ob;
-    ob.tab = reinterpret_cast<const double2*>(obst);
-    ob.g = grid;
-    ob.M = n_obst;
-    ob.use_grid = grid.nx > 0 && grid.seg_start != nullptr && n_obst > 0;
-    ob.full_cells = 0;
-    if (ob.use_grid) {
-        const int ncells = grid.nx * grid.ny;
-        const int n_items = __ldg(grid.seg_start + ncells);
-        ob.full_cells = (int)(((long long)n_obst * ncells) / (n_items > 0 ? n_items : 1));
-        if (ob.full_cells < 1) ob.full_cells = 1;
-    }
-    return ob;
 }
 
 }  // namespace rrtfnd

@@ -95,21 +95,18 @@ __global__ void __launch_bounds__(256) points_occupied_kernel(const double* __re
 __global__ void __launch_bounds__(128) edges_vs_circles_grid_kernel(const double* __restrict__ p1x, const double* __restrict__ p1y,
                                                                     const double* __restrict__ p2x, const double* __restrict__ p2y,
                                                                     long long n_edges, const double* __restrict__ obst, int M,
-                                                                    const rrtfnd_obst_grid_t grid, uint8_t* __restrict__ out_hit) {
-    const Obst ob = make_obst(obst, M, grid);
-    long long tests = 0;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
-        const double ay = p1y[e], by = p2y[e];
-        const Seg sg = make_seg(p1x[e], ay, p2x[e], by);
-        out_hit[e] = seg_blocked_lane(ob, sg, ay, by, tests) ? 1 : 0;
-    }
+                                                                    const __grid_constant__ rrtfnd_obst_grid_t grid,
+                                                                    uint8_t* __restrict__ out_hit) {
+    const Obst ob = make_obst(obst, M, &grid);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x)
+        out_hit[e] = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, p1x[e], p1y[e], p2x[e], p2y[e], 0, 1) & 1;
 }
 
 __global__ void __launch_bounds__(128) points_occupied_grid_kernel(const double* __restrict__ px, const double* __restrict__ py,
                                                                    long long n_points, const double* __restrict__ obst, int M,
-                                                                   const rrtfnd_obst_grid_t grid, double node_radius,
-                                                                   uint8_t* __restrict__ out) {
-    const Obst ob = make_obst(obst, M, grid);
+                                                                   const __grid_constant__ rrtfnd_obst_grid_t grid,
+                                                                   double node_radius, uint8_t* __restrict__ out) {
+    const Obst ob = make_obst(obst, M, &grid);
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     long long tests = 0;

@@ -25,21 +25,24 @@
 #include "cull.cuh"
 #include "grid.cuh"
 #include "rng.cuh"
+#include "stream.cuh"
 
 namespace rrtfnd {
 
 constexpr int kReserveWords = 64;   // must equal RESERVE_WORDS in _structs.py / ORC_RESERVE_WORDS
-constexpr int kStage = 64;          // near-set slots staged per warp between chunk flushes
+constexpr int kStage = 160;         // slots staged per warp: < 32 left over + one 128-node block of the scan
 constexpr int kIntMax = 0x7fffffff;
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline int bitmap_words(const rrtfnd_params_t& prm) { return prm.capacity / 32 + 1; }
 
-// shared memory of one warp: stage[kStage] | rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | (FN only) live bitmap + its prefix counts
-__host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm) {
-    size_t o = kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
+// shared memory of one warp: xy ring (n_stages tiles) | mbarriers | word source | stage[kStage] |
+// rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | (FN only) live bitmap + prefix counts
+__host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
+    size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) + kStage * 4 +
+               align_up((size_t)prm.near_cap * 4, 16);
     if (prm.mode == RRTFND_MODE_FN) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
-    return o;
+    return align_up(o, 128);
 }
 
 // ------------------------------------------------------------------------------------ warp helpers
@@ -83,8 +86,64 @@ __device__ __forceinline__ double path_cost(const int32_t* parent, const double*
     return cost;
 }
 
+// ---- rare paths, kept out of line so that the per-iteration code stays small ---------------------------------
+
+// Stable in-place compaction of a planner's slot arrays (FN only, when the slot array is full of tombstones).
+static __device__ __noinline__ void compact_tree(double2* XY, double* ECOST, int32_t* PARENT, int32_t* NCHILD, int32_t* ID,
+                                                 uint8_t* NFLAG, int32_t* FINISH, int n_finish, int n_slots, uint32_t* bm,
+                                                 uint32_t* pre, int* root_slot, int* best_leaf_slot, int lane) {
+    const int nwords = (n_slots + 31) >> 5;
+    for (int w = 0; w < nwords; ++w) {
+        const int s = w * 32 + lane;
+        const unsigned b = __ballot_sync(kFull, s < n_slots && ID[s] >= 0);
+        if (lane == 0) bm[w] = b;
+    }
+    __syncwarp();
+    if (lane == 0) { int run = 0; for (int w = 0; w < nwords; ++w) { pre[w] = run; run += __popc(bm[w]); } }
+    __syncwarp();
+    auto rank = [&](int s) { return (int)pre[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31)) - 1u)); };
+    for (int base = 0; base < n_slots; base += 32) {
+        const int s = base + lane;
+        const bool alive = s < n_slots && ((bm[s >> 5] >> (s & 31)) & 1u);
+        double2 v = make_double2(0.0, 0.0); double ve = 0; int vp = -1, vn = 0, vi = -1; uint8_t vf = 0;
+        if (alive) {
+            v = XY[s]; ve = ECOST[s]; vp = PARENT[s]; vn = NCHILD[s]; vi = ID[s]; vf = NFLAG[s];
+            if (vp >= 0) vp = rank(vp);
+        }
+        __syncwarp();   // the whole row is read before any of it is overwritten (destinations are <= sources)
+        if (alive) {
+            const int d = rank(s);
+            XY[d] = v; ECOST[d] = ve; PARENT[d] = vp; NCHILD[d] = vn; ID[d] = vi; NFLAG[d] = vf;
+        }
+        __syncwarp();
+    }
+    for (int f = lane; f < n_finish; f += 32) FINISH[f] = rank(FINISH[f]);
+    *root_slot = rank(*root_slot);
+    if (*best_leaf_slot >= 0) *best_leaf_slot = rank(*best_leaf_slot);
+    __syncwarp();
+}
+
+// Is any vertex bit-identical to q? (only reached when a squared distance underflowed to 0 without equality)
+static __device__ __noinline__ bool any_exact_match(const double2* XY, int n_slots, double qx, double qy, int lane) {
+    bool exact = false;
+    for (int s = lane; s < n_slots; s += 32) { const double2 t = XY[s]; exact |= (t.x == qx && t.y == qy); }
+    return __any_sync(kFull, exact);
+}
+
+// Rank of key (vd, vs) among the nodes in (d2, slot) order = the number of k-NN queries the reference makes (:683-697)
+static __device__ __noinline__ int key_rank(const double2* XY, int n_slots, double qx, double qy, double vd, int vs, int lane) {
+    int rank = 0;
+    for (int base = 0; base < n_slots; base += 32) {
+        const int s = base + lane;
+        bool le = false;
+        if (s < n_slots) { const double2 t = XY[s]; const double d = dist2(t.x, t.y, qx, qy); le = d < vd || (d == vd && s <= vs); }
+        rank += __popc(__ballot_sync(kFull, le));
+    }
+    return rank;
+}
+
 template <int WPB>
-__global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) {
+__global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int p = blockIdx.x * WPB + wib;
@@ -105,13 +164,20 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
     rrtfnd_trace_t* TRACE = bt.trace ? bt.trace + (size_t)p * prm.trace_cap : nullptr;
 
     // per-warp shared memory
-    unsigned char* ws = smem + (size_t)wib * warp_smem_bytes(prm);
-    int* stage = reinterpret_cast<int*>(ws);
+    const int n_stages = prm.reserved;                 // resolved by the host wrapper (2 or 4)
+    unsigned char* ws = smem + (size_t)wib * warp_smem_bytes(prm, n_stages);
+    unsigned char* wp = ws + (size_t)n_stages * kTileBytes;
+    XYStream xs;
+    stream_init(xs, ws, wp, n_stages, lane);
+    wp += align_up((size_t)n_stages * 8, 16);
+    WordSrc& rng = *reinterpret_cast<WordSrc*>(wp);    // identical values written by every lane
+    wp += align_up(sizeof(WordSrc), 16);
+    int* stage = reinterpret_cast<int*>(wp);
     int* rwlist = stage + kStage;
-    uint32_t* bm = reinterpret_cast<uint32_t*>(ws + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16));
+    uint32_t* bm = reinterpret_cast<uint32_t*>(rwlist + align_up((size_t)prm.near_cap * 4, 16) / 4);
     uint32_t* pre = bm + align_up((size_t)bitmap_words(prm) * 4, 16) / 4;
 
-    const Obst ob = make_obst(bt.obst, prm.n_obst, bt.grid);
+    const Obst ob = make_obst(bt.obst, prm.n_obst, &bt.grid);
 
     // ---- planner state: warp-uniform, replicated in the registers of every lane
     const double gx = PL->goal_x, gy = PL->goal_y;
@@ -124,12 +190,12 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
     int n_compactions = PL->n_compactions;
     long long my_hops = 0, my_tests = 0;     // per-lane counters, summed at the end
 
-    WordSrc rng;                              // identical in every lane
     rng.mode = prm.stream_mode;
     rng.words = bt.words ? bt.words + (size_t)p * prm.words_per_planner : nullptr;
     rng.n_words = prm.words_per_planner;
     rng.seed = PL->seed; rng.stream = PL->stream_id; rng.cursor = PL->cursor;
     rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0;
+    __syncwarp();
 
     // slot of the cached best path's leaf (ids ascend with slots: binary search around tombstones)
     int best_leaf_slot = -1;
@@ -171,37 +237,9 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
         if (n_slots >= C) {
             if (n_live >= n_slots) { status = RRTFND_ST_CAPACITY; break; }
             // ---- A'. stable in-place compaction (FN only; rare)
-            const int nwords = (n_slots + 31) >> 5;
-            for (int w = 0; w < nwords; ++w) {
-                const int s = w * 32 + lane;
-                const unsigned b = __ballot_sync(kFull, s < n_slots && ID[s] >= 0);
-                if (lane == 0) bm[w] = b;
-            }
-            __syncwarp();
-            if (lane == 0) { int run = 0; for (int w = 0; w < nwords; ++w) { pre[w] = run; run += __popc(bm[w]); } }
-            __syncwarp();
-            auto rank = [&](int s) { return (int)pre[s >> 5] + __popc(bm[s >> 5] & ((1u << (s & 31)) - 1u)); };
-            for (int base = 0; base < n_slots; base += 32) {
-                const int s = base + lane;
-                const bool alive = s < n_slots && ((bm[s >> 5] >> (s & 31)) & 1u);
-                double2 v = nan2; double ve = 0; int vp = -1, vn = 0, vi = -1; uint8_t vf = 0;
-                if (alive) {
-                    v = XY[s]; ve = ECOST[s]; vp = PARENT[s]; vn = NCHILD[s]; vi = ID[s]; vf = NFLAG[s];
-                    if (vp >= 0) vp = rank(vp);
-                }
-                __syncwarp();   // the whole row is read before any of it is overwritten (destinations are <= sources)
-                if (alive) {
-                    const int d = rank(s);
-                    XY[d] = v; ECOST[d] = ve; PARENT[d] = vp; NCHILD[d] = vn; ID[d] = vi; NFLAG[d] = vf;
-                }
-                __syncwarp();
-            }
-            for (int f = lane; f < n_finish; f += 32) FINISH[f] = rank(FINISH[f]);
-            root_slot = rank(root_slot);
-            if (best_leaf_slot >= 0) best_leaf_slot = rank(best_leaf_slot);
+            compact_tree(XY, ECOST, PARENT, NCHILD, ID, NFLAG, FINISH, n_finish, n_slots, bm, pre, &root_slot, &best_leaf_slot, lane);
             n_slots = n_live;
             ++n_compactions;
-            __syncwarp();
         }
         ++attempts;
         // Graph.random_node (src/graph.py:96-98)
@@ -224,10 +262,15 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
         int near_slot = -1;
         {
             double bd = CUDART_INF; int bs = kIntMax;
-            for (int base = 0; base < n_slots; base += 128) {
+            const int n_tiles = (n_slots + kTileNodes - 1) / kTileNodes;
+            stream_begin(xs, XY, n_slots, lane);
+            for (int t = 0; t < n_tiles; ++t) {
+                const double2* tile = stream_wait(xs, t);
+                const int base = t * kTileNodes;
                 double2 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
+                for (int u = 0; u < 4; ++u) v[u] = base + 32 * u + lane < n_slots ? tile[32 * u + lane] : nan2;
+                stream_release(xs, XY, n_slots, t, lane);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const double d = dist2(v[u].x, v[u].y, qx, qy);                     // NaN for tombstones / padding
@@ -240,18 +283,16 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
             if (bd == 0.0) {                                                      // G.id_vertex[vertex] hit (:676-678)
                 const double2 e = XY[bs];
                 bool exact = (e.x == qx && e.y == qy);
-                if (!exact) {   // d2 underflowed to 0 without equality: look for a truly identical vertex
-                    for (int s = lane; s < n_slots; s += 32) { const double2 t = XY[s]; exact |= (t.x == qx && t.y == qy); }
-                    exact = __any_sync(kFull, exact);
-                }
+                if (!exact) exact = any_exact_match(XY, n_slots, qx, qy, lane);   // d2 underflowed to 0 without equality
                 if (exact) continue;                                              // rejected at :45
             }
-            // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692)
+            // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692); the warp shares the one segment
             int rounds = 1;
             {
                 const double2 nb = XY[bs];
-                const Seg sg = make_seg(qx, qy, nb.x, nb.y);
-                if (!seg_blocked_warp(ob, sg, qy, nb.y, lane, my_tests)) near_slot = bs;
+                const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, lane, 32);
+                my_tests += r >> 1;
+                if (!__any_sync(kFull, r & 1)) near_slot = bs;
             }
             if (near_slot < 0 && n_live > 1) {
                 double lo_d = bd; int lo_s = bs;                                  // keys <= (lo_d, lo_s) are known to be blocked
@@ -264,22 +305,14 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
                     double vd = CUDART_INF; int vs = kIntMax;                      // this lane's best visible key
                     bool beyond = false;
                     int count = 0;
-                    auto test_chunk = [&](int n) {
-                        if (lane < n) {
-                            const int s = stage[lane];
-                            const double2 nb = XY[s];
-                            const Seg sg = make_seg(qx, qy, nb.x, nb.y);
-                            if (!seg_blocked_lane(ob, sg, qy, nb.y, my_tests)) {
-                                const double d = dist2(nb.x, nb.y, qx, qy);
-                                if (d < vd || (d == vd && s < vs)) { vd = d; vs = s; }
-                            }
-                        }
-                        __syncwarp();
-                    };
-                    for (int base = 0; base < n_slots; base += 128) {
+                    stream_begin(xs, XY, n_slots, lane);
+                    for (int t = 0; t < n_tiles; ++t) {
+                        const double2* tile = stream_wait(xs, t);
+                        const int base = t * kTileNodes;
                         double2 v[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
+                        for (int u = 0; u < 4; ++u) v[u] = base + 32 * u + lane < n_slots ? tile[32 * u + lane] : nan2;
+                        stream_release(xs, XY, n_slots, t, lane);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int s = base + 32 * u + lane;
@@ -287,35 +320,41 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
                             beyond |= d > T;
                             const bool in = (d > lo_d || (d == lo_d && s > lo_s)) && d <= T;
                             const unsigned m = __ballot_sync(kFull, in);
-                            if (m) {
-                                if (in) stage[count + __popc(m & lt_mask)] = s;
-                                count += __popc(m);
-                                if (count >= 32) {
-                                    __syncwarp();
-                                    test_chunk(32);
-                                    const int rem = count - 32;
-                                    const int t = lane < rem ? stage[32 + lane] : 0;
-                                    __syncwarp();
-                                    if (lane < rem) stage[lane] = t;
-                                    count = rem;
+                            if (in) stage[count + __popc(m & lt_mask)] = s;
+                            count += __popc(m);
+                        }
+                        const bool last = base + 128 >= n_slots;
+                        int head = 0;
+                        while (count - head >= 32 || (last && count > head)) {     // one lane per staged segment
+                            const int n = min(count - head, 32);
+                            __syncwarp();
+                            if (lane < n) {
+                                const int s = stage[head + lane];
+                                const double2 nb = XY[s];
+                                const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, 0, 1);
+                                my_tests += r >> 1;
+                                if (!(r & 1)) {
+                                    const double d = dist2(nb.x, nb.y, qx, qy);
+                                    if (d < vd || (d == vd && s < vs)) { vd = d; vs = s; }
                                 }
                             }
+                            __syncwarp();
+                            head += n;
+                        }
+                        if (head > 0) {                                           // keep the (< 32) leftover at the front
+                            const int rem = count - head;
+                            const int t = lane < rem ? stage[head + lane] : 0;
+                            __syncwarp();
+                            if (lane < rem) stage[lane] = t;
+                            count = rem;
+                            __syncwarp();
                         }
                     }
-                    if (count > 0) { __syncwarp(); test_chunk(count); }
                     n_scan_nodes += n_live;
                     warp_argmin(vd, vs);
                     if (vs != kIntMax) {
                         near_slot = vs;
-                        // the reference's query count = rank of the winner in (d2, slot) order
-                        int rank = 0;
-                        for (int base = 0; base < n_slots; base += 32) {
-                            const int s = base + lane;
-                            bool le = false;
-                            if (s < n_slots) { const double2 t = XY[s]; const double d = dist2(t.x, t.y, qx, qy); le = d < vd || (d == vd && s <= vs); }
-                            rank += __popc(__ballot_sync(kFull, le));
-                        }
-                        rounds = rank;
+                        rounds = key_rank(XY, n_slots, qx, qy, vd, vs, lane);
                         break;
                     }
                     if (!__any_sync(kFull, beyond)) break;                        // every node tried, none visible
@@ -387,6 +426,7 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
         bool dup = false;
         double cost_new = 0.0;
         const int n_pass = commit_cp ? 2 : 1;          // committing choose-parent needs its result before any rewire decision
+#pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
             const bool do_cp = eval_cp && pass == 0;
             const bool do_rw = pass == n_pass - 1;
@@ -396,75 +436,81 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
             bool first = true;
             int count = 0;
             k_total = 0;
-
-            auto process = [&](int n) {
-                int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
-                if (lane < n) {
-                    s = stage[lane];
-                    const double2 v = XY[s];
-                    dpl = dist_plain(v.x, v.y, px, py);                           // :842 / :899
-                    if (dpl == 0.0 && v.x == px && v.y == py) dup = true;         // src/graph.py:54-56 corner (B9)
-                    const Seg sg = make_seg(v.x, v.y, px, py);                    // Line(node, q_new): p1 = node (:846 / :903)
-                    hit = seg_blocked_lane(ob, sg, v.y, py, my_tests);
-                    if (!hit) cc = chain_walk(PARENT, ECOST, s, 0.0, my_hops);   // Graph.get_cost(id) (:848 / :905)
-                } else if (first && lane == 31) {
-                    cc = chain_walk(PARENT, ECOST, walk_from, walk_acc, my_hops); // Graph.get_cost(id_new)
-                }
-                __syncwarp();
-                if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; }
-                if (do_cp) {
-                    // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
-                    unsigned open = __ballot_sync(kFull, lane < n && !hit);
-                    while (open) {
-                        const int i = __ffs(open) - 1;
-                        open &= open - 1;
-                        const double ci = __shfl_sync(kFull, cc, i), di = __shfl_sync(kFull, dpl, i);
-                        if (cp_cn > dadd(ci, di)) {
-                            cp_slot = __shfl_sync(kFull, s, i); cp_cost = di;
-                            // G.cost[id_new] = cost, parent untouched: the chain is still id_near's (:849)
-                            cp_cn = chain_walk(PARENT, ECOST, near_slot, di, my_hops);
-                        }
-                    }
-                }
-                if (do_rw) {
-                    const bool rw = lane < n && !hit && cc > dadd(cost_new, dpl);   // :905, strict
-                    const unsigned m = __ballot_sync(kFull, rw);
-                    if (m) {   // remember the decision: short list in shared memory, overflow as a per-node flag bit
-                        const int pos = n_rw + __popc(m & lt_mask);
-                        if (rw) { if (pos < prm.near_cap) rwlist[pos] = s; else NFLAG[s] |= 2; }
-                        n_rw += __popc(m);
-                    }
-                }
-                first = false;
-                __syncwarp();
-            };
-
-            for (int base = 0; base < n_slots; base += 128) {
+            const int n_tiles = (n_slots + kTileNodes - 1) / kTileNodes;
+            stream_begin(xs, XY, n_slots, lane);
+            for (int t = 0; t < n_tiles; ++t) {
+                const double2* tile = stream_wait(xs, t);
+                const int base = t * kTileNodes;
                 double2 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; v[u] = s < n_slots ? XY[s] : nan2; }
+                for (int u = 0; u < 4; ++u) v[u] = base + 32 * u + lane < n_slots ? tile[32 * u + lane] : nan2;
+                stream_release(xs, XY, n_slots, t, lane);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int s = base + 32 * u + lane;
                     const bool in = dist2(v[u].x, v[u].y, px, py) <= r2 && s != new_slot;
                     const unsigned m = __ballot_sync(kFull, in);
-                    if (m) {
-                        if (in) stage[count + __popc(m & lt_mask)] = s;
-                        count += __popc(m); k_total += __popc(m);
-                        const int cap = first ? 31 : 32;
-                        if (count >= cap) {
-                            __syncwarp();
-                            process(cap);
-                            const int rem = count - cap;                           // < 32
-                            const int t = lane < rem ? stage[cap + lane] : 0;
-                            __syncwarp();
-                            if (lane < rem) stage[lane] = t;
-                            count = rem;
+                    if (in) stage[count + __popc(m & lt_mask)] = s;
+                    count += __popc(m); k_total += __popc(m);
+                }
+                const bool last = base + 128 >= n_slots;
+                int head = 0;
+                while (count - head >= (first ? 31 : 32) || (last && count > head)) {
+                    const int n = min(count - head, first ? 31 : 32);
+                    __syncwarp();
+                    // ---- one chunk: lane i < n owns candidate i; in the first chunk lane 31 walks the new node's chain
+                    int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
+                    int w_from = -1; double w_acc = 0.0;
+                    if (lane < n) {
+                        s = stage[head + lane];
+                        const double2 c = XY[s];
+                        dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
+                        if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
+                        // Line(node, q_new): p1 = node (:846 / :903)
+                        const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
+                        my_tests += r >> 1;
+                        hit = r & 1;
+                        if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
+                    } else if (first && lane == 31) { w_from = walk_from; w_acc = walk_acc; }   // Graph.get_cost(id_new)
+                    if (w_from >= 0) cc = chain_walk(PARENT, ECOST, w_from, w_acc, my_hops);
+                    __syncwarp();
+                    if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; }
+                    if (do_cp) {
+                        // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
+                        unsigned open = __ballot_sync(kFull, lane < n && !hit);
+                        while (open) {
+                            const int i = __ffs(open) - 1;
+                            open &= open - 1;
+                            const double ci = __shfl_sync(kFull, cc, i), di = __shfl_sync(kFull, dpl, i);
+                            if (cp_cn > dadd(ci, di)) {
+                                cp_slot = __shfl_sync(kFull, s, i); cp_cost = di;
+                                // G.cost[id_new] = cost, parent untouched: the chain is still id_near's (:849)
+                                cp_cn = chain_walk(PARENT, ECOST, near_slot, di, my_hops);
+                            }
                         }
                     }
+                    if (do_rw) {
+                        const bool rw = lane < n && !hit && cc > dadd(cost_new, dpl);   // :905, strict
+                        const unsigned m = __ballot_sync(kFull, rw);
+                        if (m) {   // remember the decision: short list in shared memory, overflow as a per-node flag bit
+                            const int pos = n_rw + __popc(m & lt_mask);
+                            if (rw) { if (pos < prm.near_cap) rwlist[pos] = s; else NFLAG[s] |= 2; }
+                            n_rw += __popc(m);
+                        }
+                    }
+                    first = false;
+                    __syncwarp();
+                    head += n;
+                }
+                if (head > 0) {                                                   // keep the (< 32) leftover at the front
+                    const int rem = count - head;
+                    const int t = lane < rem ? stage[head + lane] : 0;
+                    __syncwarp();
+                    if (lane < rem) stage[lane] = t;
+                    count = rem;
+                    __syncwarp();
                 }
             }
-            if (count > 0) { __syncwarp(); process(count); }
 
             if (pass == 0 && commit_cp && k_total > 0) {   // EXTENSION (not the shipped behaviour): adopt the returned edge
                 if (lane == 0) { PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost; }
@@ -667,7 +713,7 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 template <int WPB>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
-    const size_t bytes = warp_smem_bytes(*prm) * WPB;
+    const size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
     auto kern = plan_kernel<WPB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -676,14 +722,17 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
     return (int)cudaGetLastError();
 }
 
-// Warps (= planners) per CTA. prm->reserved makes an explicit choice (1, 2, 4 or 8); 0 = automatic: one planner
-// per CTA spreads a small batch evenly over the SMs (an SM holds at most 32 CTAs), larger batches need more warps
-// per CTA to reach the SM's warp limit.
-static int choose_wpb(const rrtfnd_params_t& prm, int n_planners) {
-    if (prm.reserved == 1 || prm.reserved == 2 || prm.reserved == 4 || prm.reserved == 8) return prm.reserved;
+// Launch geometry. prm->reserved = warps (= planners) per CTA (1, 2, 4, 8) + 16 * xy-ring stages (2 or 4); a zero
+// field = automatic: one planner per CTA spreads a small batch evenly over the SMs (an SM holds at most 32 CTAs),
+// larger batches need more warps per CTA to reach the SM's warp limit; few resident warps get the deeper ring.
+struct PlanCfg { int wpb, stages; };
+static PlanCfg choose_cfg(const rrtfnd_params_t& prm, int n_planners) {
+    PlanCfg c{prm.reserved & 15, (prm.reserved >> 4) & 15};
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return n_planners <= 32 * sms ? 1 : 2;
+    if (c.wpb != 1 && c.wpb != 2 && c.wpb != 4 && c.wpb != 8) c.wpb = n_planners <= 32 * sms ? 1 : 2;
+    if (c.stages != 2 && c.stages != 4) c.stages = n_planners <= 16 * sms ? 4 : 2;
+    return c;
 }
 
 }  // namespace rrtfnd
@@ -706,7 +755,7 @@ static int check_params(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
 
 extern "C" int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm) {
     if (!prm) return RRTFND_E_BADARG;
-    const size_t b = warp_smem_bytes(*prm);
+    const size_t b = warp_smem_bytes(*prm, 4);
     return b <= kMaxSmem ? (int64_t)b : (int64_t)RRTFND_E_SMEM;
 }
 
@@ -718,7 +767,9 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     rrtfnd_batch_t b = *bt;
     if (!(q.flags & RRTFND_FLAG_TRACE)) b.trace = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (choose_wpb(q, b.n_planners)) {
+    const PlanCfg cfg = choose_cfg(q, b.n_planners);
+    q.reserved = cfg.stages;                    // the kernel reads its ring depth here
+    switch (cfg.wpb) {
         case 1: return launch_plan<1>(&q, &b, st);
         case 2: return launch_plan<2>(&q, &b, st);
         case 4: return launch_plan<4>(&q, &b, st);

@@ -23,11 +23,11 @@ struct WordSrc {
     bool have_blk, exhausted;
 };
 
-__device__ __forceinline__ void philox4x32_10(unsigned long long blk, unsigned long long stream,
-                                              unsigned long long seed, uint32_t out[4]) {
+// One Philox4x32-10 block. Not inlined: the ten rounds exist once in the kernel however many draws it makes.
+static __device__ __noinline__ uint4 philox4x32_10(unsigned long long blk, unsigned long long stream, unsigned long long seed) {
     uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -36,10 +36,12 @@ __device__ __forceinline__ void philox4x32_10(unsigned long long blk, unsigned l
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    return make_uint4(c0, c1, c2, c3);
 }
 
-__device__ __forceinline__ uint32_t next_word(WordSrc& r) {
+// The word source of a planner lives in shared memory (one copy per warp, every lane reads and writes the same
+// values), so drawing a word is an ordinary call instead of a block of code inlined at every draw.
+static __device__ __noinline__ uint32_t next_word(WordSrc& r) {
     const unsigned long long i = r.cursor++;
     if (r.mode == RRTFND_STREAM_WORDS) {
         if ((long long)i >= r.n_words) { r.exhausted = true; return 0u; }
@@ -47,9 +49,8 @@ __device__ __forceinline__ uint32_t next_word(WordSrc& r) {
     }
     const unsigned long long b = i >> 2;
     if (!r.have_blk || b != r.blk_idx) {
-        uint32_t o[4];
-        philox4x32_10(b, r.stream, r.seed, o);
-        r.b0 = o[0]; r.b1 = o[1]; r.b2 = o[2]; r.b3 = o[3];
+        const uint4 o = philox4x32_10(b, r.stream, r.seed);
+        r.b0 = o.x; r.b1 = o.y; r.b2 = o.z; r.b3 = o.w;
         r.blk_idx = b;
         r.have_blk = true;
     }
