@@ -84,7 +84,7 @@ class PlannerBatch:
             (FLAG_TRACE if trace else 0)
         prm.trace_cap = int(iter_num) + 1 if trace else 0
         prm.max_attempts = int(max_attempts)
-        prm.reserved = int(launch)   # planners (warps) per CTA (1, 2, 4, 8) + 16 * xy-ring stages (2, 4); 0 fields = automatic
+        prm.reserved = int(launch)   # planners per CTA (1, 2, 4) + 16 * xy-ring stages (2, 4) + 256 * resident warps per SM (16, 24, 32); 0 fields = automatic
         prm.step_length, prm.radius, prm.node_radius, prm.bias = float(step_length), float(radius or 0.0), \
             float(node_radius), float(bias)
         (prm.x_lo, prm.x_hi), (prm.y_lo, prm.y_hi) = [(float(a), float(b)) for a, b in xy_range]

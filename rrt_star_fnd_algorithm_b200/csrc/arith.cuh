@@ -18,6 +18,8 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 // has about twenty call sites and must fit the instruction cache (see profiles/).
 static __device__ __noinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 static __device__ __noinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+// two quotients over one divisor: the two Newton chains are independent and interleave inside one body
+static __device__ __noinline__ double2 ddiv2(double n1, double n2, double d) { return make_double2(__ddiv_rn(n1, d), __ddiv_rn(n2, d)); }
 
 // calc_distance (src/algorithm.py:954-961): np.linalg.norm(p - q) = sqrt(ddot(v, v)); OpenBLAS' ddot tail
 // loop is FMA-contracted, i.e. sqrt(fma(dy, dy, fl(dx*dx))).
@@ -73,9 +75,8 @@ __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double 
     const double delta = dsub(dmul(b, b), dmul(s.a4, c));                       // :620
     if (!(delta >= 0.0)) return false;                                          // :569 (NaN -> no hit as well)
     const double sq = dsqrt(delta);                                             // :602-603
-    const double x1 = ddiv(dadd(-b, sq), s.a2);
-    const double x2 = ddiv(dsub(-b, sq), s.a2);
-    return (x1 > s.lo && x1 < s.hi) || (x2 > s.lo && x2 < s.hi);                // :576, :632-635
+    const double2 x = ddiv2(dadd(-b, sq), dsub(-b, sq), s.a2);                  // x1, x2 (:602-603)
+    return (x.x > s.lo && x.x < s.hi) || (x.y > s.lo && x.y < s.hi);                // :576, :632-635
 }
 
 // Map.is_occupied_c for one circle (src/map.py:44-45)

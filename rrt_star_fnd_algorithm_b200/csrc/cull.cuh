@@ -19,9 +19,8 @@ namespace rrtfnd {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// What a kernel needs to test obstacles: the table, the grid (pointer to the kernel's __grid_constant__ parameter or
-// to any other copy) and the cell-count limit above which a bounding box is cheaper to test against the whole table
-// (cells overlap, so their lists repeat circles).
+// What a kernel needs to test obstacles: the table and the grid (pointer to the kernel's __grid_constant__ parameter
+// or to any other copy); full_cells > 0 says that the grid is usable.
 struct Obst {
     const double2* tab;               // [M][2]: (ox, oy), (r, K)
     const rrtfnd_obst_grid_t* g;
@@ -56,25 +55,43 @@ static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, 
                                         int full_cells, double p1x, double p1y, double p2x, double p2y, int first,
                                         int stride) {
     const Seg sg = make_seg(p1x, p1y, p2x, p2y);
-    int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, nx = 0;
-    bool cull = false;
+    int cy0 = 0, cy1 = 0, nx = 0;
+    double x0 = 0, y0 = 0, inv = 0, cell = 0, slack = 0, dxdy = 0;
+    const double ylo = p1y < p2y ? p1y : p2y, yhi = p1y < p2y ? p2y : p1y;
+    bool cull = false, flat = true;
     if (full_cells > 0 && !sg.vertical && fabs(sg.m) <= g->slope_max) {
-        const double x0 = g->x0, y0 = g->y0, inv = g->inv_cell;
+        x0 = g->x0; y0 = g->y0; inv = g->inv_cell;
         nx = g->nx;
-        const int ny = g->ny;
-        cx0 = grid_cell(sg.lo, x0, inv, nx);
-        cx1 = grid_cell(sg.hi, x0, inv, nx);
-        cy0 = grid_cell(p1y < p2y ? p1y : p2y, y0, inv, ny);
-        cy1 = grid_cell(p1y < p2y ? p2y : p1y, y0, inv, ny);
-        cull = (cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= full_cells;
+        cy0 = grid_cell(ylo, y0, inv, g->ny);
+        cy1 = grid_cell(yhi, y0, inv, g->ny);
+        // A circle that can hit lies within r + margin of the SEGMENT (not merely of its bounding box), so its
+        // inflated box contains the segment's closest point and the cell of that point lists it: only cells the
+        // segment passes through need to be visited. Per row of cells the segment's x-extent is computed in ordinary
+        // floating point and widened by `slack`, far more than its rounding error (a few ulps of the coordinates).
+        cell = 1.0 / inv;
+        slack = g->coord_max * 1e-9;
+        dxdy = (p2x - p1x) / (p2y - p1y);
+        flat = !(fabs(dxdy) < 1e300);                       // (nearly) horizontal: every row gets the whole x-range
+        cull = true;
     }
     if (!cull) { cy0 = 0; cy1 = 0; }                       // one pseudo-row holding the whole table
     const int32_t* __restrict__ start = g->seg_start;
     const int32_t* __restrict__ items = g->seg_items;
     int tests = 0;
     for (int cy = cy0; cy <= cy1; ++cy) {
-        int j = cull ? __ldg(start + cy * nx + cx0) : 0;
-        const int e = cull ? __ldg(start + cy * nx + cx1 + 1) : M;
+        int j = 0, e = M;
+        if (cull) {
+            double xa = sg.lo, xb = sg.hi;
+            if (cy1 > cy0 && !flat) {                       // the part of the segment inside this row's y-interval
+                const double ra = fmax(y0 + cy * cell - slack, ylo), rb = fmin(y0 + (cy + 1) * cell + slack, yhi);
+                const double xs = p1x + (ra - p1y) * dxdy, xe = p1x + (rb - p1y) * dxdy;
+                xa = fmax(sg.lo, fmin(xs, xe) - slack);
+                xb = fmin(sg.hi, fmax(xs, xe) + slack);
+            }
+            const int cx0 = grid_cell(xa, x0, inv, nx), cx1 = grid_cell(xb, x0, inv, nx);
+            j = __ldg(start + cy * nx + cx0);
+            e = __ldg(start + cy * nx + cx1 + 1);
+        }
         for (j += first; j < e; j += stride) {
             double ox, oy, r, K;
             load_obst(tab, cull ? __ldg(items + j) : j, ox, oy, r, K);

@@ -32,15 +32,16 @@ namespace rrtfnd {
 constexpr int kReserveWords = 64;   // must equal RESERVE_WORDS in _structs.py / ORC_RESERVE_WORDS
 constexpr int kStage = 160;         // slots staged per warp: < 32 left over + one 128-node block of the scan
 constexpr int kIntMax = 0x7fffffff;
+constexpr int kChainCap = 96;       // edge costs of the new node's parent chain cached per warp (choose-parent re-sums them)
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline int bitmap_words(const rrtfnd_params_t& prm) { return prm.capacity / 32 + 1; }
 
-// shared memory of one warp: xy ring (n_stages tiles) | mbarriers | word source | stage[kStage] |
+// shared memory of one warp: xy ring (n_stages tiles) | mbarriers | word source | chain[kChainCap] | stage[kStage] |
 // rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | (FN only) live bitmap + prefix counts
 __host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
-    size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) + kStage * 4 +
-               align_up((size_t)prm.near_cap * 4, 16);
+    size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) +
+               kChainCap * 8 + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
     if (prm.mode == RRTFND_MODE_FN) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
     return align_up(o, 128);
 }
@@ -142,8 +143,10 @@ static __device__ __noinline__ int key_rank(const double2* XY, int n_slots, doub
     return rank;
 }
 
-template <int WPB>
-__global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
+// WPB warps (= planners) per CTA; MINW = resident warps per SM the register allocation must allow (16 -> 128
+// registers, 24 -> 80, 32 -> 64): small batches get registers, large ones get occupancy.
+template <int WPB, int MINW>
+__global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int p = blockIdx.x * WPB + wib;
@@ -172,6 +175,8 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
     wp += align_up((size_t)n_stages * 8, 16);
     WordSrc& rng = *reinterpret_cast<WordSrc*>(wp);    // identical values written by every lane
     wp += align_up(sizeof(WordSrc), 16);
+    double* chain = reinterpret_cast<double*>(wp);     // edge costs along the new node's parent chain, leaf side first
+    wp += kChainCap * 8;
     int* stage = reinterpret_cast<int*>(wp);
     int* rwlist = stage + kStage;
     uint32_t* bm = reinterpret_cast<uint32_t*>(rwlist + align_up((size_t)prm.near_cap * 4, 16) / 4);
@@ -433,6 +438,7 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
             const int walk_from = PARENT[new_slot];
             const double walk_acc = ECOST[new_slot];
             double cp_cn = 0.0;
+            int chain_depth = 0;
             bool first = true;
             int count = 0;
             k_total = 0;
@@ -460,7 +466,7 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
                     __syncwarp();
                     // ---- one chunk: lane i < n owns candidate i; in the first chunk lane 31 walks the new node's chain
                     int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
-                    int w_from = -1; double w_acc = 0.0;
+                    int w_from = -1; const double w_acc = 0.0;
                     if (lane < n) {
                         s = stage[head + lane];
                         const double2 c = XY[s];
@@ -471,10 +477,22 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
                         my_tests += r >> 1;
                         hit = r & 1;
                         if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
-                    } else if (first && lane == 31) { w_from = walk_from; w_acc = walk_acc; }   // Graph.get_cost(id_new)
-                    if (w_from >= 0) cc = chain_walk(PARENT, ECOST, w_from, w_acc, my_hops);
+                    }
+                    int depth = 0;
+                    if (first && lane == 31) {                                    // Graph.get_cost(id_new), remembering the addends
+                        int n = walk_from, q = PARENT[n];
+                        cc = walk_acc;
+                        while (q >= 0) {
+                            const double e = ECOST[n];
+                            if (depth < kChainCap) chain[depth] = e;
+                            cc = dadd(cc, e);
+                            n = q; q = PARENT[n];
+                            ++depth;
+                        }
+                        my_hops += depth;
+                    } else if (w_from >= 0) cc = chain_walk(PARENT, ECOST, w_from, w_acc, my_hops);
                     __syncwarp();
-                    if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; }
+                    if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; chain_depth = __shfl_sync(kFull, depth, 31); }
                     if (do_cp) {
                         // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
                         unsigned open = __ballot_sync(kFull, lane < n && !hit);
@@ -485,7 +503,14 @@ __global__ void __launch_bounds__(32 * WPB) plan_kernel(const rrtfnd_params_t pr
                             if (cp_cn > dadd(ci, di)) {
                                 cp_slot = __shfl_sync(kFull, s, i); cp_cost = di;
                                 // G.cost[id_new] = cost, parent untouched: the chain is still id_near's (:849)
-                                cp_cn = chain_walk(PARENT, ECOST, near_slot, di, my_hops);
+                                if (chain_depth <= kChainCap) {                       // re-sum the cached addends
+                                    cp_cn = di;
+                                    for (int h = 0; h < chain_depth; ++h) cp_cn = dadd(cp_cn, chain[h]);
+                                } else {
+                                    long long h = 0;
+                                    cp_cn = chain_walk(PARENT, ECOST, near_slot, di, h);   // every lane walks the same chain
+                                    if (lane == 0) my_hops += h;
+                                }
                             }
                         }
                     }
@@ -711,28 +736,41 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int WPB>
+template <int WPB, int MINW>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
     const size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
-    auto kern = plan_kernel<WPB>;
+    auto kern = plan_kernel<WPB, MINW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     kern<<<(bt->n_planners + WPB - 1) / WPB, 32 * WPB, bytes, st>>>(*prm, *bt);
     return (int)cudaGetLastError();
 }
 
-// Launch geometry. prm->reserved = warps (= planners) per CTA (1, 2, 4, 8) + 16 * xy-ring stages (2 or 4); a zero
-// field = automatic: one planner per CTA spreads a small batch evenly over the SMs (an SM holds at most 32 CTAs),
-// larger batches need more warps per CTA to reach the SM's warp limit; few resident warps get the deeper ring.
-struct PlanCfg { int wpb, stages; };
+// Launch geometry. prm->reserved = warps (= planners) per CTA (1, 2, 4) + 16 * xy-ring stages (2 or 4) + 256 *
+// resident warps per SM to allocate registers for (16, 24, 32); a zero field = automatic: one planner per CTA spreads
+// a small batch evenly over the SMs (an SM holds at most 32 CTAs), larger batches need more warps per CTA to reach
+// the SM's warp limit; few resident warps get more registers and the deeper ring.
+struct PlanCfg { int wpb, stages, minw; };
 static PlanCfg choose_cfg(const rrtfnd_params_t& prm, int n_planners) {
-    PlanCfg c{prm.reserved & 15, (prm.reserved >> 4) & 15};
+    PlanCfg c{prm.reserved & 15, (prm.reserved >> 4) & 15, (prm.reserved >> 8) & 255};
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (c.wpb != 1 && c.wpb != 2 && c.wpb != 4 && c.wpb != 8) c.wpb = n_planners <= 32 * sms ? 1 : 2;
-    if (c.stages != 2 && c.stages != 4) c.stages = n_planners <= 16 * sms ? 4 : 2;
+    if (c.wpb != 1 && c.wpb != 2 && c.wpb != 4) c.wpb = n_planners <= 32 * sms ? 1 : 2;
+    // measured on B200 (profiles/): trading registers for residency (80 / 64 registers) spills and halves throughput,
+    // and a ring deeper than 2 tiles does not pay once a dozen warps share an SM
+    if (c.minw != 16 && c.minw != 24 && c.minw != 32) c.minw = 16;
+    if (c.stages != 2 && c.stages != 4) c.stages = 2;
     return c;
+}
+
+template <int WPB>
+static int launch_wpb(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, int minw, cudaStream_t st) {
+    switch (minw) {
+        case 16: return launch_plan<WPB, 16>(prm, bt, st);
+        case 24: return launch_plan<WPB, 24>(prm, bt, st);
+        default: return launch_plan<WPB, 32>(prm, bt, st);
+    }
 }
 
 }  // namespace rrtfnd
@@ -770,10 +808,9 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     const PlanCfg cfg = choose_cfg(q, b.n_planners);
     q.reserved = cfg.stages;                    // the kernel reads its ring depth here
     switch (cfg.wpb) {
-        case 1: return launch_plan<1>(&q, &b, st);
-        case 2: return launch_plan<2>(&q, &b, st);
-        case 4: return launch_plan<4>(&q, &b, st);
-        case 8: return launch_plan<8>(&q, &b, st);
+        case 1: return launch_wpb<1>(&q, &b, cfg.minw, st);
+        case 2: return launch_wpb<2>(&q, &b, cfg.minw, st);
+        case 4: return launch_wpb<4>(&q, &b, cfg.minw, st);
         default: return RRTFND_E_BADARG;
     }
 }

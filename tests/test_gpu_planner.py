@@ -115,7 +115,7 @@ def test_resume_after_need_words():
     check_against_golden(b, case, g)
 
 
-@pytest.mark.parametrize("launch", [1, 2 + 16 * 2, 4 + 16 * 4, 8 + 16 * 2])
+@pytest.mark.parametrize("launch", [1 + 256 * 16, 2 + 16 * 2 + 256 * 32, 4 + 16 * 4 + 256 * 24, 1 + 16 * 2 + 256 * 32])
 @pytest.mark.parametrize("grid", [True, False])
 @pytest.mark.parametrize("name", ["dense_fn", "int_star"])
 def test_every_launch_geometry_gives_the_same_tree(name, launch, grid):
