@@ -114,6 +114,7 @@ def oracle_params(w, flags):
     p.stream_mode, p.flags = S.STREAM_PHILOX, flags
     p.step_length, p.radius, p.node_radius, p.bias = w["step_length"], w["radius"], w["node_radius"], w["bias"]
     (p.x_lo, p.x_hi), (p.y_lo, p.y_hi) = w["xy_range"]
+    p.goal_node_radius = w["node_radius"]
     return p
 
 

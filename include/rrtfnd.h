@@ -77,9 +77,10 @@ typedef struct rrtfnd_params {
     int64_t max_attempts;      /* attempts allowed per planner over its lifetime (<=0: unlimited) */
     double step_length;    /* steer() max_length (src/algorithm.py:731) */
     double radius;         /* near-set / rewire radius (:837, :893) */
-    double node_radius;    /* Map.node_radius (src/map.py:45) and goal test 2*node_radius (:758) */
+    double node_radius;    /* Map.node_radius: inflation of Map.is_occupied_c (src/map.py:45) */
     double bias;           /* Graph.random_node bias (src/graph.py:96) */
     double x_lo, x_hi, y_lo, y_hi; /* Graph.xy_range (src/graph.py:98) */
+    double goal_node_radius; /* the planners' own `node_radius` argument: goal test dist < 2 * it (src/algorithm.py:757-758) */
 } rrtfnd_params_t;
 
 /* Per-planner scalars. One entry per planner, device resident, read back by the host. */
@@ -107,6 +108,9 @@ typedef struct rrtfnd_planner {
     int32_t n_removed;         /* total forced removals */
     int32_t solution_found;    /* src/algorithm.py:114 */
     int32_t n_compactions;
+    int32_t fn_count;          /* RRT_star_FN's n_of_nodes (src/algorithm.py:209): 1 + this call's insertions - removals;
+                                  NOT the live count when the Graph already held nodes */
+    int32_t reserved;
 } rrtfnd_planner_t;
 
 /* One record per successful iteration (RRTFND_FLAG_TRACE). */

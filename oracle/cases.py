@@ -98,6 +98,7 @@ def params_for(case, *, flags=None, capacity=None, stream_mode=0, n_words=0, nea
     p.step_length = case["step_length"]
     p.radius = case["radius"] or 0.0
     p.node_radius = case["node_radius"]
+    p.goal_node_radius = case.get("goal_node_radius", case["node_radius"])
     p.bias = case["bias"]
     (p.x_lo, p.x_hi), (p.y_lo, p.y_hi) = case["xy_range"]
     return p

@@ -45,6 +45,7 @@ typedef struct orc_tree {
     uint64_t cursor;
     int64_t n_edge_checks, n_edge_checks_ref, n_circle_tests, n_scan_nodes, n_chain_hops;
     int n_rewired, n_removed;
+    int fn_count;     /* RRT_star_FN's n_of_nodes (src/algorithm.py:209) */
     /* scratch */
     int* cand;
     double* cand_d;
@@ -207,7 +208,7 @@ orc_tree_t* orc_create(int id_capacity, int finish_cap, int path_cap, double sx,
     t->best_cost = INFINITY;
     /* Graph.__init__ (src/graph.py:25-32) */
     t->x[0] = sx; t->y[0] = sy; t->parent[0] = -1; t->ecost[0] = 0.0; t->alive[0] = 1;
-    t->last_id = 0; t->n_live = 1; t->root = 0;
+    t->last_id = 0; t->n_live = 1; t->root = 0; t->fn_count = 1;
     return t;
 }
 
@@ -229,7 +230,7 @@ int orc_load(orc_tree_t* t, int n, const int* ids, const double* x, const double
         t->alive[id] = 1; t->x[id] = x[i]; t->y[id] = y[i]; t->parent[id] = parent[i]; t->ecost[id] = ecost[i];
     }
     for (int i = 0; i < n; ++i) if (parent[i] >= 0) t->nchild[parent[i]]++;
-    t->n_live = n; t->root = root_id; t->last_id = last_id;
+    t->n_live = n; t->root = root_id; t->last_id = last_id; t->fn_count = 1;   /* a loaded tree = a new planner call */
     return 0;
 }
 
@@ -252,7 +253,7 @@ void orc_get_planner(const orc_tree_t* t, rrtfnd_planner_t* p) {
     p->n_slots = t->last_id + 1; p->n_live = t->n_live; p->last_id = t->last_id; p->iter = t->iter;
     p->root_slot = t->root; p->n_finish = t->n_finish; p->best_len = t->best_len; p->status = t->status;
     p->n_rewired = t->n_rewired; p->n_removed = t->n_removed; p->solution_found = t->solution_found;
-    p->n_compactions = 0;
+    p->n_compactions = 0; p->fn_count = t->fn_count; p->reserved = 0;
 }
 
 int orc_get_best_path(const orc_tree_t* t, int* out) {
@@ -397,7 +398,7 @@ int orc_run(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, doubl
         int id_new = ++t->last_id;
         t->x[id_new] = px; t->y[id_new] = py; t->alive[id_new] = 1; t->nchild[id_new] = 0;
         double cost_new_near = dist_fma(px, py, nx, ny);                      /* :49 */
-        t->n_live++;
+        t->n_live++; t->fn_count++;                                           /* n_of_nodes += 1 (:221) */
         t->parent[id_new] = id_near;                                          /* :141-142 */
         t->ecost[id_new] = cost_new_near;
 
@@ -407,7 +408,7 @@ int orc_run(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, doubl
 
         if (prm->mode == RRTFND_MODE_RRT) {
             t->nchild[id_near]++;                                             /* add_edge (:76) */
-            if (dist_fma(px, py, gx, gy) < 2.0 * prm->node_radius) {          /* check_solution (:78) */
+            if (dist_fma(px, py, gx, gy) < 2.0 * prm->goal_node_radius) {          /* check_solution (:78) */
                 t->best_cost = find_path(t, id_new, t->best_path, &t->best_len);
                 if (t->best_len > t->path_cap) { t->status = RRTFND_ST_PATH_CAP; goto out; }
                 t->solution_found = 1;
@@ -469,7 +470,7 @@ int orc_run(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, doubl
         }
 
         /* ---- forced_removal (:233-237, :800-819) */
-        if (prm->mode == RRTFND_MODE_FN && t->n_live > prm->max_nodes) {
+        if (prm->mode == RRTFND_MODE_FN && t->fn_count > prm->max_nodes) {   /* n_of_nodes > max_nodes (:233) */
             int last_in_path = t->best_len > 0 ? t->best_path[0] : -1;
             int n_childless = 0, n_ok = 0;
             for (int i = 0; i <= t->last_id; ++i)
@@ -481,6 +482,7 @@ int orc_run(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, doubl
             int pick = t->cand[rng_randbelow(&rng, (uint32_t)n_childless)];
             while (pick == id_new || pick == last_in_path) pick = t->cand[rng_randbelow(&rng, (uint32_t)n_childless)];
             remove_vertex(t, pick);
+            --t->fn_count;                                                    /* :237 */
             ++t->n_removed;
             tr.removed_id = pick;
             for (int f = 0; f < t->n_finish; ++f)
@@ -492,7 +494,7 @@ int orc_run(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, doubl
         }
 
         /* ---- check_solution (:155-161, :240-243) */
-        if (dist_fma(px, py, gx, gy) < 2.0 * prm->node_radius) {
+        if (dist_fma(px, py, gx, gy) < 2.0 * prm->goal_node_radius) {
             if (t->n_finish >= t->finish_cap) { t->status = RRTFND_ST_FINISH_CAP; goto out; }
             t->finish[t->n_finish++] = id_new;
             t->solution_found = 1;

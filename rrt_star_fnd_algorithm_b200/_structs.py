@@ -30,6 +30,7 @@ class Params(C.Structure):
         ("words_per_planner", C.c_int64), ("max_attempts", C.c_int64),
         ("step_length", C.c_double), ("radius", C.c_double), ("node_radius", C.c_double), ("bias", C.c_double),
         ("x_lo", C.c_double), ("x_hi", C.c_double), ("y_lo", C.c_double), ("y_hi", C.c_double),
+        ("goal_node_radius", C.c_double),
     ]
 
 
@@ -43,7 +44,7 @@ class Planner(C.Structure):
         ("n_slots", C.c_int32), ("n_live", C.c_int32), ("last_id", C.c_int32), ("iter", C.c_int32),
         ("root_slot", C.c_int32), ("n_finish", C.c_int32), ("best_len", C.c_int32), ("status", C.c_int32),
         ("n_rewired", C.c_int32), ("n_removed", C.c_int32), ("solution_found", C.c_int32),
-        ("n_compactions", C.c_int32),
+        ("n_compactions", C.c_int32), ("fn_count", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

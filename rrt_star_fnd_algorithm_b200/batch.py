@@ -60,7 +60,7 @@ def fn_capacity(max_nodes: int) -> int:
 
 class PlannerBatch:
     def __init__(self, mode, *, starts, goals, obstacles, xy_range, iter_num, step_length, radius=0.0,
-                 node_radius=1.0, bias=0.0, max_nodes=200, seeds=None, stream_ids=None, words=None,
+                 node_radius=1.0, goal_node_radius=None, bias=0.0, max_nodes=200, seeds=None, stream_ids=None, words=None,
                  capacity=None, near_cap=64, finish_cap=1024, path_cap=1024, trace=False,
                  eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None, launch=0,
                  grid=True, grid_cell=0.0):
@@ -87,6 +87,7 @@ class PlannerBatch:
         prm.reserved = int(launch)   # planners per CTA (1, 2, 4) + 16 * xy-ring stages (2, 4) + 256 * resident warps per SM (16, 24, 32); 0 fields = automatic
         prm.step_length, prm.radius, prm.node_radius, prm.bias = float(step_length), float(radius or 0.0), \
             float(node_radius), float(bias)
+        prm.goal_node_radius = float(node_radius if goal_node_radius is None else goal_node_radius)
         (prm.x_lo, prm.x_hi), (prm.y_lo, prm.y_hi) = [(float(a), float(b)) for a, b in xy_range]
         self.prm = prm
 
@@ -156,6 +157,32 @@ class PlannerBatch:
             b = self._batch()
             _abi.check(_abi.lib.rrtfnd_init_batch(C.byref(self.prm), C.byref(b), self._stream()), "rrtfnd_init_batch")
         self._initialised = True
+
+    def load_tree(self, p: int, ids, xy, parent_ids, cost, root_id: int, last_id: int):
+        """Replace planner p's tree by an existing one (a Graph that already holds nodes): rows in ascending id,
+        parents given as ids (-1 = none). Planner-local bookkeeping (finish list, best path) starts empty, as it does
+        at the top of the reference's planner functions (src/algorithm.py:113-116)."""
+        if not self._initialised:
+            self.reset()
+        ids = np.asarray(ids, dtype=np.int32)
+        n = len(ids)
+        if n > self.prm.capacity - 1:
+            raise ValueError(f"tree of {n} nodes does not fit the capacity {self.prm.capacity}")
+        assert np.all(np.diff(ids) > 0), "ids must be strictly ascending"
+        slot_of = {int(i): s for s, i in enumerate(ids.tolist())}
+        par = np.asarray(parent_ids, dtype=np.int64)
+        pslot = np.array([slot_of[int(q)] if q >= 0 else -1 for q in par], dtype=np.int32)
+        nchild = np.bincount(pslot[pslot >= 0], minlength=n).astype(np.int32)
+        dev = self.device
+        self.xy[p, :n] = torch.from_numpy(np.ascontiguousarray(xy, dtype=np.float64).reshape(n, 2)).to(dev)
+        self.ecost[p, :n] = torch.from_numpy(np.ascontiguousarray(cost, dtype=np.float64)).to(dev)
+        self.parent[p, :n] = torch.from_numpy(pslot).to(dev)
+        self.nchild[p, :n] = torch.from_numpy(nchild).to(dev)
+        self.id[p, :n] = torch.from_numpy(ids).to(dev)
+        self.nflags[p, :n] = 0
+        pl = self.planners_t[p].cpu().numpy().view(PLANNER_DTYPE).copy()
+        pl["n_slots"], pl["n_live"], pl["last_id"], pl["root_slot"] = n, n, int(last_id), slot_of[int(root_id)]
+        self.planners_t[p] = torch.from_numpy(pl.view(np.uint8)).to(dev)
 
     def run(self):
         """Grow every tree until iter == iter_num (asynchronous on the current stream)."""

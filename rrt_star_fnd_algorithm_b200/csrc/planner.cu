@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     int n_finish = PL->n_finish, best_len = PL->best_len, status = RRTFND_ST_RUNNING;
     int n_rewired = PL->n_rewired, n_removed = PL->n_removed, solution_found = PL->solution_found;
     int n_compactions = PL->n_compactions;
+    int fn_count = PL->fn_count;             // n_of_nodes of RRT_star_FN (:209): counts this call's nodes, not the live ones
     long long my_hops = 0, my_tests = 0;     // per-lane counters, summed at the end
 
     rng.mode = prm.stream_mode;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     }
 
     const double r2 = dmul(prm.radius, prm.radius);
-    const double goal_thresh = dmul(2.0, prm.node_radius);
+    const double goal_thresh = dmul(2.0, prm.goal_node_radius);
     const bool eval_cp = (prm.flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
     const bool commit_cp = (prm.flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) != 0;
     const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         }
         const int new_slot = n_slots++;
         const int id_new = ++last_id;                                            // Graph.add_vertex (src/graph.py:57-61)
-        ++n_live;
+        ++n_live; ++fn_count;                                                    // n_of_nodes += 1 (:221)
         const double e0 = dist_fma(px, py, nb.x, nb.y);                          // :49
         const bool reached = dist_fma(px, py, gx, gy) < goal_thresh;             // check_solution (:757-758)
         if (lane == 0) {
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 
         // ================================================================ F. forced_removal (:233-237, :800-819)
         int removed_id = -1;
-        if (prm.mode == RRTFND_MODE_FN && n_live > prm.max_nodes) {
+        if (prm.mode == RRTFND_MODE_FN && fn_count > prm.max_nodes) {                 // n_of_nodes > max_nodes (:233)
             const int leaf = best_leaf_slot;
             const int total = n_childless;
             int n_ok = total - (NCHILD[new_slot] == 0 ? 1 : 0);
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             }
             __syncwarp();
             n_childless += __shfl_sync(kFull, d_childless, 0);
-            --n_live; ++n_removed;
+            --n_live; --fn_count; ++n_removed;
         }
 
         // ================================================================ G. goal test and best path (:155-170, :240-251)
@@ -714,7 +715,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         PL->n_slots = n_slots; PL->n_live = n_live; PL->last_id = last_id; PL->iter = iter;
         PL->root_slot = root_slot; PL->n_finish = n_finish; PL->best_len = best_len; PL->status = status;
         PL->n_rewired = n_rewired; PL->n_removed = n_removed; PL->solution_found = solution_found;
-        PL->n_compactions = n_compactions;
+        PL->n_compactions = n_compactions; PL->fn_count = fn_count;
     }
 }
 
@@ -731,7 +732,7 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
     PL->n_scan_nodes = 0; PL->n_chain_hops = 0;
     PL->n_slots = 1; PL->n_live = 1; PL->last_id = 0; PL->iter = 0; PL->root_slot = 0; PL->n_finish = 0;
     PL->best_len = 0; PL->status = RRTFND_ST_RUNNING; PL->n_rewired = 0; PL->n_removed = 0;
-    PL->solution_found = 0; PL->n_compactions = 0;
+    PL->solution_found = 0; PL->n_compactions = 0; PL->fn_count = 1; PL->reserved = 0;
 }
 
 constexpr size_t kMaxSmem = 227 * 1024;
