@@ -229,19 +229,30 @@ int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, v
  * zero its counters. planners[p].start/goal/seed/stream_id must already be set. */
 int rrtfnd_init_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, void* stream);
 
-/* ---- RRT*-FND tree surgery (src/algorithm.py:294-552), one CTA per planner --------------------- */
+/* ---- RRT*-FND tree surgery (src/algorithm.py:294-434), one warp per planner ----------------------------------
+ * Node ids at the interface, like the reference's arguments. `path` is the planner's stored best path
+ * (batch.best_path, ids goal side first); obstacles are batch.obst / prm->n_obst / prm->node_radius as they are
+ * at the time of the call (the culling grid is not used: the map has usually just changed). */
 
-/* select_branch (src/algorithm.py:294-325): re-root at `current_slot[p]`, delete everything outside its subtree. */
-int rrtfnd_fnd_select_branch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* current_slot,
-                             void* stream);
-/* valid_path (src/algorithm.py:344-367) over the stored best path: delete occupied path nodes and their
- * off-path subtrees; out_separate_root[p] = slot of the last orphaned on-path child (or the previous root). */
-int rrtfnd_fnd_valid_path(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, int32_t* out_separate_root,
-                          void* stream);
-/* reconnect (src/algorithm.py:370-404): link the separate root to the first (lowest id) root-tree node within
- * `radius` (calc_distance <= radius) whose segment is free. out_linked[p] = slot linked to or -1. */
-int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root,
-                         double radius, int32_t* out_linked, void* stream);
+/* select_branch + remove_children (src/algorithm.py:294-341): re-root planner p at node current_id[p] of its path
+ * and delete everything outside that node's subtree; start <- its position, path <- path[:index + 1], best cost
+ * re-summed to the new root. out_status[p] (may be NULL): 0, -1 = not on the path / not alive (ValueError in the
+ * reference), -2 = it is already the root (KeyError in the reference). */
+int rrtfnd_fnd_select_branch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* current_id,
+                             int32_t* out_status, void* stream);
+/* valid_path (src/algorithm.py:344-367): delete the path nodes occupied under Map.is_occupied_c together with the
+ * off-path subtrees hanging from them; the on-path child of each becomes a root. out_separate_root_id[p] = id of the
+ * last such child (goal side), previous_root_id[p] if no path node is occupied, -1 with out_index_error[p] = 1 when
+ * the goal-side leaf itself is occupied (the reference raises IndexError at :358 after removing its children). */
+int rrtfnd_fnd_valid_path(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* previous_root_id,
+                          int32_t* out_separate_root_id, int32_t* out_index_error, void* stream);
+/* reconnect + get_near_nodes + get_distance_dict + check_for_tree_associativity (src/algorithm.py:370-434, :938-951):
+ * link the separate root to the first node in ascending id that belongs to the root tree, lies within `radius`
+ * (get_distance_dict's formula) and sees it (through_obstacle(Line(node, separate root)) is False); edge cost =
+ * calc_distance. On success the stored best path / cost become find_path(last_node = path[0], root).
+ * out_linked_id[p] = id linked to, or -1. */
+int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root_id,
+                         double radius, int32_t* out_linked_id, void* stream);
 
 /* ---- host-buffer entry point (what the Python drop-in and bench `e2e` call) -------------------- */
 

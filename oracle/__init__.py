@@ -60,6 +60,11 @@ def lib():
     L.orc_near_set.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, vp]
     L.orc_run.argtypes = [vp, C.POINTER(Params), vp, C.c_double, C.c_double, vp, C.c_int64, C.c_uint64,
                           C.c_uint64, vp]
+    L.orc_fnd_select_branch.argtypes = [vp, C.c_int]
+    L.orc_fnd_valid_path.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int, ip]
+    L.orc_fnd_reconnect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.orc_set_best_path.argtypes = [vp, vp, C.c_int]
+    L.orc_get_root.argtypes = [vp]
     L.orc_cull_probe.restype = C.c_int64
     L.orc_cull_probe.argtypes = [C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int64)]
     L.orc_run_batch.argtypes = [C.POINTER(Params), C.c_int, vp, vp, vp, vp, C.c_int]
@@ -134,6 +139,28 @@ class OracleTree:
         out = np.zeros(65536, np.int32)
         n = self.L.orc_get_finish(self.h, _ptr(out))
         return out[:n].copy()
+
+    # ---- FND tree surgery (src/algorithm.py:294-404) on the stored best path
+    def set_best_path(self, ids):
+        a = np.ascontiguousarray(ids, np.int32)
+        if self.L.orc_set_best_path(self.h, _ptr(a), len(a)):
+            raise ValueError("path longer than path_cap")
+
+    def root(self):
+        return self.L.orc_get_root(self.h)
+
+    def select_branch(self, current_id):
+        return self.L.orc_fnd_select_branch(self.h, int(current_id))
+
+    def valid_path(self, obstacles, node_radius, previous_root):
+        ob = obst_table3(obstacles)
+        err = C.c_int(0)
+        sep = self.L.orc_fnd_valid_path(self.h, _ptr(ob), len(ob), float(node_radius), int(previous_root), C.byref(err))
+        return sep, bool(err.value)
+
+    def reconnect(self, obstacles, separate_root, radius, last_node):
+        ob = obst_table3(obstacles)
+        return self.L.orc_fnd_reconnect(self.h, _ptr(ob), len(ob), int(separate_root), float(radius), int(last_node))
 
     def get_cost(self, id_):
         return self.L.orc_get_cost(self.h, int(id_))

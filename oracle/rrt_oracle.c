@@ -352,6 +352,108 @@ static double find_path(orc_tree_t* t, int from, int* path, int* len) {
     return cost;
 }
 
+
+/* ------------------------------------------------------------------- FND tree surgery (row a15) */
+
+static int in_path(const orc_tree_t* t, int id) {
+    for (int i = 0; i < t->best_len; ++i) if (t->best_path[i] == id) return 1;
+    return 0;
+}
+
+/* remove_children (src/algorithm.py:328-341): delete every descendant of `id` reached through children that are not
+ * on the path (children on the path are kept and not descended into). Children are visited in ascending id. */
+static void remove_children(orc_tree_t* t, int id) {
+    for (int c = 0; c <= t->last_id; ++c) {
+        if (!t->alive[c] || t->parent[c] != id || in_path(t, c)) continue;
+        if (t->nchild[c] != 0) remove_children(t, c);
+        remove_vertex(t, c);
+    }
+}
+
+/* select_branch (src/algorithm.py:294-325) with path = the stored best path (ids goal side first).
+ * Returns 0, or -1 if `current` is not on the path (the reference raises ValueError at path.index). */
+int orc_fnd_select_branch(orc_tree_t* t, int current) {
+    int idx = -1;
+    for (int i = 0; i < t->best_len; ++i) if (t->best_path[i] == current) { idx = i; break; }
+    if (idx < 0 || !t->alive[current]) return -1;
+    int parent = t->parent[current];
+    if (parent < 0) return -2;                    /* G.children[None] -> KeyError in the reference */
+    t->parent[current] = -1;                      /* :305 */
+    t->nchild[parent]--;                          /* :306-307 */
+    for (int i = t->best_len - 1; i > idx; --i)   /* reversed(stranded_nodes): root side first (:315-317) */
+        remove_children(t, t->best_path[i]);
+    for (int i = idx + 1; i < t->best_len; ++i) { /* :322-323 */
+        int n = t->best_path[i];
+        if (t->parent[n] >= 0 && !t->alive[t->parent[n]]) t->parent[n] = -1;   /* its parent entry is already gone */
+        remove_vertex(t, n);
+    }
+    t->root = current;                            /* G.start = G.vertices[current] (:303) */
+    t->best_len = idx + 1;                        /* new_path = path[:idx + 1] (:313) */
+    int len;
+    t->best_cost = find_path(t, t->best_path[0], 0, &len);
+    int k = 0;                                    /* planner-local finish list: keep the surviving entries */
+    for (int f = 0; f < t->n_finish; ++f) if (t->alive[t->finish[f]]) t->finish[k++] = t->finish[f];
+    t->n_finish = k;
+    return 0;
+}
+
+/* valid_path (src/algorithm.py:344-367) over the stored path. Returns the separate root id (previous_root if no
+ * path node is occupied); *index_error = 1 if the reference would raise IndexError at :358 (occupied goal-side leaf). */
+int orc_fnd_valid_path(orc_tree_t* t, const double* obst, int M, double node_radius, int previous_root, int* index_error) {
+    int sep = previous_root;
+    *index_error = 0;
+    for (int i = t->best_len - 1; i >= 0; --i) {  /* reversed(nodes_in_path): root side first (:355) */
+        int id = t->best_path[i];
+        if (!t->alive[id]) continue;
+        if (!is_occupied(t->x[id], t->y[id], obst, M, node_radius)) continue;   /* :356 */
+        remove_children(t, id);                   /* :357 */
+        int child = -1;                           /* G.children[id][0]: the remaining (on-path) child (:358) */
+        for (int c = 0; c <= t->last_id; ++c) if (t->alive[c] && t->parent[c] == id) { child = c; break; }
+        if (child < 0) { *index_error = 1; return sep; }
+        if (t->parent[id] >= 0 && !t->alive[t->parent[id]]) t->parent[id] = -1;
+        remove_vertex(t, id);                     /* :359 */
+        t->parent[child] = -1;                    /* :360 */
+        sep = child;                              /* :361 */
+    }
+    return sep;
+}
+
+/* reconnect (src/algorithm.py:370-404) + get_near_nodes (:423-434) + get_distance_dict (:938-951, called with the
+ * harness' default for its unused third argument) + check_for_tree_associativity (:407-420).
+ * Returns the id the separate root was linked to, or -1; on success the stored best path / cost are recomputed from
+ * last_node (find_path(G, last_node, id_root), :400). */
+int orc_fnd_reconnect(orc_tree_t* t, const double* obst, int M, int sep, double radius, int last_node) {
+    const double qx = t->x[sep], qy = t->y[sep];
+    const double y2 = qx * qx + qy * qy;
+    for (int i = 0; i <= t->last_id; ++i) {
+        if (!t->alive[i]) continue;
+        /* np.sqrt(x2 - 2 * matmul + y2): the BLAS dot of a 2-vector is fma(px, qx, fl(py*qy)) (probed) */
+        double x2 = t->x[i] * t->x[i] + t->y[i] * t->y[i];
+        double dot = fma(t->x[i], qx, t->y[i] * qy);
+        double d = sqrt((x2 - 2.0 * dot) + y2);
+        if (!(d <= radius)) continue;             /* :432 (NaN from cancellation is not <= radius) */
+        int n = i;                                /* check_for_tree_associativity(G, root, i) */
+        while (t->parent[n] >= 0) n = t->parent[n];
+        if (n != t->root) continue;
+        ++t->n_edge_checks; ++t->n_edge_checks_ref;
+        if (through_obstacle(t->x[i], t->y[i], qx, qy, obst, M, &t->n_circle_tests)) continue;   /* Line(node, separate) :387-388 */
+        t->parent[sep] = i;                       /* G.add_edge(id_separate_root, node, cost) :389-390 */
+        t->nchild[i]++;
+        t->ecost[sep] = dist_fma(t->x[i], t->y[i], qx, qy);
+        if (last_node >= 0) t->best_cost = find_path(t, last_node, t->best_path, &t->best_len);
+        return i;
+    }
+    return -1;
+}
+
+int orc_set_best_path(orc_tree_t* t, const int* ids, int n) {
+    if (n > t->path_cap) return -1;
+    memcpy(t->best_path, ids, (size_t)n * sizeof(int));
+    t->best_len = n;
+    return 0;
+}
+int orc_get_root(const orc_tree_t* t) { return t->root; }
+
 /* --------------------------------------------------------------------------------- the planner */
 
 /* One call = the body of RRT / RRT_star / RRT_star_FN (src/algorithm.py:54-265) run until

@@ -44,8 +44,8 @@ def _load():
     lib.rrtfnd_chain_cost.argtypes = [PB, i32, vp, vp, i64, vp, vp]
     lib.rrtfnd_plan_batch.argtypes = [PP, PB, vp]
     lib.rrtfnd_init_batch.argtypes = [PP, PB, vp]
-    lib.rrtfnd_fnd_select_branch.argtypes = [PP, PB, vp, vp]
-    lib.rrtfnd_fnd_valid_path.argtypes = [PP, PB, vp, vp]
+    lib.rrtfnd_fnd_select_branch.argtypes = [PP, PB, vp, vp, vp]
+    lib.rrtfnd_fnd_valid_path.argtypes = [PP, PB, vp, vp, vp, vp]
     lib.rrtfnd_fnd_reconnect.argtypes = [PP, PB, vp, dbl, vp, vp]
     lib.rrtfnd_plan_host.argtypes = [PP, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     lib.rrtfnd_obst_grid_build_host.argtypes = [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, C.POINTER(ObstGrid), vp, vp, vp, vp, vp]

@@ -141,6 +141,66 @@ def RRT_STAR_FND(G: Graph, iter_num: int, map: Map, step_length: int, radius: fl
     init_movement()
 
 
+# ---- FND tree surgery (src/algorithm.py:294-434) on Graph objects --------------------------------------------------
+
+def _surgery_batch(G: Graph, map: Map, path):
+    """Upload G (possibly a forest) with `path` as the stored path; returns the PlannerBatch and the kept positions."""
+    from .batch import PlannerBatch
+    ids, xy, parent, cost, root_id = G._export()
+    cap = len(ids) + 2
+    b = PlannerBatch("star", starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
+                     obstacles=map.obstacles_c, xy_range=G.xy_range, iter_num=1, step_length=1.0, radius=1.0,
+                     node_radius=map.node_radius, capacity=cap, path_cap=max(64, cap), finish_cap=8, grid=False)
+    b.reset()
+    b.load_tree(0, ids, xy, parent, cost, root_id, G.last_id)
+    b.set_best_path(0, path)
+    return b, {i: G.vertices[i] for i in G.vertices}
+
+
+def _download(G: Graph, b, keep):
+    t = b.tree(0)
+    pl = b.planners()[0]
+    G._import(t["ids"], np.column_stack([t["x"], t["y"]]), t["parent"], t["cost"], G.last_id, keep)
+    root_id = b.slot_id(0, int(pl["root_slot"]))
+    G.start = G.vertices[root_id]
+
+
+def select_branch(G: Graph, current_node: int, path: list, map: Map) -> list:
+    """Re-root the tree at `current_node` (a node of `path`), deleting everything outside its subtree; returns the
+    remaining path (src/algorithm.py:294-325)."""
+    b, keep = _surgery_batch(G, map, path)
+    st = int(b.select_branch([current_node])[0])
+    if st == -1:
+        raise ValueError(f"{current_node} is not in list")          # path.index(current_node) in the reference
+    if st == -2:
+        raise KeyError(None)                                        # G.children[None] in the reference
+    _download(G, b, keep)
+    return [int(i) for i in b.best_path(0)]
+
+
+def valid_path(G: Graph, path: list, map: Map, previous_root: int) -> int:
+    """Delete path nodes that collide with obstacles, and what hangs off them; returns the root of the separated
+    tree (src/algorithm.py:344-367)."""
+    b, keep = _surgery_batch(G, map, path)
+    sep, err = b.valid_path([previous_root])
+    _download(G, b, keep)
+    if int(err[0]):
+        raise IndexError("list index out of range")                 # G.children[id_node][0] at :358
+    return int(sep[0])
+
+
+def reconnect(G: Graph, path: list, map: Map, step_size: float, id_root: int, id_separate_root: int,
+              last_node: int):
+    """Link the separated tree back to the first visible root-tree node within `step_size`; returns (path, cost) from
+    `last_node` to the root, or None (src/algorithm.py:370-404)."""
+    b, keep = _surgery_batch(G, map, [last_node] + [i for i in path if i != last_node])
+    linked = int(b.reconnect([id_separate_root], step_size)[0])
+    if linked < 0:
+        return None
+    _download(G, b, keep)
+    return [int(i) for i in b.best_path(0)], np.float64(b.planners()[0]["best_cost"])
+
+
 # ---- helpers user code calls directly --------------------------------------------------------------------------------
 
 def calc_distance(p1: tuple, p2: tuple) -> float:

@@ -184,6 +184,78 @@ class PlannerBatch:
         pl["n_slots"], pl["n_live"], pl["last_id"], pl["root_slot"] = n, n, int(last_id), slot_of[int(root_id)]
         self.planners_t[p] = torch.from_numpy(pl.view(np.uint8)).to(dev)
 
+    # ------------------------------------------------------------------ FND tree surgery (src/algorithm.py:294-434)
+    def _ids_tensor(self, ids):
+        a = np.asarray(ids, dtype=np.int32).reshape(-1)
+        assert len(a) == self.P, "one node id per planner"
+        return torch.from_numpy(a.copy()).to(self.device)
+
+    def set_obstacles(self, obstacles, grid=True, grid_cell=0.0):
+        """Replace the obstacle table (a moved / extended map) and rebuild the culling grid."""
+        self.obst_host = obstacle_table(obstacles)
+        self.prm.n_obst = len(self.obst_host)
+        self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(self.device)
+        self.grid, self._grid_t = ObstGrid(), None
+        if grid and len(self.obst_host):
+            pl = self.planners()
+            pts = np.concatenate([np.column_stack([pl["start_x"], pl["start_y"]]), np.column_stack([pl["goal_x"], pl["goal_y"]]),
+                                  np.array([[self.prm.x_lo, self.prm.y_lo], [self.prm.x_hi, self.prm.y_hi]])])
+            n = pl["n_slots"]
+            xy = self.xy.cpu().numpy()
+            live = [xy[p, :int(n[p])] for p in range(self.P)]
+            allxy = np.concatenate(live + [pts])
+            allxy = allxy[~np.isnan(allxy).any(axis=1)]
+            bounds = (allxy[:, 0].min(), allxy[:, 0].max(), allxy[:, 1].min(), allxy[:, 1].max())
+            g, arrs = build_obstacle_grid(self.obst_host[:, :3], self.prm.node_radius, bounds, grid_cell)
+            if arrs is not None:
+                self._grid_t = [torch.from_numpy(a).to(self.device) for a in arrs]
+                g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in self._grid_t]
+                self.grid = g
+
+    def select_branch(self, current_ids):
+        """select_branch for every planner: re-root at node current_ids[p] of its best path. Returns statuses."""
+        cur = self._ids_tensor(current_ids)
+        out = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            b = self._batch()
+            _abi.check(_abi.lib.rrtfnd_fnd_select_branch(C.byref(self.prm), C.byref(b), C.c_void_p(cur.data_ptr()),
+                                                         C.c_void_p(out.data_ptr()), self._stream()), "rrtfnd_fnd_select_branch")
+        return out.cpu().numpy()
+
+    def valid_path(self, previous_root_ids):
+        """valid_path for every planner against the current obstacle table. Returns (separate root ids, index_error flags)."""
+        prev = self._ids_tensor(previous_root_ids)
+        sep = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        err = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            b = self._batch()
+            _abi.check(_abi.lib.rrtfnd_fnd_valid_path(C.byref(self.prm), C.byref(b), C.c_void_p(prev.data_ptr()),
+                                                      C.c_void_p(sep.data_ptr()), C.c_void_p(err.data_ptr()), self._stream()),
+                       "rrtfnd_fnd_valid_path")
+        return sep.cpu().numpy(), err.cpu().numpy()
+
+    def reconnect(self, separate_root_ids, radius):
+        """reconnect for every planner. Returns the id each separate root was linked to (-1 = none)."""
+        sep = self._ids_tensor(separate_root_ids)
+        out = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            b = self._batch()
+            _abi.check(_abi.lib.rrtfnd_fnd_reconnect(C.byref(self.prm), C.byref(b), C.c_void_p(sep.data_ptr()), float(radius),
+                                                     C.c_void_p(out.data_ptr()), self._stream()), "rrtfnd_fnd_reconnect")
+        return out.cpu().numpy()
+
+    def slot_id(self, p: int, slot: int) -> int:
+        return int(self.id[p, slot].item())
+
+    def set_best_path(self, p: int, ids):
+        """Store `ids` (goal side first) as planner p's path: the `path` argument of the FND functions."""
+        a = np.asarray(ids, dtype=np.int32)
+        assert len(a) <= self.prm.path_cap
+        self.best_path_t[p, :len(a)] = torch.from_numpy(a).to(self.device)
+        pl = self.planners_t[p].cpu().numpy().view(PLANNER_DTYPE).copy()
+        pl["best_len"] = len(a)
+        self.planners_t[p] = torch.from_numpy(pl.view(np.uint8)).to(self.device)
+
     def run(self):
         """Grow every tree until iter == iter_num (asynchronous on the current stream)."""
         if not self._initialised:

@@ -1,6 +1,280 @@
-// fnd.cu — RRT*-FND tree surgery (placeholder while the kernels are being written; replaced below).
+// fnd.cu — RRT*-FND tree surgery on the device-resident batch.
+//
+//   rrtfnd_fnd_select_branch   select_branch + remove_children     src/algorithm.py:294-341
+//   rrtfnd_fnd_valid_path      valid_path                          src/algorithm.py:344-367
+//   rrtfnd_fnd_reconnect       reconnect + get_near_nodes + get_distance_dict + check_for_tree_associativity
+//                                                                  src/algorithm.py:370-434, :938-951
+//
+// One warp per planner; node ids at the interface (the reference's arguments are ids), slots inside. The reference
+// deletes subtrees recursively through its children lists; here a node decides for itself by walking its parent chain
+// (the tree only stores parents), decisions are written to nflags first and applied afterwards so that every walk sees
+// the tree as it was. `path` is the planner's stored best path (ids, goal side first), as in the reference's usage
+// example (test_select_branch, :437-479). Obstacles are read un-culled from batch.obst (they have usually just changed).
 #include <cuda_runtime.h>
+#include <stdint.h>
+
 #include "../../include/rrtfnd.h"
-extern "C" int rrtfnd_fnd_select_branch(const rrtfnd_params_t*, const rrtfnd_batch_t*, const int32_t*, void*) { return RRTFND_E_BADARG; }
-extern "C" int rrtfnd_fnd_valid_path(const rrtfnd_params_t*, const rrtfnd_batch_t*, int32_t*, void*) { return RRTFND_E_BADARG; }
-extern "C" int rrtfnd_fnd_reconnect(const rrtfnd_params_t*, const rrtfnd_batch_t*, const int32_t*, double, int32_t*, void*) { return RRTFND_E_BADARG; }
+#include "arith.cuh"
+#include "cull.cuh"
+
+namespace rrtfnd {
+
+constexpr int kFndWarps = 4;
+constexpr uint8_t kKeep = 4, kOnPath = 8, kOccupied = 16, kDelete = 32;
+
+struct PlannerView {
+    double2* XY; double* ECOST; int32_t* PARENT; int32_t* NCHILD; int32_t* ID; uint8_t* NFLAG; int32_t* FINISH; int32_t* BPATH;
+    rrtfnd_planner_t* PL;
+};
+
+__device__ __forceinline__ PlannerView view_of(const rrtfnd_params_t& prm, const rrtfnd_batch_t& bt, int p) {
+    const size_t o = (size_t)p * prm.capacity;
+    PlannerView v;
+    v.XY = reinterpret_cast<double2*>(bt.xy) + o; v.ECOST = bt.ecost + o; v.PARENT = bt.parent + o; v.NCHILD = bt.nchild + o;
+    v.ID = bt.id + o; v.NFLAG = bt.nflags + o; v.FINISH = bt.finish + (size_t)p * prm.finish_cap;
+    v.BPATH = bt.best_path + (size_t)p * prm.path_cap; v.PL = bt.planners + p;
+    return v;
+}
+
+// slot holding node `id`, -1 if it is not alive (ids are unique; warp-cooperative scan)
+__device__ int find_slot(const int32_t* ID, int n_slots, int id, int lane) {
+    int found = -1;
+    for (int base = 0; base < n_slots && found < 0; base += 32) {
+        const int s = base + lane;
+        const unsigned m = __ballot_sync(kFull, s < n_slots && id >= 0 && ID[s] == id);
+        if (m) found = base + __ffs(m) - 1;
+    }
+    return found;
+}
+
+__device__ void tombstone(const PlannerView& v, int s) {
+    v.ID[s] = -1; v.NCHILD[s] = -1; v.PARENT[s] = -1;
+    v.XY[s] = make_double2(CUDART_NAN, CUDART_NAN);
+}
+
+// planner-local finish list: keep the entries that are still alive, in order (lane 0)
+__device__ int filter_finish(const PlannerView& v, int n_finish) {
+    int k = 0;
+    for (int f = 0; f < n_finish; ++f) { const int s = v.FINISH[f]; if (v.ID[s] >= 0) v.FINISH[k++] = s; }
+    return k;
+}
+
+// find_path(G, leaf, root) (src/algorithm.py:778-797): ids into BPATH, cost summed leaf -> root (lane 0)
+__device__ void rewrite_best_path(const rrtfnd_params_t& prm, const PlannerView& v, int leaf, int root, int* len, double* cost) {
+    int n = leaf, L = 0; double c = 0.0;
+    while (n != root && n >= 0) {
+        if (L < prm.path_cap) v.BPATH[L] = v.ID[n];
+        ++L; c = dadd(c, v.ECOST[n]); n = v.PARENT[n];
+    }
+    if (n == root) { if (L < prm.path_cap) v.BPATH[L] = v.ID[root]; ++L; }     // a broken chain leaves the partial path (:794-795)
+    *len = L; *cost = c;
+}
+
+__global__ void __launch_bounds__(32 * kFndWarps) select_branch_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt,
+                                                                       const int32_t* __restrict__ current_id,
+                                                                       int32_t* __restrict__ out_status) {
+    const int lane = threadIdx.x & 31, p = blockIdx.x * kFndWarps + (threadIdx.x >> 5);
+    if (p >= bt.n_planners) return;
+    const PlannerView v = view_of(prm, bt, p);
+    const int n_slots = v.PL->n_slots, best_len = v.PL->best_len;
+    const int cur_id = current_id[p];
+    const int cur = find_slot(v.ID, n_slots, cur_id, lane);
+    int idx = -1;                                                            // path.index(current_node) (:313)
+    for (int base = 0; base < best_len && idx < 0; base += 32) {
+        const int i = base + lane;
+        const unsigned m = __ballot_sync(kFull, i < best_len && v.BPATH[i] == cur_id);
+        if (m) idx = base + __ffs(m) - 1;
+    }
+    int status = 0;
+    if (cur < 0 || idx < 0) status = -1;                                     // ValueError in the reference
+    else if (v.PARENT[cur] < 0) status = -2;                                 // G.children[None]: KeyError in the reference
+    if (status) { if (lane == 0 && out_status) out_status[p] = status; return; }
+    // everything outside the subtree of `current` goes (stranded path nodes and what hangs off them, :315-323)
+    for (int s = lane; s < n_slots; s += 32) {
+        if (v.ID[s] < 0) continue;
+        int n = s;
+        while (n >= 0 && n != cur) n = v.PARENT[n];
+        v.NFLAG[s] = (uint8_t)((v.NFLAG[s] & ~kKeep) | (n == cur ? kKeep : 0));
+    }
+    __syncwarp();
+    int n_del = 0;
+    for (int s = lane; s < n_slots; s += 32)
+        if (v.ID[s] >= 0 && !(v.NFLAG[s] & kKeep)) { tombstone(v, s); ++n_del; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n_del += __shfl_xor_sync(kFull, n_del, off);
+    const int leaf = find_slot(v.ID, n_slots, v.BPATH[0], lane);
+    __syncwarp();
+    if (lane == 0) {
+        v.PARENT[cur] = -1;                                                  // :305
+        const double2 c = v.XY[cur];
+        v.PL->start_x = c.x; v.PL->start_y = c.y;                            // G.start = G.vertices[current_node] (:303)
+        v.PL->root_slot = cur;
+        v.PL->n_live -= n_del;
+        double cost = 0.0;                                                   // new_path = path[:idx + 1]: the stored ids stay,
+        for (int n = leaf; n != cur && n >= 0; n = v.PARENT[n]) cost = dadd(cost, v.ECOST[n]);   // its cost is re-summed to the new root
+        v.PL->best_len = idx + 1; v.PL->best_cost = cost;
+        v.PL->n_finish = filter_finish(v, v.PL->n_finish);
+        if (out_status) out_status[p] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(32 * kFndWarps) valid_path_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt,
+                                                                    const int32_t* __restrict__ previous_root_id,
+                                                                    int32_t* __restrict__ out_sep_id,
+                                                                    int32_t* __restrict__ out_index_error) {
+    extern __shared__ int32_t fnd_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, p = blockIdx.x * kFndWarps + wib;
+    if (p >= bt.n_planners) return;
+    int32_t* pslot = fnd_smem + (size_t)wib * prm.path_cap;                  // slot of path node i, -1 if it is gone
+    const PlannerView v = view_of(prm, bt, p);
+    const int n_slots = v.PL->n_slots, L = min(v.PL->best_len, prm.path_cap), M = prm.n_obst;
+    const double2* tab = reinterpret_cast<const double2*>(bt.obst);
+    for (int i = lane; i < L; i += 32) pslot[i] = -1;
+    __syncwarp();
+    for (int s = lane; s < n_slots; s += 32) {
+        const int id = v.ID[s];
+        uint8_t f = v.NFLAG[s] & (uint8_t)~(kOnPath | kOccupied | kDelete);
+        if (id >= 0)
+            for (int i = 0; i < L; ++i) if (v.BPATH[i] == id) { pslot[i] = s; f |= kOnPath; break; }
+        v.NFLAG[s] = f;
+    }
+    __syncwarp();
+    for (int i = lane; i < L; i += 32) {                                      // map.is_occupied_c(pos_node) (:356)
+        const int s = pslot[i];
+        if (s < 0) continue;
+        const double2 c = v.XY[s];
+        bool occ = false;
+        for (int j = 0; j < M && !occ; ++j) {
+            double ox, oy, r, K;
+            load_obst(tab, j, ox, oy, r, K);
+            occ = point_in_inflated(c.x, c.y, ox, oy, r, prm.node_radius);
+        }
+        if (occ) v.NFLAG[s] |= kOccupied;
+    }
+    __syncwarp();
+    const int leaf = L > 0 ? pslot[0] : -1;
+    // a node goes if the first path node on its parent chain (itself included) is occupied: that is the occupied node
+    // and the off-path subtrees hanging from it (remove_children, :357). An occupied goal-side leaf stays: the
+    // reference raises IndexError at :358 after removing its children.
+    for (int s = lane; s < n_slots; s += 32) {
+        if (v.ID[s] < 0) continue;
+        int n = s;
+        while (n >= 0 && !(v.NFLAG[n] & kOnPath)) n = v.PARENT[n];
+        if (n >= 0 && (v.NFLAG[n] & kOccupied) && s != leaf) v.NFLAG[s] |= kDelete;
+    }
+    __syncwarp();
+    int sep = -1, err = 0;
+    if (lane == 0) {
+        for (int i = L - 1; i >= 1; --i) {                                    // root side first (:355)
+            const int s = pslot[i];
+            if (s < 0 || !(v.NFLAG[s] & kOccupied)) continue;
+            const int pv = v.PARENT[s];
+            if (pv >= 0 && !(v.NFLAG[pv] & kDelete)) v.NCHILD[pv] -= 1;       // Graph.remove_vertex (:359)
+            const int c = pslot[i - 1];                                       // the remaining child is the one on the path (:358)
+            if (c >= 0) { v.PARENT[c] = -1; sep = c; }                        // :360-361
+        }
+        if (leaf >= 0 && (v.NFLAG[leaf] & kOccupied)) { err = 1; v.NCHILD[leaf] = 0; }   // its children were removed before the raise
+    }
+    sep = __shfl_sync(kFull, sep, 0); err = __shfl_sync(kFull, err, 0);
+    __syncwarp();
+    int n_del = 0;
+    for (int s = lane; s < n_slots; s += 32)
+        if (v.ID[s] >= 0 && (v.NFLAG[s] & kDelete)) { tombstone(v, s); ++n_del; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n_del += __shfl_xor_sync(kFull, n_del, off);
+    __syncwarp();
+    if (lane == 0) {
+        v.PL->n_live -= n_del;
+        v.PL->n_finish = filter_finish(v, v.PL->n_finish);
+        if (out_index_error) out_index_error[p] = err;
+        out_sep_id[p] = err ? -1 : (sep >= 0 ? v.ID[sep] : previous_root_id[p]);
+    }
+}
+
+__global__ void __launch_bounds__(32 * kFndWarps) reconnect_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt,
+                                                                   const int32_t* __restrict__ separate_root_id, double radius,
+                                                                   int32_t* __restrict__ out_linked_id) {
+    const int lane = threadIdx.x & 31, p = blockIdx.x * kFndWarps + (threadIdx.x >> 5);
+    if (p >= bt.n_planners) return;
+    const PlannerView v = view_of(prm, bt, p);
+    const int n_slots = v.PL->n_slots, root = v.PL->root_slot;
+    const int sep = find_slot(v.ID, n_slots, separate_root_id[p], lane);
+    int link = -1;
+    if (sep >= 0) {
+        const double2 q = v.XY[sep];
+        const double y2 = dadd(dmul(q.x, q.x), dmul(q.y, q.y));
+        const double2* tab = reinterpret_cast<const double2*>(bt.obst);
+        for (int base = 0; base < n_slots && link < 0; base += 32) {         // dict order = ascending id: first hit wins (:386-392)
+            const int s = base + lane;
+            bool ok = false;
+            if (s < n_slots && v.ID[s] >= 0) {
+                const double2 c = v.XY[s];
+                // get_distance_dict (:938-951): sqrt(|p|^2 - 2 p.q + |q|^2), the BLAS dot being fma(px, qx, fl(py*qy))
+                const double x2 = dadd(dmul(c.x, c.x), dmul(c.y, c.y));
+                const double dot = __fma_rn(c.x, q.x, dmul(c.y, q.y));
+                const double d = dsqrt(dadd(dsub(x2, dmul(2.0, dot)), y2));
+                if (d <= radius) {                                            // NaN (cancellation) is not <= radius (:432)
+                    int n = s;
+                    while (v.PARENT[n] >= 0) n = v.PARENT[n];                 // check_for_tree_associativity (:407-420)
+                    if (n == root)                                            // Line(node, separate root) (:387-388)
+                        ok = !(seg_blocked(tab, &bt.grid, prm.n_obst, 0, c.x, c.y, q.x, q.y, 0, 1) & 1);
+                }
+            }
+            const unsigned m = __ballot_sync(kFull, ok);
+            if (m) link = base + __ffs(m) - 1;
+        }
+    }
+    const int leaf = link >= 0 ? find_slot(v.ID, n_slots, v.BPATH[0], lane) : -1;
+    __syncwarp();
+    if (lane == 0) {
+        if (link >= 0) {
+            const double2 q = v.XY[sep], c = v.XY[link];
+            v.PARENT[sep] = link; v.NCHILD[link] += 1;                        // G.add_edge(id_separate_root, node, cost) (:389-390)
+            v.ECOST[sep] = dist_fma(c.x, c.y, q.x, q.y);
+            int L = 0; double cost = 0.0;                                     // find_path(G, last_node, id_root) (:400)
+            rewrite_best_path(prm, v, leaf, root, &L, &cost);
+            v.PL->best_len = L; v.PL->best_cost = cost;
+        }
+        out_linked_id[p] = link >= 0 ? v.ID[link] : -1;
+    }
+}
+
+}  // namespace rrtfnd
+
+using namespace rrtfnd;
+
+static int fnd_check(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
+    if (!prm || !bt || bt->n_planners <= 0 || prm->capacity < 2) return RRTFND_E_BADARG;
+    if (!bt->planners || !bt->xy || !bt->ecost || !bt->parent || !bt->nchild || !bt->id || !bt->nflags || !bt->finish || !bt->best_path)
+        return RRTFND_E_BADARG;
+    return 0;
+}
+
+extern "C" int rrtfnd_fnd_select_branch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, const int32_t* current_id,
+                                        int32_t* out_status, void* stream) {
+    if (fnd_check(prm, bt) || !current_id) return RRTFND_E_BADARG;
+    const int blocks = (bt->n_planners + kFndWarps - 1) / kFndWarps;
+    select_branch_kernel<<<blocks, 32 * kFndWarps, 0, (cudaStream_t)stream>>>(*prm, *bt, current_id, out_status);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rrtfnd_fnd_valid_path(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, const int32_t* previous_root_id,
+                                     int32_t* out_separate_root_id, int32_t* out_index_error, void* stream) {
+    if (fnd_check(prm, bt) || !previous_root_id || !out_separate_root_id || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
+    const size_t smem = (size_t)kFndWarps * prm->path_cap * sizeof(int32_t);
+    if (smem > 227 * 1024) return RRTFND_E_SMEM;
+    cudaError_t e = cudaFuncSetAttribute(valid_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int blocks = (bt->n_planners + kFndWarps - 1) / kFndWarps;
+    valid_path_kernel<<<blocks, 32 * kFndWarps, smem, (cudaStream_t)stream>>>(*prm, *bt, previous_root_id, out_separate_root_id,
+                                                                              out_index_error);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, const int32_t* separate_root_id,
+                                    double radius, int32_t* out_linked_id, void* stream) {
+    if (fnd_check(prm, bt) || !separate_root_id || !out_linked_id || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
+    const int blocks = (bt->n_planners + kFndWarps - 1) / kFndWarps;
+    reconnect_kernel<<<blocks, 32 * kFndWarps, 0, (cudaStream_t)stream>>>(*prm, *bt, separate_root_id, radius, out_linked_id);
+    return (int)cudaGetLastError();
+}

@@ -38,11 +38,11 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 __host__ __device__ inline int bitmap_words(const rrtfnd_params_t& prm) { return prm.capacity / 32 + 1; }
 
 // shared memory of one warp: xy ring (n_stages tiles) | mbarriers | word source | chain[kChainCap] | stage[kStage] |
-// rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | (FN only) live bitmap + prefix counts
+// rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | live bitmap + prefix counts (compaction)
 __host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
     size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) +
                kChainCap * 8 + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
-    if (prm.mode == RRTFND_MODE_FN) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
+    o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);   // any mode: FND surgery leaves tombstones too
     return align_up(o, 128);
 }
 

@@ -1,0 +1,148 @@
+"""FND tree surgery (select_branch / valid_path / reconnect, src/algorithm.py:294-434).
+
+Goldens (tests/golden/fnd_*.npz) come from the unmodified reference (oracle/make_fnd_golden.py, the call sequence of the
+reference's own usage example test_select_branch). CPU: the C oracle against them. GPU: the CUDA operators through the
+C ABI against them, batched, and the drop-in functions on Graph objects."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import cases as K
+from oracle.make_fnd_golden import FND_CASES
+from oracle.philox import philox_words
+from rrt_star_fnd_algorithm_b200 import _structs as S
+
+from util import assert_tree_equal, load_npz
+
+IDS = [fc["name"] for fc in FND_CASES]
+
+
+def stage_tree(g, prefix):
+    return {k: g[f"{prefix}_{k}"] for k in ("ids", "x", "y", "parent", "cost", "nchild")}
+
+
+def grown_oracle(case, extra=0):
+    words = philox_words(case["seed"], case["stream_id"], K.words_needed(case))
+    prm = K.params_for(case, stream_mode=S.STREAM_WORDS, n_words=len(words), flags=0)
+    t = O.OracleTree(case["start"], case["iter_num"] + extra + 2)
+    assert t.run(prm, case["obstacles"], case["goal"], words=words)[0] == S.ST_DONE
+    return t
+
+
+@pytest.mark.parametrize("fc", FND_CASES, ids=IDS)
+def test_oracle_fnd_matches_reference_golden(fc):
+    case, g = K.case_by_name(fc["case"]), load_npz(f"fnd_{fc['name']}.npz")
+    t = grown_oracle(case)
+    assert np.array_equal(t.best_path(), g["path0"])
+    assert t.select_branch(int(g["current"])) == 0
+    assert_tree_equal(t.export(), stage_tree(g, "sb"), "select_branch")
+    assert np.array_equal(t.best_path(), g["path1"]) and t.root() == int(g["sb_root"])
+    sep, err = t.valid_path(g["obstacles2"], case["node_radius"], int(g["current"]))
+    assert err == bool(g["vp_index_error"])
+    assert_tree_equal(t.export(), stage_tree(g, "vp"), "valid_path")
+    if err:
+        return
+    assert sep == int(g["vp_sep"])
+    linked = t.reconnect(g["obstacles2"], sep, fc["radius"], int(g["path0"][0]))
+    assert linked == int(g["rc_linked"])
+    assert_tree_equal(t.export(), stage_tree(g, "rc"), "reconnect")
+    if linked >= 0:
+        assert np.array_equal(t.best_path(), g["rcret_path"]) and t.planner().best_cost == float(g["rcret_cost"])
+
+
+def test_select_branch_rejects_a_node_off_the_path():
+    t = grown_oracle(K.case_by_name("float_fn"))
+    off = next(int(i) for i in t.export()["ids"][::-1] if int(i) not in set(t.best_path().tolist()))
+    assert t.select_branch(off) == -1
+
+
+# ------------------------------------------------------------------------------------------------------------- GPU
+def grown_batch(case, P=1, **kw):
+    from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
+    b = PlannerBatch(case["mode"], starts=[case["start"]] * P, goals=[case["goal"]] * P, obstacles=case["obstacles"],
+                     xy_range=case["xy_range"], iter_num=case["iter_num"], step_length=case["step_length"],
+                     radius=case["radius"], node_radius=case["node_radius"], bias=case["bias"], max_nodes=case["max_nodes"],
+                     seeds=[case["seed"]] * P, stream_ids=[case["stream_id"]] * P, **kw).run()
+    b.check_status()
+    return b
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fc", FND_CASES, ids=IDS)
+def test_gpu_fnd_matches_reference_golden(fc):
+    case, g = K.case_by_name(fc["case"]), load_npz(f"fnd_{fc['name']}.npz")
+    P = 3                                                   # identical planners: the operators are batched
+    b = grown_batch(case, P)
+    for p in range(P):
+        assert np.array_equal(b.best_path(p), g["path0"])
+    st = b.select_branch([int(g["current"])] * P)
+    assert list(st) == [0] * P
+    for p in range(P):
+        assert_tree_equal(b.tree(p), stage_tree(g, "sb"), f"select_branch[{p}]")
+        assert np.array_equal(b.best_path(p), g["path1"])
+        pl = b.planners()[p]
+        assert b.slot_id(p, int(pl["root_slot"])) == int(g["sb_root"])
+        assert (pl["start_x"], pl["start_y"]) == (g["sb_x"][list(g["sb_ids"]).index(int(g["sb_root"]))],
+                                                  g["sb_y"][list(g["sb_ids"]).index(int(g["sb_root"]))])
+    b.set_obstacles([tuple(r) for r in g["obstacles2"]])
+    sep, err = b.valid_path([int(g["current"])] * P)
+    for p in range(P):
+        assert bool(err[p]) == bool(g["vp_index_error"])
+        assert_tree_equal(b.tree(p), stage_tree(g, "vp"), f"valid_path[{p}]")
+    if bool(g["vp_index_error"]):
+        return
+    assert list(sep) == [int(g["vp_sep"])] * P
+    linked = b.reconnect(sep, fc["radius"])
+    assert list(linked) == [int(g["rc_linked"])] * P
+    for p in range(P):
+        assert_tree_equal(b.tree(p), stage_tree(g, "rc"), f"reconnect[{p}]")
+        if int(g["rc_linked"]) >= 0:
+            assert np.array_equal(b.best_path(p), g["rcret_path"])
+            assert b.planners()[p]["best_cost"] == float(g["rcret_cost"])
+
+
+@pytest.mark.gpu
+def test_gpu_fnd_then_regrow_with_the_planner():
+    """After the surgery the batch is a valid planner state: growing on from it equals the oracle doing the same."""
+    fc = next(f for f in FND_CASES if f["name"] == "float_a")
+    case, g = K.case_by_name(fc["case"]), load_npz("fnd_float_a.npz")
+    b = grown_batch(case, 2)
+    t = grown_oracle(case, extra=200)
+    cur = int(g["current"])
+    assert list(b.select_branch([cur, cur])) == [0, 0] and t.select_branch(cur) == 0
+    assert_tree_equal(b.tree(1), t.export(), "after select_branch")
+    # 200 more FN iterations from the pruned, re-rooted tree (Philox stream continues at the saved cursor)
+    more = dict(case, iter_num=case["iter_num"] + 200)
+    b.prm.iter_num = more["iter_num"]
+    b.run(); b.check_status()
+    prm = K.params_for(more, stream_mode=S.STREAM_PHILOX, flags=0)
+    st, _ = t.run(prm, case["obstacles"], case["goal"], seed=case["seed"], stream_id=case["stream_id"])
+    assert st == S.ST_DONE
+    assert_tree_equal(b.tree(0), t.export(), "regrown")
+    assert b.planners()[0]["best_cost"] == t.planner().best_cost
+
+
+@pytest.mark.gpu
+def test_dropin_fnd_functions_on_graph_objects():
+    import contextlib, io, random
+    from rrt_star_fnd_algorithm_b200 import algorithm as A, graph, map as map_mod
+    from oracle.make_dropin_golden import build_objects
+    fc = next(f for f in FND_CASES if f["name"] == "star_a")
+    case, g = K.case_by_name(fc["case"]), load_npz("fnd_star_a.npz")
+    # rebuild the grown tree as a Graph from the oracle, then run the drop-in surgery on it
+    t = grown_oracle(case)
+    G, m = build_objects(graph, map_mod, case)
+    e = t.export()
+    G._import(e["ids"], np.column_stack([e["x"], e["y"]]), e["parent"], e["cost"], int(e["ids"].max()), {0: G.start})
+    path = [int(i) for i in g["path0"]]
+    new_path = A.select_branch(G, int(g["current"]), path, m)
+    assert new_path == [int(i) for i in g["path1"]] and G.id_vertex[G.start] == int(g["sb_root"])
+    from oracle.make_dropin_golden import graph_arrays
+    assert_tree_equal(graph_arrays(G), stage_tree(g, "sb"), "drop-in select_branch")
+    m.add_obstacles([[G.vertices[new_path[i]], fc["block_r"]] for i in fc["block"]])
+    sep = A.valid_path(G, new_path, m, int(g["current"]))
+    assert sep == int(g["vp_sep"])
+    assert_tree_equal(graph_arrays(G), stage_tree(g, "vp"), "drop-in valid_path")
+    ret = A.reconnect(G, new_path, m, fc["radius"], G.id_vertex[G.start], sep, path[0])
+    assert ret is not None and list(ret[0]) == [int(i) for i in g["rcret_path"]] and float(ret[1]) == float(g["rcret_cost"])
+    assert_tree_equal(graph_arrays(G), stage_tree(g, "rc"), "drop-in reconnect")
