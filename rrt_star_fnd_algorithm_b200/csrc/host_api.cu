@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <math.h>
+#include <stdio.h>
+#include <chrono>
 #include <string.h>
 
 #include <vector>
@@ -82,6 +84,11 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
                                 int32_t* parent_host, int32_t* nchild_host, int32_t* id_host, int32_t* best_path_host,
                                 int32_t device) {
     if (!prm || P <= 0 || !starts_goals_host || !seeds_host || (prm->n_obst > 0 && !obst_host)) return RRTFND_E_BADARG;
+    const bool timing = getenv("RRTFND_HOST_TIMING") != nullptr;     // phase times on stderr (diagnostics)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     if (prm->stream_mode == RRTFND_STREAM_WORDS && !words_host) return RRTFND_E_BADARG;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return RRTFND_E_NOGPU;
@@ -134,6 +141,8 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
     CK(d_ob.alloc(ob.size() * 8));
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const auto t1 = now();
+    auto t2 = t1, t3 = t1;
     int rc = 0;
     do {
         if ((rc = (int)cudaMemcpyAsync(d_pl.p, pl.data(), (size_t)P * sizeof(rrtfnd_planner_t), cudaMemcpyHostToDevice, st))) break;
@@ -162,7 +171,9 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         rrtfnd_params_t q = *prm;
         q.flags &= ~RRTFND_FLAG_TRACE;
         if ((rc = rrtfnd_init_batch(&q, &bt, st))) break;
+        if (timing) { cudaStreamSynchronize(st); t2 = now(); }
         if ((rc = rrtfnd_plan_batch(&q, &bt, st))) break;
+        if (timing) { cudaStreamSynchronize(st); t3 = now(); }
         if (planners_host && (rc = (int)cudaMemcpyAsync(planners_host, d_pl.p, (size_t)P * sizeof(rrtfnd_planner_t), cudaMemcpyDeviceToHost, st))) break;
         if (xy_host && (rc = (int)cudaMemcpyAsync(xy_host, d_xy.p, n * 16, cudaMemcpyDeviceToHost, st))) break;
         if (ecost_host && (rc = (int)cudaMemcpyAsync(ecost_host, d_e.p, n * 8, cudaMemcpyDeviceToHost, st))) break;
@@ -173,5 +184,10 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         rc = (int)cudaStreamSynchronize(st);
     } while (0);
     cudaStreamDestroy(st);
+    if (timing) {
+        const auto t4 = now();
+        fprintf(stderr, "rrtfnd_plan_host: setup+alloc %.1f ms, h2d+init %.1f ms, plan %.1f ms, d2h %.1f ms\n", ms(t0, t1), ms(t1, t2),
+                ms(t2, t3), ms(t3, t4));
+    }
     return rc;
 }

@@ -1,0 +1,88 @@
+"""Multi-GPU plumbing on CPU: world-size-2 gloo. Ranks own contiguous blocks of planners and meet once, after growth,
+to gather the per-planner records and broadcast the globally best path (parallel.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rrt_star_fnd_algorithm_b200._structs import PLANNER_BYTES, PLANNER_DTYPE
+from rrt_star_fnd_algorithm_b200.parallel import gather_records, shard_range
+
+
+def test_shard_range_partitions_every_planner_once():
+    for n in (1, 7, 8, 16384, 4097):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (a, ca), (b, _) in zip(spans, spans[1:]):
+                assert a + ca == b
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_workload_problems_do_not_depend_on_the_sharding():
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    w = W.c3()
+    s_all, g_all, seeds, sids = W.planner_problems(w, 0, 12)
+    for world in (2, 3):
+        parts = [W.planner_problems(w, *shard_range(12, r, world)) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), s_all)
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), g_all)
+        assert np.array_equal(np.concatenate([p[3] for p in parts]), sids)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _records(rank, P, path_cap):
+    """Synthetic planner records: planner i of rank r has best cost 100 - (r * P + i) % 7, rank 1 planner 2 has none."""
+    pl = np.zeros(P, dtype=PLANNER_DTYPE)
+    paths = np.zeros((P, path_cap), dtype=np.int32)
+    for i in range(P):
+        g = rank * P + i
+        pl["best_cost"][i] = 100.0 - (g % 7)
+        pl["best_len"][i] = 3 + g % 4
+        pl["iter"][i] = 10 + g
+        paths[i, :pl["best_len"][i]] = np.arange(pl["best_len"][i]) + 1000 * g
+    if rank == 1:
+        pl["best_cost"][2], pl["best_len"][2] = np.inf, 0
+    return torch.from_numpy(pl.view(np.uint8).reshape(P, PLANNER_BYTES).copy()), torch.from_numpy(paths)
+
+
+def _worker(rank, world, port, P, path_cap, out_dir, all_inf):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rec, paths = _records(rank, P, path_cap)
+        if all_inf:
+            v = rec.numpy().reshape(-1).view(PLANNER_DTYPE)
+            v["best_cost"], v["best_len"] = np.inf, 0
+        allrec, gidx, path = gather_records(rec, paths)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), allrec=allrec.numpy(), gidx=gidx, path=path.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("all_inf", [False, True])
+def test_gather_records_world_size_2_gloo(tmp_path, all_inf):
+    world, P, path_cap = 2, 5, 16
+    mp.spawn(_worker, args=(world, _free_port(), P, path_cap, str(tmp_path), all_inf), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    # every rank ends with the same gathered records, the same winner and the winner's path
+    for k in ("allrec", "gidx", "path"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    allrec = outs[0]["allrec"].reshape(-1).view(PLANNER_DTYPE)
+    assert len(allrec) == world * P and list(allrec["iter"]) == [10 + g for g in range(world * P)]
+    if all_inf:
+        assert int(outs[0]["gidx"]) == -1 and len(outs[0]["path"]) == 0
+        return
+    costs = allrec["best_cost"]
+    want = int(np.flatnonzero(costs == costs.min())[0])          # lowest global index on ties
+    assert int(outs[0]["gidx"]) == want == 6                     # 100 - 6 is the minimum, first reached by planner 6 (rank 1)
+    assert list(outs[0]["path"]) == list(np.arange(3 + want % 4) + 1000 * want)
