@@ -206,7 +206,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     w, P = load_workload(args)
     first = rank * P
@@ -264,8 +265,15 @@ def main():
     # the counters are totals of ONE step (state is re-initialised each step); the timed region holds `steps` of them
     rate = args.steps / (ms / 1e3)
 
+    # ---- e2e through the host-buffer C ABI (pinned host memory, copies inside the timed region); EVERY rank takes
+    # part (its own planners, collectives inside), so this must come before the non-zero ranks leave
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, w, P, first, b, dev)
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -290,11 +298,6 @@ def main():
                 "peak_source": peak_src,
                 "note": "trees of resident planners are L1/L2/shared-memory resident, so DRAM traffic is far below "
                         "the algorithmic bytes; the kernel is FP64-issue / latency bound (see profiles/)"}
-
-    # ---- e2e through the host-buffer C ABI (pinned host memory, copies inside the timed region)
-    e2e = None
-    if not args.no_e2e:
-        e2e = run_e2e(args, w, P, first, b, dev)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -325,6 +328,7 @@ def main():
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
