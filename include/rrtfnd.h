@@ -41,6 +41,7 @@ extern "C" {
 #define RRTFND_FLAG_EVAL_CHOOSE_PARENT 1   /* evaluate choose_parent_kdtree's return value (src/algorithm.py:822-852) */
 #define RRTFND_FLAG_COMMIT_CHOOSE_PARENT 2 /* EXTENSION: use that return value as the new node's edge (the reference drops it, :146/:224) */
 #define RRTFND_FLAG_TRACE 4                /* write one rrtfnd_trace_t per successful iteration */
+#define RRTFND_FLAG_NODE_GRID 8            /* answer nearest / near-set queries of large trees through batch.node_grid (RRT, RRT* only) */
 
 /* per-planner status (rrtfnd_planner_t.status) */
 #define RRTFND_ST_RUNNING 0        /* iter < iter_num, can be resumed */
@@ -141,6 +142,22 @@ typedef struct rrtfnd_obst_grid {
     const int32_t* pt_items;    /* obstacle indices for Map.is_occupied_c (src/map.py:38-47), inflated by node_radius */
 } rrtfnd_obst_grid_t;
 
+/* Uniform grid over the NODES of each planner (RRTFND_FLAG_NODE_GRID): replaces the k-d tree the reference rebuilds
+ * twice per attempt (src/algorithm.py:41-43, :145) for large trees. Every inserted node is pushed onto the singly
+ * linked list of its cell; a query gathers the nodes of a window of cells that provably contains every node within
+ * the distance it needs and then runs the SAME exact predicates as the full scans on that candidate list, so results
+ * are identical to the scans (and to the reference) by construction. Used once a tree has min_nodes nodes.
+ * cell(v) as in rrtfnd_obst_grid_t. No removals: not available with RRTFND_MODE_FN or after FND surgery. */
+typedef struct rrtfnd_node_grid {
+    double x0, y0, inv_cell, cell;
+    int32_t nx, ny;
+    int32_t min_nodes;          /* trees smaller than this are scanned */
+    int32_t cand_cap;           /* candidate slots per planner (a window holding more falls back to the scan) */
+    int32_t* head;              /* [P][nx*ny] newest node of each cell, -1 = empty (reset by rrtfnd_init_batch) */
+    int32_t* next;              /* [P][capacity] next (older) node of the same cell, -1 = end */
+    int32_t* cand;              /* [P][2*cand_cap] scratch */
+} rrtfnd_node_grid_t;
+
 /* Device-resident batch of P independent planners, structure-of-arrays, fixed capacity. */
 typedef struct rrtfnd_batch {
     int32_t n_planners;
@@ -158,6 +175,7 @@ typedef struct rrtfnd_batch {
     const uint32_t* words;      /* [P][words_per_planner] or NULL */
     rrtfnd_trace_t* trace;      /* [P][trace_cap] or NULL */
     rrtfnd_obst_grid_t grid;    /* optional culling grid over obst */
+    rrtfnd_node_grid_t node_grid; /* optional grid over the nodes (RRTFND_FLAG_NODE_GRID) */
 } rrtfnd_batch_t;
 
 /* ---- library info ------------------------------------------------------------------------ */

@@ -5,7 +5,7 @@ ABI_VERSION = 2
 
 MODE_RRT, MODE_STAR, MODE_FN = 0, 1, 2
 STREAM_WORDS, STREAM_PHILOX = 0, 1
-FLAG_EVAL_CHOOSE_PARENT, FLAG_COMMIT_CHOOSE_PARENT, FLAG_TRACE = 1, 2, 4
+FLAG_EVAL_CHOOSE_PARENT, FLAG_COMMIT_CHOOSE_PARENT, FLAG_TRACE, FLAG_NODE_GRID = 1, 2, 4, 8
 
 ST_RUNNING, ST_DONE, ST_NEED_WORDS, ST_ATTEMPT_CAP = 0, 1, 2, 3
 ST_CAPACITY, ST_NEAR_CAP, ST_FINISH_CAP, ST_PATH_CAP, ST_DUPLICATE, ST_NO_CHILDLESS, ST_STREAM_EXHAUSTED = -1, -2, -3, -4, -5, -6, -7
@@ -64,6 +64,14 @@ class ObstGrid(C.Structure):
     ]
 
 
+class NodeGrid(C.Structure):
+    _fields_ = [
+        ("x0", C.c_double), ("y0", C.c_double), ("inv_cell", C.c_double), ("cell", C.c_double),
+        ("nx", C.c_int32), ("ny", C.c_int32), ("min_nodes", C.c_int32), ("cand_cap", C.c_int32),
+        ("head", C.c_void_p), ("next", C.c_void_p), ("cand", C.c_void_p),
+    ]
+
+
 class Batch(C.Structure):
     _fields_ = [
         ("n_planners", C.c_int32), ("reserved", C.c_int32),
@@ -72,7 +80,7 @@ class Batch(C.Structure):
         ("parent", C.c_void_p), ("nchild", C.c_void_p), ("id", C.c_void_p), ("nflags", C.c_void_p),
         ("finish", C.c_void_p), ("best_path", C.c_void_p),
         ("obst", C.c_void_p), ("words", C.c_void_p), ("trace", C.c_void_p),
-        ("grid", ObstGrid),
+        ("grid", ObstGrid), ("node_grid", NodeGrid),
     ]
 
 

@@ -8,7 +8,7 @@ import torch
 
 from . import _abi
 from ._structs import (
-    Batch, ObstGrid, Params, PLANNER_BYTES, PLANNER_DTYPE, TRACE_BYTES, TRACE_DTYPE,
+    Batch, NodeGrid, ObstGrid, Params, FLAG_NODE_GRID, PLANNER_BYTES, PLANNER_DTYPE, TRACE_BYTES, TRACE_DTYPE,
     MODE_RRT, MODE_STAR, MODE_FN, STREAM_WORDS, STREAM_PHILOX, FLAG_EVAL_CHOOSE_PARENT, FLAG_TRACE,
     ST_DONE, ST_RUNNING, ST_NEED_WORDS, STATUS_NAMES,
 )
@@ -63,7 +63,8 @@ class PlannerBatch:
                  node_radius=1.0, goal_node_radius=None, bias=0.0, max_nodes=200, seeds=None, stream_ids=None, words=None,
                  capacity=None, near_cap=64, finish_cap=1024, path_cap=1024, trace=False,
                  eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None, launch=0,
-                 grid=True, grid_cell=0.0):
+                 grid=True, grid_cell=0.0, node_grid=False, node_grid_cell=0.0, node_grid_min_nodes=4096,
+                 node_grid_cand_cap=8192):
         if not torch.cuda.is_available():
             raise RuntimeError("PlannerBatch needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -126,6 +127,23 @@ class PlannerBatch:
                 self._grid_t = [torch.from_numpy(a).to(dev) for a in arrs]
                 g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in self._grid_t]
                 self.grid = g
+        # grid over the nodes themselves for large trees (config 4): same results as the scans, far fewer nodes touched
+        self.node_grid = NodeGrid()
+        if node_grid:
+            if m == MODE_FN:
+                raise ValueError("the node grid does not support forced removal (RRT*-FN)")
+            pts = np.concatenate([starts, goals, np.asarray(xy_range, dtype=np.float64).T])
+            x0, x1, y0, y1 = pts[:, 0].min(), pts[:, 0].max(), pts[:, 1].min(), pts[:, 1].max()
+            cell = float(node_grid_cell) if node_grid_cell > 0 else max(float(radius or step_length) / 2.0, max(x1 - x0, y1 - y0) / 1024.0)
+            g = self.node_grid
+            g.x0, g.y0, g.cell, g.inv_cell = x0, y0, cell, 1.0 / cell
+            g.nx, g.ny = max(1, int(np.ceil((x1 - x0) / cell))), max(1, int(np.ceil((y1 - y0) / cell)))
+            g.min_nodes, g.cand_cap = int(node_grid_min_nodes), int(node_grid_cand_cap)
+            self._ng_t = [torch.empty((P, g.nx * g.ny), dtype=torch.int32, device=dev),
+                          torch.empty((P, Cn), dtype=torch.int32, device=dev),
+                          torch.empty((P, 2 * g.cand_cap), dtype=torch.int32, device=dev)]
+            g.head, g.next, g.cand = [t.data_ptr() for t in self._ng_t]
+            prm.flags |= FLAG_NODE_GRID
         self.trace_t = torch.zeros((P, max(prm.trace_cap, 1) * TRACE_BYTES), dtype=torch.uint8, device=dev) if trace else None
         self._initialised = False
         smem = _abi.lib.rrtfnd_plan_smem_bytes(C.byref(prm))
@@ -142,6 +160,7 @@ class PlannerBatch:
         b.parent, b.nchild, b.id = self.parent.data_ptr(), self.nchild.data_ptr(), self.id.data_ptr()
         b.nflags = self.nflags.data_ptr()
         b.grid = self.grid
+        b.node_grid = self.node_grid
         b.finish, b.best_path = self.finish.data_ptr(), self.best_path_t.data_ptr()
         b.obst = self.obst.data_ptr()
         b.words = self.words.data_ptr() if self.words is not None else None
@@ -162,6 +181,8 @@ class PlannerBatch:
         """Replace planner p's tree by an existing one (a Graph that already holds nodes): rows in ascending id,
         parents given as ids (-1 = none). Planner-local bookkeeping (finish list, best path) starts empty, as it does
         at the top of the reference's planner functions (src/algorithm.py:113-116)."""
+        if self.prm.flags & FLAG_NODE_GRID:
+            raise ValueError("load_tree is not available with the node grid (it is filled by inserts only)")
         if not self._initialised:
             self.reset()
         ids = np.asarray(ids, dtype=np.int32)

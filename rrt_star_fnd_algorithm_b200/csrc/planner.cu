@@ -143,9 +143,80 @@ static __device__ __noinline__ int key_rank(const double2* XY, int n_slots, doub
     return rank;
 }
 
+// ---- node grid (RRTFND_FLAG_NODE_GRID): candidate lists instead of full scans for large trees -------------------
+
+// Gather the slots of every node in cells [cx0, cx1] x [cy0, cy1] into cand[0 .. cap). Lanes take cells round-robin and
+// walk their linked lists in lock step. Returns the number of nodes found (> cap = overflow, list unusable).
+static __device__ __noinline__ int ng_gather(const int32_t* __restrict__ head, const int32_t* __restrict__ next, int nx,
+                                             int cx0, int cx1, int cy0, int cy1, int32_t* cand, int cap, int lane) {
+    const int w = cx1 - cx0 + 1, n_cells = w * (cy1 - cy0 + 1);
+    const unsigned lt = (1u << lane) - 1u;
+    int n = 0;
+    for (int k0 = 0; k0 < n_cells && n <= cap; k0 += 32) {
+        const int k = k0 + lane;
+        int cur = k < n_cells ? head[(cy0 + k / w) * nx + cx0 + k % w] : -1;
+        for (;;) {
+            const unsigned m = __ballot_sync(kFull, cur >= 0);
+            if (!m) break;
+            if (cur >= 0) {
+                const int pos = n + __popc(m & lt);
+                if (pos < cap) cand[pos] = cur;
+                cur = next[cur];
+            }
+            n += __popc(m);
+        }
+    }
+    __syncwarp();
+    return n;
+}
+
+// ascending sort of n (<= 512) distinct slots by rank counting: out[rank(x)] = x
+static __device__ __noinline__ void ng_sort(const int32_t* in, int32_t* out, int n, int lane) {
+    for (int i = lane; i < n; i += 32) {
+        const int x = in[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += in[j] < x;
+        out[r] = x;
+    }
+    __syncwarp();
+}
+
+// key_rank over a candidate list that holds every node with a key <= (vd, vs)
+static __device__ __noinline__ int ng_key_rank(const double2* XY, const int32_t* list, int n, double qx, double qy, double vd,
+                                               int vs, int lane) {
+    int rank = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool le = false;
+        if (i < n) { const int s = list[i]; const double2 t = XY[s]; const double d = dist2(t.x, t.y, qx, qy); le = d < vd || (d == vd && s <= vs); }
+        rank += __popc(__ballot_sync(kFull, le));
+    }
+    return rank;
+}
+
+// One tile of 128 (slot, position) pairs for a scan body: from the TMA ring when scanning the whole tree, gathered
+// through a candidate list otherwise. Padding has slot -1 / position NaN, for which every predicate is false.
+template <bool NG>
+__device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, const int32_t* list, int n_items, int t, int lane,
+                                           double2 (&v)[4], int (&sl)[4]) {
+    const int base = t * kTileNodes;
+    const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
+    if (NG && list) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = base + 32 * u + lane; sl[u] = i < n_items ? list[i] : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = sl[u] >= 0 ? XY[sl[u]] : nan2;
+    } else {
+        const double2* tile = stream_wait(xs, t);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; sl[u] = s; v[u] = s < n_items ? tile[32 * u + lane] : nan2; }
+        stream_release(xs, XY, n_items, t, lane);
+    }
+}
+
 // WPB warps (= planners) per CTA; MINW = resident warps per SM the register allocation must allow (16 -> 128
 // registers, 24 -> 80, 32 -> 64): small batches get registers, large ones get occupancy.
-template <int WPB, int MINW>
+template <int WPB, int MINW, bool NG>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -183,6 +254,18 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     uint32_t* pre = bm + align_up((size_t)bitmap_words(prm) * 4, 16) / 4;
 
     const Obst ob = make_obst(bt.obst, prm.n_obst, &bt.grid);
+    // node grid (NG kernels only)
+    const rrtfnd_node_grid_t& ng = bt.node_grid;
+    int32_t* HEAD = NG ? ng.head + (size_t)p * ng.nx * ng.ny : nullptr;
+    int32_t* NEXT = NG ? ng.next + (size_t)p * C : nullptr;
+    int32_t* CAND = NG ? ng.cand + (size_t)p * 2 * ng.cand_cap : nullptr;
+    // all nodes within rho cells' width of a point lie in the (2 rho + 1)^2 cells around the point's cell
+    auto ng_window = [&](double x, double y, int rho, int& cx0, int& cx1, int& cy0, int& cy1) {
+        const int cx = grid_cell(x, ng.x0, ng.inv_cell, ng.nx), cy = grid_cell(y, ng.y0, ng.inv_cell, ng.ny);
+        cx0 = max(cx - rho, 0); cx1 = min(cx + rho, ng.nx - 1); cy0 = max(cy - rho, 0); cy1 = min(cy + rho, ng.ny - 1);
+        return cx0 == 0 && cy0 == 0 && cx1 == ng.nx - 1 && cy1 == ng.ny - 1;
+    };
+    auto ng_complete_d2 = [&](int rho) { const double w = rho * ng.cell; return w * w * (1.0 - 1e-9); };
 
     // ---- planner state: warp-uniform, replicated in the registers of every lane
     const double gx = PL->goal_x, gy = PL->goal_y;
@@ -268,23 +351,36 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         int near_slot = -1;
         {
             double bd = CUDART_INF; int bs = kIntMax;
-            const int n_tiles = (n_slots + kTileNodes - 1) / kTileNodes;
-            stream_begin(xs, XY, n_slots, lane);
-            for (int t = 0; t < n_tiles; ++t) {
-                const double2* tile = stream_wait(xs, t);
-                const int base = t * kTileNodes;
-                double2 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = base + 32 * u + lane < n_slots ? tile[32 * u + lane] : nan2;
-                stream_release(xs, XY, n_slots, t, lane);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double d = dist2(v[u].x, v[u].y, qx, qy);                     // NaN for tombstones / padding
-                    if (d < bd) { bd = d; bs = base + 32 * u + lane; }
+            // what the scans below run over: the whole tree (TMA ring), or - node grid - the nodes of a window of cells
+            const int32_t* list = nullptr;
+            int n_items = n_slots, rho = 1;
+            bool covers_all = true;
+            const bool use_ng = NG && n_live >= ng.min_nodes;
+            for (;;) {      // (node grid: widen the window until the nearest node is certain; one pass when scanning)
+                if (use_ng) {
+                    int cx0, cx1, cy0, cy1;
+                    covers_all = ng_window(qx, qy, rho, cx0, cx1, cy0, cy1);
+                    const int n = ng_gather(HEAD, NEXT, ng.nx, cx0, cx1, cy0, cy1, CAND, ng.cand_cap, lane);
+                    if (n > ng.cand_cap) { list = nullptr; n_items = n_slots; covers_all = true; }
+                    else { list = CAND; n_items = n; }
                 }
+                bd = CUDART_INF; bs = kIntMax;
+                const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
+                if (!list) stream_begin(xs, XY, n_slots, lane);
+                for (int t = 0; t < n_tiles; ++t) {
+                    double2 v[4]; int sl[4];
+                    fetch_tile<NG>(xs, XY, list, n_items, t, lane, v, sl);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double d = dist2(v[u].x, v[u].y, qx, qy);                 // NaN for tombstones / padding
+                        if (d < bd || (NG && d == bd && sl[u] < bs)) { bd = d; bs = sl[u]; }
+                    }
+                }
+                warp_argmin(bd, bs);
+                n_scan_nodes += list ? n_items : n_live;
+                if (!list || covers_all || (bs != kIntMax && bd <= ng_complete_d2(rho))) break;
+                rho *= 2;
             }
-            warp_argmin(bd, bs);
-            n_scan_nodes += n_live;
             if (bs == kIntMax) continue;                                          // empty tree (cannot happen)
             if (bd == 0.0) {                                                      // G.id_vertex[vertex] hit (:676-678)
                 const double2 e = XY[bs];
@@ -308,20 +404,25 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 for (;;) {
                     T = dadd(T, T);
                     if (T < t_floor) T = t_floor;
+                    if (NG && list && !covers_all && T > ng_complete_d2(rho)) {    // the window must hold every node within sqrt(T)
+                        rho = max(2 * rho, (int)(sqrt(T) * ng.inv_cell) + 1);
+                        int cx0, cx1, cy0, cy1;
+                        covers_all = ng_window(qx, qy, rho, cx0, cx1, cy0, cy1);
+                        const int n = ng_gather(HEAD, NEXT, ng.nx, cx0, cx1, cy0, cy1, CAND, ng.cand_cap, lane);
+                        if (n > ng.cand_cap) { list = nullptr; n_items = n_slots; covers_all = true; }
+                        else n_items = n;
+                    }
                     double vd = CUDART_INF; int vs = kIntMax;                      // this lane's best visible key
-                    bool beyond = false;
+                    bool beyond = NG && list && !covers_all;
                     int count = 0;
-                    stream_begin(xs, XY, n_slots, lane);
+                    const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
+                    if (!list) stream_begin(xs, XY, n_slots, lane);
                     for (int t = 0; t < n_tiles; ++t) {
-                        const double2* tile = stream_wait(xs, t);
-                        const int base = t * kTileNodes;
-                        double2 v[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) v[u] = base + 32 * u + lane < n_slots ? tile[32 * u + lane] : nan2;
-                        stream_release(xs, XY, n_slots, t, lane);
+                        double2 v[4]; int sl[4];
+                        fetch_tile<NG>(xs, XY, list, n_items, t, lane, v, sl);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int s = base + 32 * u + lane;
+                            const int s = sl[u];
                             const double d = dist2(v[u].x, v[u].y, qx, qy);
                             beyond |= d > T;
                             const bool in = (d > lo_d || (d == lo_d && s > lo_s)) && d <= T;
@@ -329,7 +430,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                             if (in) stage[count + __popc(m & lt_mask)] = s;
                             count += __popc(m);
                         }
-                        const bool last = base + 128 >= n_slots;
+                        const bool last = t + 1 >= n_tiles;
                         int head = 0;
                         while (count - head >= 32 || (last && count > head)) {     // one lane per staged segment
                             const int n = min(count - head, 32);
@@ -349,18 +450,19 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         }
                         if (head > 0) {                                           // keep the (< 32) leftover at the front
                             const int rem = count - head;
-                            const int t = lane < rem ? stage[head + lane] : 0;
+                            const int t2 = lane < rem ? stage[head + lane] : 0;
                             __syncwarp();
-                            if (lane < rem) stage[lane] = t;
+                            if (lane < rem) stage[lane] = t2;
                             count = rem;
                             __syncwarp();
                         }
                     }
-                    n_scan_nodes += n_live;
+                    n_scan_nodes += list ? n_items : n_live;
                     warp_argmin(vd, vs);
                     if (vs != kIntMax) {
                         near_slot = vs;
-                        rounds = key_rank(XY, n_slots, qx, qy, vd, vs, lane);
+                        rounds = (NG && list) ? ng_key_rank(XY, list, n_items, qx, qy, vd, vs, lane)
+                                              : key_rank(XY, n_slots, qx, qy, vd, vs, lane);
                         break;
                     }
                     if (!__any_sync(kFull, beyond)) break;                        // every node tried, none visible
@@ -389,6 +491,10 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             XY[new_slot] = make_double2(px, py);
             ID[new_slot] = id_new; PARENT[new_slot] = near_slot; ECOST[new_slot] = e0;   // :141-142
             NCHILD[new_slot] = 0; NFLAG[new_slot] = 0;
+            if (NG) {                                                             // push onto its cell's list
+                const int c = grid_cell(py, ng.y0, ng.inv_cell, ng.ny) * ng.nx + grid_cell(px, ng.x0, ng.inv_cell, ng.nx);
+                NEXT[new_slot] = HEAD[c]; HEAD[c] = new_slot;
+            }
         }
         __syncwarp();
 
@@ -431,6 +537,15 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         int cp_slot = near_slot; double cp_cost = e0;
         bool dup = false;
         double cost_new = 0.0;
+        // node grid: the ball lies inside the window of cells within `radius` of q_new; its nodes, sorted by slot, replace the scan
+        const int32_t* nlist = nullptr;
+        int n_near_items = n_slots;
+        if (NG && n_live >= ng.min_nodes) {
+            int cx0, cx1, cy0, cy1;
+            ng_window(px, py, (int)(prm.radius * ng.inv_cell) + 1, cx0, cx1, cy0, cy1);
+            const int n = ng_gather(HEAD, NEXT, ng.nx, cx0, cx1, cy0, cy1, CAND, ng.cand_cap, lane);
+            if (n <= ng.cand_cap && n <= 512) { ng_sort(CAND, CAND + ng.cand_cap, n, lane); nlist = CAND + ng.cand_cap; n_near_items = n; }
+        }
         const int n_pass = commit_cp ? 2 : 1;          // committing choose-parent needs its result before any rewire decision
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
@@ -443,31 +558,27 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             bool first = true;
             int count = 0;
             k_total = 0;
-            const int n_tiles = (n_slots + kTileNodes - 1) / kTileNodes;
-            stream_begin(xs, XY, n_slots, lane);
+            const int n_tiles = (n_near_items + kTileNodes - 1) / kTileNodes;
+            if (!nlist) stream_begin(xs, XY, n_slots, lane);
             for (int t = 0; t < n_tiles; ++t) {
-                const double2* tile = stream_wait(xs, t);
-                const int base = t * kTileNodes;
-                double2 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = base + 32 * u + lane < n_slots ? tile[32 * u + lane] : nan2;
-                stream_release(xs, XY, n_slots, t, lane);
+                double2 v[4]; int sl[4];
+                fetch_tile<NG>(xs, XY, nlist, n_near_items, t, lane, v, sl);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int s = base + 32 * u + lane;
+                    const int s = sl[u];
                     const bool in = dist2(v[u].x, v[u].y, px, py) <= r2 && s != new_slot;
                     const unsigned m = __ballot_sync(kFull, in);
                     if (in) stage[count + __popc(m & lt_mask)] = s;
                     count += __popc(m); k_total += __popc(m);
                 }
-                const bool last = base + 128 >= n_slots;
+                const bool last = t + 1 >= n_tiles;
                 int head = 0;
                 while (count - head >= (first ? 31 : 32) || (last && count > head)) {
                     const int n = min(count - head, first ? 31 : 32);
                     __syncwarp();
                     // ---- one chunk: lane i < n owns candidate i; in the first chunk lane 31 walks the new node's chain
                     int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
-                    int w_from = -1; const double w_acc = 0.0;
+                    int w_from = -1;
                     if (lane < n) {
                         s = stage[head + lane];
                         const double2 c = XY[s];
@@ -479,19 +590,22 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         hit = r & 1;
                         if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
                     }
+                    // parent-chain walks, one loop for all lanes (Graph.get_cost, src/graph.py:41-46): lane 31 of the first
+                    // chunk walks the new node's chain, starts from its edge cost and records the addends
+                    const bool rec = first && lane == 31;
                     int depth = 0;
-                    if (first && lane == 31) {                                    // Graph.get_cost(id_new), remembering the addends
-                        int n = walk_from, q = PARENT[n];
-                        cc = walk_acc;
+                    if (rec) { w_from = walk_from; cc = walk_acc; }
+                    if (w_from >= 0) {
+                        int wn = w_from, q = PARENT[wn];
                         while (q >= 0) {
-                            const double e = ECOST[n];
-                            if (depth < kChainCap) chain[depth] = e;
+                            const double e = ECOST[wn];
+                            if (rec && depth < kChainCap) chain[depth] = e;
                             cc = dadd(cc, e);
-                            n = q; q = PARENT[n];
+                            wn = q; q = PARENT[wn];
                             ++depth;
                         }
                         my_hops += depth;
-                    } else if (w_from >= 0) cc = chain_walk(PARENT, ECOST, w_from, w_acc, my_hops);
+                    }
                     __syncwarp();
                     if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; chain_depth = __shfl_sync(kFull, depth, 31); }
                     if (do_cp) {
@@ -544,7 +658,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             }
         }
         if (__any_sync(kFull, dup)) { status = RRTFND_ST_DUPLICATE; break; }
-        n_scan_nodes += n_live;
+        n_scan_nodes += nlist ? n_near_items : n_live;
         n_edge_checks += k_total;
         n_edge_checks_ref += 2 * (long long)k_total + 2;   // each candidate twice + Line(q_new, q_new) twice
 
@@ -733,15 +847,21 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
     PL->n_slots = 1; PL->n_live = 1; PL->last_id = 0; PL->iter = 0; PL->root_slot = 0; PL->n_finish = 0;
     PL->best_len = 0; PL->status = RRTFND_ST_RUNNING; PL->n_rewired = 0; PL->n_removed = 0;
     PL->solution_found = 0; PL->n_compactions = 0; PL->fn_count = 1; PL->reserved = 0;
+    if ((prm.flags & RRTFND_FLAG_NODE_GRID) && bt.node_grid.head) {               // heads were reset to -1 by the host wrapper
+        const rrtfnd_node_grid_t& g = bt.node_grid;
+        const int c = grid_cell(PL->start_y, g.y0, g.inv_cell, g.ny) * g.nx + grid_cell(PL->start_x, g.x0, g.inv_cell, g.nx);
+        g.head[(size_t)p * g.nx * g.ny + c] = 0;
+        g.next[o] = -1;
+    }
 }
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int WPB, int MINW>
+template <int WPB, int MINW, bool NG = false>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
     const size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
-    auto kern = plan_kernel<WPB, MINW>;
+    auto kern = plan_kernel<WPB, MINW, NG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     kern<<<(bt->n_planners + WPB - 1) / WPB, 32 * WPB, bytes, st>>>(*prm, *bt);
@@ -808,6 +928,12 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     cudaStream_t st = (cudaStream_t)stream;
     const PlanCfg cfg = choose_cfg(q, b.n_planners);
     q.reserved = cfg.stages;                    // the kernel reads its ring depth here
+    if (q.flags & RRTFND_FLAG_NODE_GRID) {      // large single trees: node-grid kernel, one planner per CTA
+        const rrtfnd_node_grid_t& g = b.node_grid;
+        if (q.mode == RRTFND_MODE_FN || g.nx <= 0 || g.ny <= 0 || !g.head || !g.next || !g.cand || g.cand_cap < 32 || !(g.inv_cell > 0.0))
+            return RRTFND_E_BADARG;
+        return launch_plan<1, 16, true>(&q, &b, (cudaStream_t)stream);
+    }
     switch (cfg.wpb) {
         case 1: return launch_wpb<1>(&q, &b, cfg.minw, st);
         case 2: return launch_wpb<2>(&q, &b, cfg.minw, st);
@@ -819,6 +945,12 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
 extern "C" int rrtfnd_init_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, void* stream) {
     if (!prm || !bt || bt->n_planners <= 0 || !bt->planners || !bt->xy || !bt->nflags) return RRTFND_E_BADARG;
     const int nt = 128;
+    if ((prm->flags & RRTFND_FLAG_NODE_GRID) && bt->node_grid.head) {
+        const rrtfnd_node_grid_t& g = bt->node_grid;
+        if (g.nx <= 0 || g.ny <= 0 || !g.next) return RRTFND_E_BADARG;
+        cudaError_t e = cudaMemsetAsync(g.head, 0xff, (size_t)bt->n_planners * g.nx * g.ny * sizeof(int32_t), (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     init_kernel<<<(bt->n_planners + nt - 1) / nt, nt, 0, (cudaStream_t)stream>>>(*prm, *bt);
     return (int)cudaGetLastError();
 }

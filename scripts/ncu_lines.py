@@ -6,7 +6,8 @@ import csv, os, re, subprocess, sys, tempfile, collections
 rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "rrt_star_fnd_algorithm_b200", "librrtfnd.so")
+so = os.environ.get("RRTFND_SO", os.path.join(root, "rrt_star_fnd_algorithm_b200", "librrtfnd.so"))
+by_inst = os.environ.get("BY_INST") is not None
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 sass = None
@@ -56,11 +57,12 @@ for r in rows[2:]:
             per[key][2][hdr[i]] += v
     tot += s
 src = {}
-print(f"total samples {tot}")
-for (f, l), (s, ex, st) in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
+tot_inst = sum(v[1] for v in per.values())
+print(f"total samples {tot}, total warp instructions {tot_inst}")
+for (f, l), (s, ex, st) in sorted(per.items(), key=lambda kv: -(kv[1][1] if by_inst else kv[1][0]))[:top]:
     if f not in src:
         p = os.path.join(root, "rrt_star_fnd_algorithm_b200", "csrc", f)
         src[f] = open(p).read().splitlines() if os.path.exists(p) else []
     text = src[f][l - 1].strip()[:90] if 0 < l <= len(src[f]) else ""
     main = ",".join(f"{k[6:]}:{v}" for k, v in st.most_common(3))
-    print(f"{100.0 * s / tot:5.1f}%  {f}:{l:<4d} inst={ex:<12d} [{main}]  {text}")
+    print(f"{100.0 * s / max(tot, 1):5.1f}% samp {100.0 * ex / max(tot_inst, 1):5.1f}% inst  {f}:{l:<4d} [{main}]  {text}")

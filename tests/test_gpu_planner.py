@@ -141,3 +141,36 @@ def test_rewire_list_overflow_path(name):
     assert int(g["rec_n_rewired"].max()) >= 2
     b = make_batch(case, seeds=[case["seed"]], stream_ids=[case["stream_id"]], near_cap=1).run()
     check_against_golden(b, case, g)
+
+
+@pytest.mark.parametrize("name,cell", [("main_star_long", 0.0), ("float_star", 1.5), ("int_star", 40.0), ("main_rrt", 30.0),
+                                       ("float_star", 0.4)])
+def test_node_grid_gives_the_same_tree_as_the_scans(name, cell):
+    """Config 4's node grid answers nearest / near-set queries from a window of cells: identical trees, records, counts."""
+    case, g = K.case_by_name(name), load_golden(name)
+    b = make_batch(case, seeds=[case["seed"]] * 2, stream_ids=[case["stream_id"]] * 2, starts=[case["start"]] * 2,
+                   goals=[case["goal"]] * 2, node_grid=True, node_grid_cell=cell, node_grid_min_nodes=8,
+                   node_grid_cand_cap=64 if cell == 0.4 else 4096).run()     # the tiny cap forces fallbacks to the scan
+    for p in range(2):
+        check_against_golden(b, case, g, p)
+
+
+def test_node_grid_large_tree_matches_the_oracle():
+    """20,000 nodes in a 400 x 400 map, 60 obstacles: grid from 256 nodes on, every node equal to the CPU oracle's."""
+    import oracle as O
+    rng = np.random.default_rng(8)
+    obst = [(float(x), float(y), float(r)) for x, y, r in zip(rng.uniform(20, 380, 60), rng.uniform(20, 380, 60), rng.uniform(3, 12, 60))]
+    case = dict(name="big", mode="star", seed=21, stream_id=3, start=(5.0, 5.0), goal=(390.0, 390.0), xy_range=[[0, 400], [0, 400]],
+                obstacles=obst, iter_num=20000, step_length=2.0, radius=4.0, node_radius=1.0, bias=0.01, max_nodes=0)
+    b = make_batch(case, seeds=[21], stream_ids=[3], trace=False, node_grid=True, node_grid_min_nodes=256,
+                   finish_cap=8192, path_cap=8192).run()
+    b.check_status()
+    t = O.OracleTree(case["start"], case["iter_num"] + 2, finish_cap=8192, path_cap=8192)
+    prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0, finish_cap=8192, path_cap=8192)
+    st, _ = t.run(prm, obst, case["goal"], seed=21, stream_id=3)
+    assert st == S.ST_DONE
+    assert_tree_equal(b.tree(0), t.export(), "big")
+    pl, opl = b.planners()[0], t.planner()
+    for f in ("cursor", "attempts", "best_cost", "n_rewired", "n_edge_checks", "n_edge_checks_ref"):
+        assert pl[f] == getattr(opl, f), f
+    assert pl["n_scan_nodes"] < 0.05 * opl.n_scan_nodes           # the point of the grid
