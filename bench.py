@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--planners", type=int, default=0, help="planners per GPU (0 = workload default)")
     ap.add_argument("--iters", type=int, default=0, help="iterations per planner (0 = workload default)")
     ap.add_argument("--launch", type=int, default=0)
@@ -53,7 +53,7 @@ def parse_args():
 
 
 # default planners per GPU: config 3 is 16,384 planners over 8 GPUs = 2,048 per GPU (weak scaling unit)
-DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 2048}
+DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 2048, "c4": 1}
 
 
 class ClockSampler:
@@ -215,6 +215,8 @@ def main():
     kw = dict(obstacles=w["obstacles"], xy_range=w["xy_range"], iter_num=w["iter_num"], step_length=w["step_length"],
               radius=w["radius"], node_radius=w["node_radius"], bias=w["bias"], max_nodes=w["max_nodes"],
               near_cap=args.near_cap, launch=args.launch)
+    if w.get("node_grid"):
+        kw.update(node_grid=True, finish_cap=65536, path_cap=65536)
     b = PlannerBatch(w["mode"], starts=starts, goals=goals, seeds=seeds, stream_ids=sids, device=dev, **kw)
 
     def barrier():

@@ -49,6 +49,7 @@ def lib():
     L.orc_get_best_path.argtypes = [vp, vp]
     L.orc_get_finish.argtypes = [vp, vp]
     L.orc_through_obstacle.argtypes = [C.c_double] * 4 + [vp, C.c_int]
+    L.orc_through_obstacle_batch.argtypes = [vp, C.c_int64, vp, C.c_int, vp]
     L.orc_is_occupied.argtypes = [C.c_double, C.c_double, vp, C.c_int, C.c_double]
     L.orc_get_cost.restype = C.c_double
     L.orc_get_cost.argtypes = [vp, C.c_int]
@@ -77,9 +78,23 @@ def _ptr(a):
 
 
 def obst_table3(obstacles) -> np.ndarray:
-    """[(ox, oy, r), ...] -> contiguous float64 [M][3]."""
-    a = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 3))
-    return a
+    """[(ox, oy, r), ...] (or rows that already carry K) -> contiguous float64 [M][4]: ox, oy, r, K.
+
+    K = -r ** 2 + ox ** 2 + oy ** 2 is evaluated here in Python on the caller's number types with the reference's own
+    expression (src/algorithm.py:619): `**` on Python numbers is libm pow (exact integers for int obstacles), which is
+    not always fl(r * r)."""
+    rows = []
+    for ob in obstacles:
+        ob = tuple(ob)
+        if len(ob) == 4:
+            rows.append(tuple(float(v) for v in ob))
+            continue
+        x0, y0, r = ob
+        if isinstance(x0, np.generic): x0 = x0.item()
+        if isinstance(y0, np.generic): y0 = y0.item()
+        if isinstance(r, np.generic): r = r.item()
+        rows.append((float(x0), float(y0), float(r), float(-r ** 2 + x0 ** 2 + y0 ** 2)))
+    return np.ascontiguousarray(np.asarray(rows, dtype=np.float64).reshape(-1, 4))
 
 
 class OracleTree:
@@ -180,6 +195,14 @@ class OracleTree:
 def through_obstacle(p1, p2, obstacles) -> bool:
     ob = obst_table3(obstacles)
     return bool(lib().orc_through_obstacle(float(p1[0]), float(p1[1]), float(p2[0]), float(p2[1]), _ptr(ob), len(ob)))
+
+
+def through_obstacle_batch(p1, p2, obstacles) -> np.ndarray:
+    seg = np.ascontiguousarray(np.concatenate([np.asarray(p1, np.float64).reshape(-1, 2), np.asarray(p2, np.float64).reshape(-1, 2)], 1))
+    ob = obst_table3(obstacles)
+    out = np.zeros(len(seg), np.uint8)
+    lib().orc_through_obstacle_batch(_ptr(seg), len(seg), _ptr(ob), len(ob), _ptr(out))
+    return out.astype(bool)
 
 
 def is_occupied(p, obstacles, node_radius) -> bool:

@@ -135,7 +135,10 @@ static double dist2(double nx, double ny, double qx, double qy) {
 }
 
 /* intersection_circle(Line(p1, p2), circle) — src/line.py:5-16, src/algorithm.py:555-578, :594-635 */
-static int seg_hits_circle(double p1x, double p1y, double p2x, double p2y, double ox, double oy, double r) {
+/* K = ((-(r**2)) + ox**2) + oy**2, the circle-only part of `c` (:619), is evaluated by the Python side with the
+ * reference's own expression on the caller's number types (`**` is libm pow there, which differs from r*r by an ulp
+ * for a few radii), exactly as the product's obstacle table is built. */
+static int seg_hits_circle(double p1x, double p1y, double p2x, double p2y, double ox, double oy, double r, double K) {
     if (p2x == p1x) {                         /* src/line.py:9; src/algorithm.py:563-567 */
         return fabs(ox - p1x) <= r;
     }
@@ -143,7 +146,7 @@ static int seg_hits_circle(double p1x, double p1y, double p2x, double p2y, doubl
     double k = p1y - m * p1x;                 /* src/line.py:16 */
     double a = 1.0 + m * m;                   /* src/algorithm.py:617 */
     double b = 2.0 * ((-ox + m * k) - m * oy);            /* :618 */
-    double c = ((((-(r * r)) + ox * ox) + oy * oy) - (2.0 * oy) * k) + k * k; /* :619 */
+    double c = (K - (2.0 * oy) * k) + k * k; /* :619 */
     double delta = b * b - (4.0 * a) * c;     /* :620 */
     if (delta < 0.0) return 0;                /* :569 */
     double s = sqrt(delta);                   /* :602-603 */
@@ -154,12 +157,12 @@ static int seg_hits_circle(double p1x, double p1y, double p2x, double p2y, doubl
     return (x1 > lo && x1 < hi) || (x2 > lo && x2 < hi); /* :576 */
 }
 
-/* through_obstacle (src/algorithm.py:581-591); obst is [M][3] ox, oy, r */
+/* through_obstacle (src/algorithm.py:581-591); obst is [M][4] ox, oy, r, K */
 static int through_obstacle(double p1x, double p1y, double p2x, double p2y, const double* obst, int M,
                             int64_t* n_tests) {
     for (int j = 0; j < M; ++j) {
         if (n_tests) ++*n_tests;
-        if (seg_hits_circle(p1x, p1y, p2x, p2y, obst[3 * j], obst[3 * j + 1], obst[3 * j + 2])) return 1;
+        if (seg_hits_circle(p1x, p1y, p2x, p2y, obst[4 * j], obst[4 * j + 1], obst[4 * j + 2], obst[4 * j + 3])) return 1;
     }
     return 0;
 }
@@ -167,9 +170,9 @@ static int through_obstacle(double p1x, double p1y, double p2x, double p2y, cons
 /* Map.is_occupied_c (src/map.py:38-47) */
 static int is_occupied(double px, double py, const double* obst, int M, double node_radius) {
     for (int j = 0; j < M; ++j) {
-        double dx = px - obst[3 * j], dy = py - obst[3 * j + 1];
+        double dx = px - obst[4 * j], dy = py - obst[4 * j + 1];
         double d = sqrt(dx * dx + dy * dy);
-        if (d < node_radius + obst[3 * j + 2]) return 1;
+        if (d < node_radius + obst[4 * j + 2]) return 1;
     }
     return 0;
 }
@@ -270,6 +273,12 @@ int orc_get_finish(const orc_tree_t* t, int* out) {
 
 int orc_through_obstacle(double p1x, double p1y, double p2x, double p2y, const double* obst, int M) {
     return through_obstacle(p1x, p1y, p2x, p2y, obst, M, 0);
+}
+
+/* many segments at once: seg is [n][4] (p1x, p1y, p2x, p2y) */
+void orc_through_obstacle_batch(const double* seg, int64_t n, const double* obst, int M, unsigned char* out) {
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = (unsigned char)through_obstacle(seg[4 * i], seg[4 * i + 1], seg[4 * i + 2], seg[4 * i + 3], obst, M, 0);
 }
 
 int orc_is_occupied(double px, double py, const double* obst, int M, double node_radius) {
@@ -457,7 +466,7 @@ int orc_get_root(const orc_tree_t* t) { return t->root; }
 /* --------------------------------------------------------------------------------- the planner */
 
 /* One call = the body of RRT / RRT_star / RRT_star_FN (src/algorithm.py:54-265) run until
- * iter == prm->iter_num. obst is [M][3]. trace may be NULL. Returns status. */
+ * iter == prm->iter_num. obst is [M][4]. trace may be NULL. Returns status. */
 int orc_run(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, double gx, double gy,
             const uint32_t* words, int64_t n_words, uint64_t seed, uint64_t stream_id, rrtfnd_trace_t* trace) {
     const int M = prm->n_obst;

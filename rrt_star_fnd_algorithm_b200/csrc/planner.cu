@@ -36,13 +36,16 @@ constexpr int kChainCap = 96;       // edge costs of the new node's parent chain
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline int bitmap_words(const rrtfnd_params_t& prm) { return prm.capacity / 32 + 1; }
+// Compaction keeps a live bitmap + prefix counts in shared memory: always for FN; for the other modes (tombstones only
+// after FND surgery) while the capacity is moderate. Without it a full slot array is a capacity error.
+__host__ __device__ inline bool can_compact(const rrtfnd_params_t& prm) { return prm.mode == RRTFND_MODE_FN || prm.capacity <= 32768; }
 
 // shared memory of one warp: xy ring (n_stages tiles) | mbarriers | word source | chain[kChainCap] | stage[kStage] |
 // rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | live bitmap + prefix counts (compaction)
 __host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
     size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) +
                kChainCap * 8 + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
-    o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);   // any mode: FND surgery leaves tombstones too
+    if (can_compact(prm)) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
     return align_up(o, 128);
 }
 
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             status = RRTFND_ST_NEED_WORDS; break;
         }
         if (n_slots >= C) {
-            if (n_live >= n_slots) { status = RRTFND_ST_CAPACITY; break; }
+            if (n_live >= n_slots || !can_compact(prm)) { status = RRTFND_ST_CAPACITY; break; }
             // ---- A'. stable in-place compaction (FN only; rare)
             compact_tree(XY, ECOST, PARENT, NCHILD, ID, NFLAG, FINISH, n_finish, n_slots, bm, pre, &root_slot, &best_leaf_slot, lane);
             n_slots = n_live;

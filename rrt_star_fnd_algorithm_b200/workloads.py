@@ -49,7 +49,16 @@ def c3():
                 seed_base=3000, planners=16384)
 
 
-WORKLOADS = {"c1": c1, "c2": c2, "c3": c3}
+def c4():
+    """Config 4: one RRT* tree grown to 1M nodes on a 1000x1000 map with 500 circles; near-set / nearest queries go
+    through the device node grid (large-tree stress). Replicas (other streams) fill the GPU; the tree does not shard."""
+    obst = _circles(4, 500, 0, 1000, 2.0, 10.0)
+    return dict(name="c4", mode="star", obstacles=obst, xy_range=[[0.0, 1000.0], [0.0, 1000.0]], iter_num=1000000,
+                step_length=2.0, radius=4.0, node_radius=1.0, bias=0.0, max_nodes=0, start=None, goal=None,
+                seed_base=4000, planners=1, node_grid=True)
+
+
+WORKLOADS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4}
 
 
 def planner_problems(w, first, count):

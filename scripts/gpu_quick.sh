@@ -1,0 +1,4 @@
+set -x
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -12
+python scripts/perf_probe.py c3 2048 5000 1 0 64
+python scripts/perf_probe.py c2 4096 5000 1 0 64

@@ -15,7 +15,8 @@ cell = float(sys.argv[7]) if len(sys.argv) > 7 else 0.0
 s, g, seeds, sids = W.planner_problems(w, 0, P)
 b = PlannerBatch(w["mode"], starts=s, goals=g, obstacles=w["obstacles"], xy_range=w["xy_range"], iter_num=w["iter_num"],
                  step_length=w["step_length"], radius=w["radius"], node_radius=w["node_radius"], bias=w["bias"],
-                 max_nodes=w["max_nodes"], seeds=seeds, stream_ids=sids, eval_choose_parent=ecp, launch=launch, near_cap=ncap, grid_cell=cell)
+                 max_nodes=w["max_nodes"], seeds=seeds, stream_ids=sids, eval_choose_parent=ecp, launch=launch, near_cap=ncap, grid_cell=cell,
+                 **(dict(node_grid=True, finish_cap=65536, path_cap=65536, node_grid_cell=float(os.environ.get("NG_CELL", 0)), node_grid_min_nodes=int(os.environ.get("NG_MIN", 4096))) if w.get("node_grid") or os.environ.get("NODE_GRID") else {}))
 for rep in range(2):
     b.reset(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

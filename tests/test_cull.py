@@ -75,8 +75,8 @@ def test_culled_edge_and_point_operators_equal_the_full_ones(workload):
     assert 0.02 < full.mean() < 0.98
     bad = np.flatnonzero(full != cull)
     assert bad.size == 0, (bad[:5], p1[bad[:5]], p2[bad[:5]])
-    for i in rng.integers(0, n, 300):                             # and both equal the CPU oracle
-        assert bool(full[i]) == O.through_obstacle(p1[i], p2[i], w["obstacles"])
+    want = O.through_obstacle_batch(p1, p2, w["obstacles"])      # and both equal the CPU oracle (no pre-check, no culling)
+    assert np.array_equal(full.astype(bool), want)
     # points
     pts = rng.uniform(x0, x1, (n, 2))
     tx, ty = d(pts[:, 0]), d(pts[:, 1])
@@ -89,3 +89,43 @@ def test_culled_edge_and_point_operators_equal_the_full_ones(workload):
     assert np.array_equal(of, oc)
     for i in rng.integers(0, n, 300):
         assert bool(of[i]) == O.is_occupied(pts[i], w["obstacles"], w["node_radius"])
+
+
+@pytest.mark.gpu
+def test_root_precheck_borderline_segments_equal_the_oracle():
+    """Segments whose endpoint x sits within ulps of an intersection root (the pre-check's margin decides nothing there:
+    they must fall through to the exact arithmetic), plus tangent lines and segments wholly inside a circle."""
+    import torch
+    from rrt_star_fnd_algorithm_b200 import _abi
+    from rrt_star_fnd_algorithm_b200.batch import obstacle_table
+    rng = np.random.default_rng(17)
+    obst = [(float(x), float(y), float(r)) for x, y, r in zip(rng.uniform(10, 190, 40), rng.uniform(10, 190, 40), rng.uniform(1, 9, 40))]
+    ob = np.asarray(obst)
+    n = 300_000
+    j = rng.integers(0, len(ob), n)
+    th = rng.uniform(0, 2 * np.pi, n)
+    m = np.tan(rng.uniform(-1.5, 1.5, n))                             # line through a rim point with slope m
+    rim = ob[j, :2] + ob[j, 2:3] * np.column_stack([np.cos(th), np.sin(th)])
+    eps = rng.choice([0.0, 1e-16, -1e-16, 3e-16, -3e-16, 1e-13, -1e-13, 1e-10, -1e-10, 1e-7, 1e-3], n) * np.maximum(np.abs(rim[:, 0]), 1.0)
+    L = np.exp(rng.uniform(np.log(1e-3), np.log(60.0), n)) * rng.choice([-1.0, 1.0], n)
+    p1 = np.column_stack([rim[:, 0] + eps, rim[:, 1] + m * eps])      # an endpoint (almost) exactly on the circle, on the line
+    p2 = np.column_stack([p1[:, 0] + L, p1[:, 1] + m * L])
+    k = n // 6
+    inside = ob[j[:k], :2] + 0.3 * ob[j[:k], 2:3] * rng.uniform(-1, 1, (k, 2))      # both endpoints inside one circle
+    p1[:k], p2[:k] = inside, ob[j[:k], :2] + 0.3 * ob[j[:k], 2:3] * rng.uniform(-1, 1, (k, 2))
+    tang = slice(k, 2 * k)                                             # tangent lines: delta ~ 0
+    nrm = np.column_stack([np.cos(th[tang]), np.sin(th[tang])]); tan_dir = np.column_stack([-nrm[:, 1], nrm[:, 0]])
+    c = ob[j[tang], :2] + ob[j[tang], 2:3] * nrm * (1 + rng.choice([0, 1e-15, -1e-15, 1e-12, -1e-12], k)[:, None])
+    p1[tang], p2[tang] = c - tan_dir * rng.uniform(0.1, 30, (k, 1)), c + tan_dir * rng.uniform(0.1, 30, (k, 1))
+    dev = torch.device("cuda:0")
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tp = [d(p1[:, 0]), d(p1[:, 1]), d(p2[:, 0]), d(p2[:, 1])]
+    tob = d(obstacle_table(obst))
+    out = torch.zeros(n, dtype=torch.uint8, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    _abi.check(_abi.lib.rrtfnd_edges_vs_circles(*[ptr(t) for t in tp], n, ptr(tob), len(obst), ptr(out), None), "full")
+    torch.cuda.synchronize()
+    got, want = out.cpu().numpy().astype(bool), O.through_obstacle_batch(p1, p2, obst)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, (bad[:5], p1[bad[:5]], p2[bad[:5]])
+    assert 0.1 < want.mean() < 0.9
