@@ -4,7 +4,7 @@
 A *step* is one complete run of the workload's planners owned by this rank: every tree is re-initialised
 to its root and grown for `iter_num` successful iterations (sample -> occupancy -> nearest visible ->
 steer -> insert -> near set -> collision checks -> choose-parent -> rewire -> goal / best-path bookkeeping).
-Weak scaling: every rank owns `--planners` planners (global planner index = rank * planners + i, so a
+Weak scaling: every rank owns `--planners` planners (default 16,384 = config 3 on one GPU; global planner index = rank * planners + i, so a
 planner's problem and tree do not depend on the sharding); after its planners finish, a rank takes part in
 one NCCL all_gather of the per-planner result records and one broadcast of the globally best path.
 
@@ -52,8 +52,10 @@ def parse_args():
     return ap.parse_args()
 
 
-# default planners per GPU: config 3 is 16,384 planners over 8 GPUs = 2,048 per GPU (weak scaling unit)
-DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 2048, "c4": 1}
+# default planners per GPU. c3 at N=1 is BASELINE.json's config 3 as written (16,384 planners on one B200, 3 GB of tree
+# state); with weak scaling every further GPU gets a batch of the same size. 16,384 planners are ~7 waves of resident
+# warps per SM, which also evens out the planner-to-planner variance that leaves SMs idle at the end of a 1-wave launch.
+DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 16384, "c4": 1}
 
 
 class ClockSampler:

@@ -59,7 +59,7 @@ static __device__ __noinline__ void stream_begin_impl(uint32_t ring, uint32_t ba
 }
 __device__ __forceinline__ void stream_begin(const XYStream& st, const double2* xy, int n_slots, int lane) {
     __syncwarp();
-    if (lane == 0) stream_begin_impl(st.ring, st.bars, st.n_stages, xy, n_slots);
+    if (lane == 0 && st.n_stages > 0) stream_begin_impl(st.ring, st.bars, st.n_stages, xy, n_slots);
 }
 
 // Wait for tile t; returns its shared-memory address (generic pointer to 128 double2, the tail of the last tile is stale)
