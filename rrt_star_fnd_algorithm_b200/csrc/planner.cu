@@ -40,6 +40,15 @@ __host__ __device__ inline int bitmap_words(const rrtfnd_params_t& prm) { return
 // after FND surgery) while the capacity is moderate. Without it a full slot array is a capacity error.
 __host__ __device__ inline bool can_compact(const rrtfnd_params_t& prm) { return prm.mode == RRTFND_MODE_FN || prm.capacity <= 32768; }
 
+// shared memory of one warp: xy ring (n_stages tiles) | mbarriers | word source | chain[kChainCap] | stage[kStage] |
+// rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | live bitmap + prefix counts (compaction)
+__host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
+    size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) +
+               kChainCap * 8 + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
+    if (can_compact(prm)) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
+    return align_up(o, 128);
+}
+
 // ------------------------------------------------------------------------------------ warp helpers
 
 // (value, index) argmin over the warp for NON-NEGATIVE doubles (their bit patterns order like unsigned integers),
@@ -211,765 +220,623 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
     }
 }
 
-// ---- the planner of one warp ---------------------------------------------------------------------------------------------
-//
-// The kernel body is a short loop over PHASES, each a non-inlined function. Everything a planner carries from one phase
-// to the next - its counters, the current sample, the new node - lives in a per-warp shared-memory record (WarpCtx) that
-// every lane reads by broadcast and writes with the same value, so no phase inherits live registers from another: the
-// register allocation is the maximum over the phases, not their union, and 32 warps fit an SM without spills.
+// WPB warps (= planners) per CTA; MINW = resident warps per SM the register allocation must allow (16 -> 128
+// registers, 24 -> 80, 32 -> 64): small batches get registers, large ones get occupancy.
+template <int WPB, int MINW, bool NG>
+__global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int p = blockIdx.x * WPB + wib;
+    if (p >= bt.n_planners) return;                       // whole warp leaves; warps never synchronise with each other
+    const int C = prm.capacity;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
-struct WarpCtx {
+    // per-planner global arrays
+    double2* XY = reinterpret_cast<double2*>(bt.xy) + (size_t)p * C;
+    double* ECOST = bt.ecost + (size_t)p * C;
+    int32_t* PARENT = bt.parent + (size_t)p * C;
+    int32_t* NCHILD = bt.nchild + (size_t)p * C;
+    int32_t* ID = bt.id + (size_t)p * C;
+    uint8_t* NFLAG = bt.nflags + (size_t)p * C;
+    int32_t* FINISH = bt.finish + (size_t)p * prm.finish_cap;
+    int32_t* BPATH = bt.best_path + (size_t)p * prm.path_cap;
+    rrtfnd_planner_t* PL = bt.planners + p;
+    rrtfnd_trace_t* TRACE = bt.trace ? bt.trace + (size_t)p * prm.trace_cap : nullptr;
+
+    // per-warp shared memory
+    const int n_stages = prm.reserved;                 // resolved by the host wrapper (2 or 4)
+    unsigned char* ws = smem + (size_t)wib * warp_smem_bytes(prm, n_stages);
+    unsigned char* wp = ws + (size_t)n_stages * kTileBytes;
     XYStream xs;
-    // planner state (rrtfnd_planner_t fields, loaded at the start and written back at the end)
-    double gx, gy, best_cost;
-    long long attempts, n_edge_checks, n_edge_checks_ref, n_scan_nodes, n_hops, n_tests;
-    int n_slots, n_live, last_id, iter, root_slot, n_finish, best_len, status;
-    int n_rewired, n_removed, solution_found, n_compactions, fn_count, best_leaf_slot, n_childless;
-    // the current attempt / iteration
-    double qx, qy, px, py, e0, cp_cost;
-    int near_slot, new_slot, id_new, reached, k_total, n_rw, cp_parent_id, removed_id, need_refresh, pad;
-};
+    stream_init(xs, ws, wp, n_stages, lane);
+    wp += align_up((size_t)n_stages * 8, 16);
+    WordSrc& rng = *reinterpret_cast<WordSrc*>(wp);    // identical values written by every lane
+    wp += align_up(sizeof(WordSrc), 16);
+    double* chain = reinterpret_cast<double*>(wp);     // edge costs along the new node's parent chain, leaf side first
+    wp += kChainCap * 8;
+    int* stage = reinterpret_cast<int*>(wp);
+    int* rwlist = stage + kStage;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(rwlist + align_up((size_t)prm.near_cap * 4, 16) / 4);
+    uint32_t* pre = bm + align_up((size_t)bitmap_words(prm) * 4, 16) / 4;
 
-// shared memory of one warp: xy ring (n_stages tiles) | mbarriers | WarpCtx | word source | chain[kChainCap] | stage[kStage] |
-// rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | live bitmap + prefix counts (compaction)
-__host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
-    size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WarpCtx), 16) +
-               align_up(sizeof(WordSrc), 16) + kChainCap * 8 + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
-    if (can_compact(prm)) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
-    return align_up(o, 128);
-}
+    const Obst ob = make_obst(bt.obst, prm.n_obst, &bt.grid);
+    // node grid (NG kernels only)
+    const rrtfnd_node_grid_t& ng = bt.node_grid;
+    int32_t* HEAD = NG ? ng.head + (size_t)p * ng.nx * ng.ny : nullptr;
+    int32_t* NEXT = NG ? ng.next + (size_t)p * C : nullptr;
+    int32_t* CAND = NG ? ng.cand + (size_t)p * 2 * ng.cand_cap : nullptr;
+    // all nodes within rho cells' width of a point lie in the (2 rho + 1)^2 cells around the point's cell
+    auto ng_window = [&](double x, double y, int rho, int& cx0, int& cx1, int& cy0, int& cy1) {
+        const int cx = grid_cell(x, ng.x0, ng.inv_cell, ng.nx), cy = grid_cell(y, ng.y0, ng.inv_cell, ng.ny);
+        cx0 = max(cx - rho, 0); cx1 = min(cx + rho, ng.nx - 1); cy0 = max(cy - rho, 0); cy1 = min(cy + rho, ng.ny - 1);
+        return cx0 == 0 && cy0 == 0 && cx1 == ng.nx - 1 && cy1 == ng.ny - 1;
+    };
+    auto ng_complete_d2 = [&](int rho) { const double w = rho * ng.cell; return w * w * (1.0 - 1e-9); };
 
-// Everything a phase needs, re-derived from the kernel parameters and the warp's shared-memory base (cheap integer math).
-struct Warp {
-    const rrtfnd_params_t* prm;
-    const rrtfnd_batch_t* bt;
-    WarpCtx* c;
-    WordSrc* rng;
-    double* chain;
-    int* stage; int* rwlist; uint32_t* bm; uint32_t* pre;
-    double2* XY; double* ECOST; int32_t* PARENT; int32_t* NCHILD; int32_t* ID; uint8_t* NFLAG; int32_t* FINISH; int32_t* BPATH;
-    int32_t* HEAD; int32_t* NEXT; int32_t* CAND;
-    int lane, p;
-};
+    // ---- planner state: warp-uniform, replicated in the registers of every lane
+    const double gx = PL->goal_x, gy = PL->goal_y;
+    double best_cost = PL->best_cost;
+    long long attempts = PL->attempts, n_edge_checks = PL->n_edge_checks, n_edge_checks_ref = PL->n_edge_checks_ref;
+    long long n_scan_nodes = PL->n_scan_nodes;
+    int n_slots = PL->n_slots, n_live = PL->n_live, last_id = PL->last_id, iter = PL->iter, root_slot = PL->root_slot;
+    int n_finish = PL->n_finish, best_len = PL->best_len, status = RRTFND_ST_RUNNING;
+    int n_rewired = PL->n_rewired, n_removed = PL->n_removed, solution_found = PL->solution_found;
+    int n_compactions = PL->n_compactions;
+    int fn_count = PL->fn_count;             // n_of_nodes of RRT_star_FN (:209): counts this call's nodes, not the live ones
+    long long my_hops = 0, my_tests = 0;     // per-lane counters, summed at the end
 
-__device__ __forceinline__ Warp make_warp(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    Warp w;
-    w.prm = prm; w.bt = bt;
-    w.lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    w.p = blockIdx.x * (blockDim.x >> 5) + wib;
-    const int n_stages = prm->reserved;                  // ring depth, resolved by the host wrapper (0 = plain loads)
-    unsigned char* wp = smem_base + (size_t)wib * warp_smem_bytes(*prm, n_stages) + (size_t)n_stages * kTileBytes +
-                        align_up((size_t)n_stages * 8, 16);
-    w.c = reinterpret_cast<WarpCtx*>(wp); wp += align_up(sizeof(WarpCtx), 16);
-    w.rng = reinterpret_cast<WordSrc*>(wp); wp += align_up(sizeof(WordSrc), 16);
-    w.chain = reinterpret_cast<double*>(wp); wp += kChainCap * 8;
-    w.stage = reinterpret_cast<int*>(wp);
-    w.rwlist = w.stage + kStage;
-    w.bm = reinterpret_cast<uint32_t*>(w.rwlist + align_up((size_t)prm->near_cap * 4, 16) / 4);
-    w.pre = w.bm + align_up((size_t)bitmap_words(*prm) * 4, 16) / 4;
-    const size_t o = (size_t)w.p * prm->capacity;
-    w.XY = reinterpret_cast<double2*>(bt->xy) + o; w.ECOST = bt->ecost + o; w.PARENT = bt->parent + o; w.NCHILD = bt->nchild + o;
-    w.ID = bt->id + o; w.NFLAG = bt->nflags + o;
-    w.FINISH = bt->finish + (size_t)w.p * prm->finish_cap; w.BPATH = bt->best_path + (size_t)w.p * prm->path_cap;
-    const rrtfnd_node_grid_t& ng = bt->node_grid;
-    const bool has_ng = (prm->flags & RRTFND_FLAG_NODE_GRID) != 0;
-    w.HEAD = has_ng ? ng.head + (size_t)w.p * ng.nx * ng.ny : nullptr;
-    w.NEXT = has_ng ? ng.next + o : nullptr;
-    w.CAND = has_ng ? ng.cand + (size_t)w.p * 2 * ng.cand_cap : nullptr;
-    return w;
-}
-
-// per-phase work counters -> the warp's totals
-__device__ __forceinline__ void add_counters(const Warp& w, int hops, int tests) {
-    hops = __reduce_add_sync(kFull, hops); tests = __reduce_add_sync(kFull, tests);
-    __syncwarp();
-    if (w.lane == 0) { w.c->n_hops += hops; w.c->n_tests += tests; }
-    __syncwarp();
-}
-
-// all nodes within rho cells' width of a point lie in the (2 rho + 1)^2 cells around the point's cell
-__device__ __forceinline__ bool ng_window(const rrtfnd_node_grid_t& ng, double x, double y, int rho, int& cx0, int& cx1, int& cy0, int& cy1) {
-    const int cx = grid_cell(x, ng.x0, ng.inv_cell, ng.nx), cy = grid_cell(y, ng.y0, ng.inv_cell, ng.ny);
-    cx0 = max(cx - rho, 0); cx1 = min(cx + rho, ng.nx - 1); cy0 = max(cy - rho, 0); cy1 = min(cy + rho, ng.ny - 1);
-    return cx0 == 0 && cy0 == 0 && cx1 == ng.nx - 1 && cy1 == ng.ny - 1;
-}
-__device__ __forceinline__ double ng_complete_d2(const rrtfnd_node_grid_t& ng, int rho) { const double w = rho * ng.cell; return w * w * (1.0 - 1e-9); }
-
-enum { kNext = 0, kRetry = 1, kStop = 2 };
-
-// ================================================================ phase 1: one attempt up to the nearest visible node
-// A. header checks  B. sample (Graph.random_node) + Map.is_occupied_c  C. nearest_node_kdtree (:666-699)
-// The reference asks the k-d tree for the 1st, 2nd, 3rd ... nearest node until one is visible. Round 0 here is that first
-// query (plain argmin). If it is blocked, the remaining order is consumed in annuli of doubling squared radius: every node
-// of an annulus is tested (one lane per segment) and the lowest (d2, slot) key among the visible ones is the node the
-// reference would have stopped at, because everything in earlier annuli was blocked. A boxed-in sample therefore costs
-// O(log N) scans instead of O(N).
-template <bool NG>
-static __device__ __noinline__ int phase_attempt(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    const Warp w = make_warp(prm, bt, smem_base);
-    WarpCtx& c = *w.c;
-    WordSrc& rng = *w.rng;
-    const int lane = w.lane;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    double2* XY = w.XY;
-    int* stage = w.stage;
-    const rrtfnd_node_grid_t& ng = bt->node_grid;
-
-    if (c.iter >= prm->iter_num) { c.status = RRTFND_ST_DONE; return kStop; }
-    if (prm->max_attempts > 0 && c.attempts >= prm->max_attempts) { c.status = RRTFND_ST_ATTEMPT_CAP; return kStop; }
-    if (prm->stream_mode == RRTFND_STREAM_WORDS && (long long)rng.cursor + kReserveWords > prm->words_per_planner) {
-        c.status = RRTFND_ST_NEED_WORDS; return kStop;
-    }
-    if (c.n_slots >= prm->capacity) {
-        if (c.n_live >= c.n_slots || !can_compact(*prm)) { c.status = RRTFND_ST_CAPACITY; return kStop; }
-        // stable in-place compaction (FN, or tombstones left by FND surgery; rare)
-        int root = c.root_slot, leaf = c.best_leaf_slot;
-        compact_tree(XY, w.ECOST, w.PARENT, w.NCHILD, w.ID, w.NFLAG, w.FINISH, c.n_finish, c.n_slots, w.bm, w.pre, &root, &leaf, lane);
-        c.root_slot = root; c.best_leaf_slot = leaf;
-        c.n_slots = c.n_live;
-        c.n_compactions += 1;
-    }
-    c.attempts += 1;
-    const int n_slots = c.n_slots, n_live = c.n_live;
-    // Graph.random_node (src/graph.py:96-98)
-    double qx, qy;
-    if (next_random(rng) < prm->bias) { qx = c.gx; qy = c.gy; }
-    else {
-        qx = dadd(prm->x_lo, dmul(dsub(prm->x_hi, prm->x_lo), next_random(rng)));
-        qy = dadd(prm->y_lo, dmul(dsub(prm->y_hi, prm->y_lo), next_random(rng)));
-    }
-    const Obst ob = make_obst(bt->obst, prm->n_obst, &bt->grid);
-    int tests = 0;
-    {   // Map.is_occupied_c (src/map.py:38-47); rejected at src/algorithm.py:39-40
-        long long t = 0;
-        const bool occ = point_occupied_warp(ob, qx, qy, prm->node_radius, lane, t);
-        tests += (int)t;
-        if (occ) { add_counters(w, 0, tests); return kRetry; }
-    }
-
-    int near_slot = -1, rounds = 1;
-    long long scanned = 0;
-    double bd = CUDART_INF; int bs = kIntMax;
-    // what the scans below run over: the whole tree (TMA ring), or - node grid - the nodes of a window of cells
-    const int32_t* list = nullptr;
-    int n_items = n_slots, rho = 1;
-    bool covers_all = true;
-    const bool use_ng = NG && n_live >= ng.min_nodes;
-    for (;;) {      // (node grid: widen the window until the nearest node is certain; one pass when scanning)
-        if (use_ng) {
-            int cx0, cx1, cy0, cy1;
-            covers_all = ng_window(ng, qx, qy, rho, cx0, cx1, cy0, cy1);
-            const int n = ng_gather(w.HEAD, w.NEXT, ng.nx, cx0, cx1, cy0, cy1, w.CAND, ng.cand_cap, lane);
-            if (n > ng.cand_cap) { list = nullptr; n_items = n_slots; covers_all = true; }
-            else { list = w.CAND; n_items = n; }
-        }
-        bd = CUDART_INF; bs = kIntMax;
-        const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
-        if (!list) stream_begin(c.xs, XY, n_slots, lane);
-        for (int t = 0; t < n_tiles; ++t) {
-            double2 v[4]; int sl[4];
-            fetch_tile<NG>(c.xs, XY, list, n_items, t, lane, v, sl);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double d = dist2(v[u].x, v[u].y, qx, qy);                 // NaN for tombstones / padding
-                if (d < bd || (NG && d == bd && sl[u] < bs)) { bd = d; bs = sl[u]; }
-            }
-        }
-        warp_argmin(bd, bs);
-        scanned += list ? n_items : n_live;
-        if (!list || covers_all || (bs != kIntMax && bd <= ng_complete_d2(ng, rho))) break;
-        rho *= 2;
-    }
-    bool reject = bs == kIntMax;                                              // empty tree (cannot happen)
-    if (!reject && bd == 0.0) {                                               // G.id_vertex[vertex] hit (:676-678), rejected at :45
-        const double2 e = XY[bs];
-        reject = (e.x == qx && e.y == qy);
-        if (!reject) reject = any_exact_match(XY, n_slots, qx, qy, lane);     // d2 underflowed to 0 without equality
-    }
-    if (reject) { c.n_scan_nodes += scanned; add_counters(w, 0, tests); return kRetry; }
-    {   // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692); the warp shares the one segment
-        const double2 nb = XY[bs];
-        const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, lane, 32);
-        tests += r >> 1;
-        if (!__any_sync(kFull, r & 1)) near_slot = bs;
-    }
-    if (near_slot < 0 && n_live > 1) {
-        double lo_d = bd; int lo_s = bs;                                      // keys <= (lo_d, lo_s) are known to be blocked
-        double T = bd;
-        const double t_floor = dmul(dmul(prm->step_length, prm->step_length), 0.0625);
-        rounds = n_live;                                                      // if nothing is visible every node was tried
-        for (;;) {
-            T = dadd(T, T);
-            if (T < t_floor) T = t_floor;
-            if (NG && list && !covers_all && T > ng_complete_d2(ng, rho)) {   // the window must hold every node within sqrt(T)
-                rho = max(2 * rho, (int)(sqrt(T) * ng.inv_cell) + 1);
-                int cx0, cx1, cy0, cy1;
-                covers_all = ng_window(ng, qx, qy, rho, cx0, cx1, cy0, cy1);
-                const int n = ng_gather(w.HEAD, w.NEXT, ng.nx, cx0, cx1, cy0, cy1, w.CAND, ng.cand_cap, lane);
-                if (n > ng.cand_cap) { list = nullptr; n_items = n_slots; covers_all = true; }
-                else n_items = n;
-            }
-            double vd = CUDART_INF; int vs = kIntMax;                          // this lane's best visible key
-            bool beyond = NG && list && !covers_all;
-            int count = 0;
-            const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
-            if (!list) stream_begin(c.xs, XY, n_slots, lane);
-            for (int t = 0; t < n_tiles; ++t) {
-                double2 v[4]; int sl[4];
-                fetch_tile<NG>(c.xs, XY, list, n_items, t, lane, v, sl);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int s = sl[u];
-                    const double d = dist2(v[u].x, v[u].y, qx, qy);
-                    beyond |= d > T;
-                    const bool in = (d > lo_d || (d == lo_d && s > lo_s)) && d <= T;
-                    const unsigned m = __ballot_sync(kFull, in);
-                    if (in) stage[count + __popc(m & lt_mask)] = s;
-                    count += __popc(m);
-                }
-                const bool last = t + 1 >= n_tiles;
-                int head = 0;
-                while (count - head >= 32 || (last && count > head)) {         // one lane per staged segment
-                    const int n = min(count - head, 32);
-                    __syncwarp();
-                    if (lane < n) {
-                        const int s = stage[head + lane];
-                        const double2 nb = XY[s];
-                        const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, 0, 1);
-                        tests += r >> 1;
-                        if (!(r & 1)) {
-                            const double d = dist2(nb.x, nb.y, qx, qy);
-                            if (d < vd || (d == vd && s < vs)) { vd = d; vs = s; }
-                        }
-                    }
-                    __syncwarp();
-                    head += n;
-                }
-                if (head > 0) {                                               // keep the (< 32) leftover at the front
-                    const int rem = count - head;
-                    const int t2 = lane < rem ? stage[head + lane] : 0;
-                    __syncwarp();
-                    if (lane < rem) stage[lane] = t2;
-                    count = rem;
-                    __syncwarp();
-                }
-            }
-            scanned += list ? n_items : n_live;
-            warp_argmin(vd, vs);
-            if (vs != kIntMax) {
-                near_slot = vs;
-                // the reference's query count = rank of the winner in (d2, slot) order
-                rounds = (NG && list) ? ng_key_rank(XY, list, n_items, qx, qy, vd, vs, lane) : key_rank(XY, n_slots, qx, qy, vd, vs, lane);
-                break;
-            }
-            if (!__any_sync(kFull, beyond)) break;                            // every node tried, none visible
-            lo_d = T; lo_s = kIntMax;
-        }
-    }
-    c.n_scan_nodes += scanned;
-    c.n_edge_checks += rounds; c.n_edge_checks_ref += rounds;
-    add_counters(w, 0, tests);
-    if (near_slot < 0) return kRetry;                                         // :45-46
-    c.qx = qx; c.qy = qy; c.near_slot = near_slot;
-    return kNext;
-}
-
-// ================================================================ phase 2: steer + insert (every lane computes, lane 0 stores)
-template <bool NG>
-static __device__ __noinline__ int phase_insert(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    const Warp w = make_warp(prm, bt, smem_base);
-    WarpCtx& c = *w.c;
-    const int lane = w.lane, near_slot = c.near_slot;
-    const double qx = c.qx, qy = c.qy;
-    const double2 nb = w.XY[near_slot];
-    double px = qx, py = qy;
-    {
-        const double d = dist_fma(qx, qy, nb.x, nb.y);                        // steer (:739)
-        const double ux = ddiv(dsub(qx, nb.x), d), uy = ddiv(dsub(qy, nb.y), d);
-        const double tx = dadd(nb.x, dmul(ux, prm->step_length)), ty = dadd(nb.y, dmul(uy, prm->step_length));
-        if (d > prm->step_length) { px = tx; py = ty; }
-    }
-    const int new_slot = c.n_slots;
-    const int id_new = c.last_id + 1;                                         // Graph.add_vertex (src/graph.py:57-61)
-    c.n_slots = new_slot + 1; c.last_id = id_new;
-    c.n_live += 1; c.fn_count += 1;                                           // n_of_nodes += 1 (:221)
-    const double e0 = dist_fma(px, py, nb.x, nb.y);                           // :49
-    const bool reached = dist_fma(px, py, c.gx, c.gy) < dmul(2.0, prm->goal_node_radius);   // check_solution (:757-758)
-    c.px = px; c.py = py; c.e0 = e0; c.new_slot = new_slot; c.id_new = id_new; c.reached = reached;
-    if (lane == 0) {
-        w.XY[new_slot] = make_double2(px, py);
-        w.ID[new_slot] = id_new; w.PARENT[new_slot] = near_slot; w.ECOST[new_slot] = e0;   // :141-142
-        w.NCHILD[new_slot] = 0; w.NFLAG[new_slot] = 0;
-        if (NG) {                                                             // push onto its cell's list
-            const rrtfnd_node_grid_t& ng = bt->node_grid;
-            const int cell = grid_cell(py, ng.y0, ng.inv_cell, ng.ny) * ng.nx + grid_cell(px, ng.x0, ng.inv_cell, ng.nx);
-            w.NEXT[new_slot] = w.HEAD[cell]; w.HEAD[cell] = new_slot;
-        }
-    }
-    __syncwarp();
-    if (prm->mode != RRTFND_MODE_RRT) return kNext;
-
-    // ---- RRT (:76-84): add_edge, goal test, no near set
-    int L = 0; double cost = 0.0; int hops = 0;
-    rrtfnd_trace_t* TRACE = bt->trace ? bt->trace + (size_t)w.p * prm->trace_cap : nullptr;
-    if (lane == 0) {
-        w.NCHILD[near_slot] += 1;                                             // add_edge (:76)
-        if (reached) {                                                        // :78-81, break before iter += 1
-            int n = new_slot;
-            while (n != c.root_slot && n >= 0) {
-                if (L < prm->path_cap) w.BPATH[L] = w.ID[n];
-                ++L; cost = dadd(cost, w.ECOST[n]); n = w.PARENT[n]; ++hops;
-            }
-            if (L < prm->path_cap) w.BPATH[L] = w.ID[c.root_slot];
-            ++L;
-        }
-        if (TRACE && c.iter < prm->trace_cap) {
-            rrtfnd_trace_t t; t.id_new = id_new; t.id_near = w.ID[near_slot]; t.n_near = 0; t.n_rewired = 0;
-            t.removed_id = -1; t.cp_parent = -1; t.cp_cost = 0.0;
-            TRACE[c.iter] = t;
-        }
-    }
-    __syncwarp();
-    add_counters(w, hops, 0);
-    if (reached) {
-        const int len = __shfl_sync(kFull, L, 0);
-        c.best_len = len; c.best_cost = __shfl_sync(kFull, cost, 0);
-        c.best_leaf_slot = new_slot; c.solution_found = 1;
-        c.status = len > prm->path_cap ? RRTFND_ST_PATH_CAP : RRTFND_ST_DONE;
-        return kStop;
-    }
-    c.iter += 1;
-    return kRetry;                                                            // next attempt
-}
-
-// ================================================================ phase 3: near set -> collision, costs, choose-parent, rewire
-// The ball (query_ball_point, :837 / :893) is produced in ascending slot order by the scan and handed to the lanes in chunks
-// of up to 32 candidates: lane i owns candidate i (its own segment test, its own parent-chain walk). In the first chunk
-// lane 31 walks the new node's chain (Graph.get_cost(id_new)). Rewire decisions are taken against the pre-rewire tree and
-// committed after the scan.
-template <bool NG>
-static __device__ __noinline__ int phase_near(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    const Warp w = make_warp(prm, bt, smem_base);
-    WarpCtx& c = *w.c;
-    const int lane = w.lane;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    double2* XY = w.XY; double* ECOST = w.ECOST; int32_t* PARENT = w.PARENT; int32_t* NCHILD = w.NCHILD; uint8_t* NFLAG = w.NFLAG;
-    int* stage = w.stage; int* rwlist = w.rwlist; double* chain = w.chain;
-    const rrtfnd_node_grid_t& ng = bt->node_grid;
-    const Obst ob = make_obst(bt->obst, prm->n_obst, &bt->grid);
-    const double px = c.px, py = c.py, e0 = c.e0;
-    const int near_slot = c.near_slot, new_slot = c.new_slot, n_slots = c.n_slots, n_live = c.n_live;
-    const double r2 = dmul(prm->radius, prm->radius);
-    const bool eval_cp = (prm->flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
-    const bool commit_cp = (prm->flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) != 0;
-
-    int n_rw = 0, k_total = 0, hops = 0, tests = 0;
-    int cp_slot = near_slot; double cp_cost = e0;
-    bool dup = false;
-    double cost_new = 0.0;
-    // node grid: the ball lies inside the window of cells within `radius` of q_new; its nodes, sorted by slot, replace the scan
-    const int32_t* nlist = nullptr;
-    int n_near_items = n_slots;
-    if (NG && n_live >= ng.min_nodes) {
-        int cx0, cx1, cy0, cy1;
-        ng_window(ng, px, py, (int)(prm->radius * ng.inv_cell) + 1, cx0, cx1, cy0, cy1);
-        const int n = ng_gather(w.HEAD, w.NEXT, ng.nx, cx0, cx1, cy0, cy1, w.CAND, ng.cand_cap, lane);
-        if (n <= ng.cand_cap && n <= 512) { ng_sort(w.CAND, w.CAND + ng.cand_cap, n, lane); nlist = w.CAND + ng.cand_cap; n_near_items = n; }
-    }
-    const int n_pass = commit_cp ? 2 : 1;          // committing choose-parent needs its result before any rewire decision
-#pragma unroll 1
-    for (int pass = 0; pass < n_pass; ++pass) {
-        const bool do_cp = eval_cp && pass == 0;
-        const bool do_rw = pass == n_pass - 1;
-        const int walk_from = PARENT[new_slot];
-        const double walk_acc = ECOST[new_slot];
-        double cp_cn = 0.0;
-        int chain_depth = 0;
-        bool first = true;
-        int count = 0;
-        k_total = 0;
-        const int n_tiles = (n_near_items + kTileNodes - 1) / kTileNodes;
-        if (!nlist) stream_begin(c.xs, XY, n_slots, lane);
-        for (int t = 0; t < n_tiles; ++t) {
-            double2 v[4]; int sl[4];
-            fetch_tile<NG>(c.xs, XY, nlist, n_near_items, t, lane, v, sl);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int s = sl[u];
-                const bool in = dist2(v[u].x, v[u].y, px, py) <= r2 && s != new_slot;
-                const unsigned m = __ballot_sync(kFull, in);
-                if (in) stage[count + __popc(m & lt_mask)] = s;
-                count += __popc(m); k_total += __popc(m);
-            }
-            const bool last = t + 1 >= n_tiles;
-            int head = 0;
-            while (count - head >= (first ? 31 : 32) || (last && count > head)) {
-                const int n = min(count - head, first ? 31 : 32);
-                __syncwarp();
-                // ---- one chunk: lane i < n owns candidate i; in the first chunk lane 31 walks the new node's chain
-                int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
-                int w_from = -1;
-                if (lane < n) {
-                    s = stage[head + lane];
-                    const double2 cpos = XY[s];
-                    dpl = dist_plain(cpos.x, cpos.y, px, py);                 // :842 / :899
-                    if (dpl == 0.0 && cpos.x == px && cpos.y == py) dup = true;   // src/graph.py:54-56 corner (B9)
-                    // Line(node, q_new): p1 = node (:846 / :903)
-                    const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, cpos.x, cpos.y, px, py, 0, 1);
-                    tests += r >> 1;
-                    hit = r & 1;
-                    if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
-                }
-                // parent-chain walks, one loop for all lanes (Graph.get_cost, src/graph.py:41-46): lane 31 of the first
-                // chunk walks the new node's chain, starts from its edge cost and records the addends
-                const bool rec = first && lane == 31;
-                int depth = 0;
-                if (rec) { w_from = walk_from; cc = walk_acc; }
-                if (w_from >= 0) {
-                    int wn = w_from, q = PARENT[wn];
-                    while (q >= 0) {
-                        const double e = ECOST[wn];
-                        if (rec && depth < kChainCap) chain[depth] = e;
-                        cc = dadd(cc, e);
-                        wn = q; q = PARENT[wn];
-                        ++depth;
-                    }
-                    hops += depth;
-                }
-                __syncwarp();
-                if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; chain_depth = __shfl_sync(kFull, depth, 31); }
-                if (do_cp) {
-                    // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
-                    unsigned open = __ballot_sync(kFull, lane < n && !hit);
-                    while (open) {
-                        const int i = __ffs(open) - 1;
-                        open &= open - 1;
-                        const double ci = __shfl_sync(kFull, cc, i), di = __shfl_sync(kFull, dpl, i);
-                        if (cp_cn > dadd(ci, di)) {
-                            cp_slot = __shfl_sync(kFull, s, i); cp_cost = di;
-                            // G.cost[id_new] = cost, parent untouched: the chain is still id_near's (:849)
-                            if (chain_depth <= kChainCap) {                   // re-sum the cached addends
-                                cp_cn = di;
-                                for (int h = 0; h < chain_depth; ++h) cp_cn = dadd(cp_cn, chain[h]);
-                            } else {
-                                long long h = 0;
-                                cp_cn = chain_walk(PARENT, ECOST, near_slot, di, h);   // every lane walks the same chain
-                                if (lane == 0) hops += (int)h;
-                            }
-                        }
-                    }
-                }
-                if (do_rw) {
-                    const bool rw = lane < n && !hit && cc > dadd(cost_new, dpl);   // :905, strict
-                    const unsigned m = __ballot_sync(kFull, rw);
-                    if (m) {   // remember the decision: short list in shared memory, overflow as a per-node flag bit
-                        const int pos = n_rw + __popc(m & lt_mask);
-                        if (rw) { if (pos < prm->near_cap) rwlist[pos] = s; else NFLAG[s] |= 2; }
-                        n_rw += __popc(m);
-                    }
-                }
-                first = false;
-                __syncwarp();
-                head += n;
-            }
-            if (head > 0) {                                                   // keep the (< 32) leftover at the front
-                const int rem = count - head;
-                const int t2 = lane < rem ? stage[head + lane] : 0;
-                __syncwarp();
-                if (lane < rem) stage[lane] = t2;
-                count = rem;
-                __syncwarp();
-            }
-        }
-        if (pass == 0 && commit_cp && k_total > 0) {   // EXTENSION (not the shipped behaviour): adopt the returned edge
-            if (lane == 0) { PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost; }
-            __syncwarp();
-        }
-    }
-    add_counters(w, hops, tests);
-    if (__any_sync(kFull, dup)) { c.status = RRTFND_ST_DUPLICATE; return kStop; }
-    c.n_scan_nodes += nlist ? n_near_items : n_live;
-    c.n_edge_checks += k_total;
-    c.n_edge_checks_ref += 2 * (long long)k_total + 2;   // each candidate twice + Line(q_new, q_new) twice
-
-    // ---- commit: rewire_kdtree's re-parenting (:906-910) and G.add_edge(*best_edge) (:148), serial on lane 0
-    int d_childless = 0, flagged = 0;
-    if (lane == 0) {
-        auto reparent = [&](int s) {
-            const int oldp = PARENT[s];
-            if (--NCHILD[oldp] == 0) ++d_childless;
-            const double2 v = XY[s];
-            PARENT[s] = new_slot;
-            ECOST[s] = dist_plain(v.x, v.y, px, py);
-            flagged |= NFLAG[s] & 1;
-        };
-        const int n_list = n_rw < prm->near_cap ? n_rw : prm->near_cap;
-        for (int i = 0; i < n_list; ++i) reparent(rwlist[i]);
-        if (n_rw > n_list) {          // more re-parented nodes than the list holds (rare): find the flagged rest
-            for (int s = 0; s < new_slot; ++s)
-                if (NFLAG[s] & 2) { NFLAG[s] &= (uint8_t)~2; reparent(s); }
-        }
-        NCHILD[new_slot] = n_rw;
-        if (n_rw == 0) ++d_childless;
-        if (NCHILD[PARENT[new_slot]]++ == 0) --d_childless;
-        if (flagged) {   // the moved subtree holds a goal-reaching node: mark its new ancestors
-            int n = new_slot;
-            while (n >= 0 && !(NFLAG[n] & 1)) { NFLAG[n] |= 1; n = PARENT[n]; }
-        }
-    }
-    __syncwarp();
-    c.n_childless += __shfl_sync(kFull, d_childless, 0);
-    c.need_refresh = __shfl_sync(kFull, flagged, 0) != 0;
-    c.n_rewired += n_rw;
-    c.k_total = k_total; c.n_rw = n_rw; c.cp_cost = cp_cost;
-    c.cp_parent_id = eval_cp ? w.ID[cp_slot] : -1;     // read before forced_removal can delete that node
-    return kNext;
-}
-
-// ================================================================ phase 4: forced_removal (:233-237, :800-819)
-static __device__ __noinline__ int phase_fn_remove(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    const Warp w = make_warp(prm, bt, smem_base);
-    WarpCtx& c = *w.c;
-    WordSrc& rng = *w.rng;
-    const int lane = w.lane, new_slot = c.new_slot, n_slots = c.n_slots;
-    int32_t* NCHILD = w.NCHILD; int32_t* FINISH = w.FINISH;
-    const int leaf = c.best_leaf_slot;
-    const int total = c.n_childless;
-    int n_ok = total - (NCHILD[new_slot] == 0 ? 1 : 0);
-    if (leaf >= 0 && leaf != new_slot && NCHILD[leaf] == 0) --n_ok;
-    if (n_ok <= 0) { c.status = RRTFND_ST_NO_CHILDLESS; return kStop; }
-    int pick = -1;
-    for (;;) {
-        const uint32_t r = next_randbelow(rng, (uint32_t)total);              // random.choice (:813 / :816)
-        if (rng.exhausted) { c.status = RRTFND_ST_STREAM_EXHAUSTED; return kStop; }
-        // r-th childless node in ascending slot order (tombstones hold nchild = -1)
-        int running = 0; pick = -1;
-        for (int base = 0; base < n_slots; base += 32) {
-            const int s = base + lane;
-            const unsigned m = __ballot_sync(kFull, s < n_slots && NCHILD[s] == 0);
-            const int cnt = __popc(m);
-            if ((int)r < running + cnt) { pick = base + (int)__fns(m, 0, (int)r - running + 1); break; }
-            running += cnt;
-        }
-        if (pick != new_slot && pick != leaf) break;                          // :815
-    }
-    // finish_nodes_of_path.remove(id_removed) (:235-236), order preserving
-    const int n_finish = c.n_finish;
-    int fpos = -1;
-    for (int base = 0; base < n_finish; base += 32) {
-        const int f = base + lane;
-        const unsigned m = __ballot_sync(kFull, f < n_finish && FINISH[f] == pick);
-        if (m) { fpos = base + __ffs(m) - 1; break; }
-    }
-    if (fpos >= 0) {
-        for (int base = fpos; base < n_finish - 1; base += 32) {
-            const int f = base + lane;
-            const bool ok = f < n_finish - 1;
-            const int v = ok ? FINISH[f + 1] : 0;
-            __syncwarp();
-            if (ok) FINISH[f] = v;
-            __syncwarp();
-        }
-        c.n_finish = n_finish - 1;
-    }
-    int d_childless = -1;                                                     // the removed node was childless
-    c.removed_id = w.ID[pick];
-    __syncwarp();
-    if (lane == 0) {                                                          // Graph.remove_vertex (src/graph.py:64-77)
-        const int par = w.PARENT[pick];
-        if (par >= 0 && --NCHILD[par] == 0) ++d_childless;
-        w.ID[pick] = -1; NCHILD[pick] = -1; w.PARENT[pick] = -1;
-        w.XY[pick] = make_double2(CUDART_NAN, CUDART_NAN);
-    }
-    __syncwarp();
-    c.n_childless += __shfl_sync(kFull, d_childless, 0);
-    c.n_live -= 1; c.fn_count -= 1; c.n_removed += 1;
-    return kNext;
-}
-
-// ================================================================ phase 5: goal test and best path (:155-170, :240-251), end of iteration
-static __device__ __noinline__ int phase_goal(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    const Warp w = make_warp(prm, bt, smem_base);
-    WarpCtx& c = *w.c;
-    const int lane = w.lane, new_slot = c.new_slot, root_slot = c.root_slot;
-    int32_t* PARENT = w.PARENT; double* ECOST = w.ECOST; int32_t* FINISH = w.FINISH; int32_t* BPATH = w.BPATH; int32_t* ID = w.ID;
-    int hops = 0;
-    const bool reached = c.reached != 0;
-    if (reached) {
-        if (c.n_finish >= prm->finish_cap) { c.status = RRTFND_ST_FINISH_CAP; return kStop; }
-        int L = 0; double cost = 0.0;
-        if (lane == 0) {
-            FINISH[c.n_finish] = new_slot;
-            int n = new_slot;                                                 // mark the ancestors of the new finish node
-            while (n >= 0 && !(w.NFLAG[n] & 1)) { w.NFLAG[n] |= 1; n = PARENT[n]; }
-            if (prm->mode == RRTFND_MODE_STAR) {                              // unconditional overwrite (:160-161)
-                n = new_slot;
-                while (n != root_slot && n >= 0) {
-                    if (L < prm->path_cap) BPATH[L] = ID[n];
-                    ++L; cost = dadd(cost, ECOST[n]); n = PARENT[n]; ++hops;
-                }
-                if (L < prm->path_cap) BPATH[L] = ID[root_slot];
-                ++L;
-            }
-        }
-        __syncwarp();
-        c.n_finish += 1;
-        c.solution_found = 1;
-        if (prm->mode == RRTFND_MODE_STAR) {
-            const int len = __shfl_sync(kFull, L, 0);
-            c.best_len = len; c.best_cost = __shfl_sync(kFull, cost, 0); c.best_leaf_slot = new_slot;
-            if (len > prm->path_cap) { c.status = RRTFND_ST_PATH_CAP; add_counters(w, hops, 0); return kStop; }
-        }
-    }
-    // The reference recomputes every finish node's path each iteration and keeps a strictly cheaper one (:166-170, :247-251).
-    // A path cost only changes when a node with a goal-reaching descendant is rewired, and the list only grows through a
-    // new finish node, so those are the only iterations in which it can have an effect.
-    const int n_finish = c.n_finish;
-    if ((reached || c.need_refresh) && n_finish > 0) {
-        double bd = CUDART_INF; int bf = kIntMax;
-        for (int f = lane; f < n_finish; f += 32) {
-            long long h = 0;
-            const double cost = path_cost(PARENT, ECOST, FINISH[f], root_slot, h);
-            hops += (int)h;
-            if (cost < bd) { bd = cost; bf = f; }
-        }
-        __syncwarp();
-        warp_argmin(bd, bf);
-        if (bd < c.best_cost) {                                               // strict (:168, :249)
-            const int leaf = FINISH[bf];
-            int L = 0;
-            if (lane == 0) {
-                int n = leaf;
-                while (n != root_slot && n >= 0) {
-                    if (L < prm->path_cap) BPATH[L] = ID[n];
-                    ++L; n = PARENT[n]; ++hops;
-                }
-                if (L < prm->path_cap) BPATH[L] = ID[root_slot];
-                ++L;
-            }
-            __syncwarp();
-            const int len = __shfl_sync(kFull, L, 0);
-            c.best_len = len; c.best_cost = bd; c.best_leaf_slot = leaf;
-            if (len > prm->path_cap) { c.status = RRTFND_ST_PATH_CAP; add_counters(w, hops, 0); return kStop; }
-        }
-    }
-    add_counters(w, hops, 0);
-    // ---- end of iteration
-    rrtfnd_trace_t* TRACE = bt->trace ? bt->trace + (size_t)w.p * prm->trace_cap : nullptr;
-    if (TRACE && c.iter < prm->trace_cap && lane == 0) {
-        const bool eval_cp = (prm->flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
-        rrtfnd_trace_t t;
-        t.id_new = c.id_new; t.id_near = ID[c.near_slot]; t.n_near = c.k_total; t.n_rewired = c.n_rw;
-        t.removed_id = c.removed_id;
-        t.cp_parent = c.cp_parent_id; t.cp_cost = eval_cp ? c.cp_cost : 0.0;
-        TRACE[c.iter] = t;
-    }
-    __syncwarp();
-    c.iter += 1;                                                              // :173 / :254
-    return kNext;
-}
-
-// load the planner record into the warp's context (start / resume)
-static __device__ __noinline__ void phase_load(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    const Warp w = make_warp(prm, bt, smem_base);
-    WarpCtx& c = *w.c;
-    WordSrc& rng = *w.rng;
-    const int lane = w.lane;
-    const rrtfnd_planner_t* PL = bt->planners + w.p;
-    c.gx = PL->goal_x; c.gy = PL->goal_y; c.best_cost = PL->best_cost;
-    c.attempts = PL->attempts; c.n_edge_checks = PL->n_edge_checks; c.n_edge_checks_ref = PL->n_edge_checks_ref;
-    c.n_scan_nodes = PL->n_scan_nodes; c.n_hops = 0; c.n_tests = 0;
-    c.n_slots = PL->n_slots; c.n_live = PL->n_live; c.last_id = PL->last_id; c.iter = PL->iter; c.root_slot = PL->root_slot;
-    c.n_finish = PL->n_finish; c.best_len = PL->best_len; c.status = RRTFND_ST_RUNNING;
-    c.n_rewired = PL->n_rewired; c.n_removed = PL->n_removed; c.solution_found = PL->solution_found;
-    c.n_compactions = PL->n_compactions; c.fn_count = PL->fn_count;
-    c.removed_id = -1; c.need_refresh = 0;
-    rng.mode = prm->stream_mode;
-    rng.words = bt->words ? bt->words + (size_t)w.p * prm->words_per_planner : nullptr;
-    rng.n_words = prm->words_per_planner;
+    rng.mode = prm.stream_mode;
+    rng.words = bt.words ? bt.words + (size_t)p * prm.words_per_planner : nullptr;
+    rng.n_words = prm.words_per_planner;
     rng.seed = PL->seed; rng.stream = PL->stream_id; rng.cursor = PL->cursor;
     rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0;
-    const int n_slots = PL->n_slots, best_len = PL->best_len;
+    __syncwarp();
+
     // slot of the cached best path's leaf (ids ascend with slots: binary search around tombstones)
     int best_leaf_slot = -1;
     if (best_len > 0) {
-        const int leaf_id = w.BPATH[0];
+        const int leaf_id = BPATH[0];
         int lo = 0, hi = n_slots - 1;
         while (lo <= hi) {
             const int mid = (lo + hi) >> 1;
             int m2 = mid;
-            while (m2 <= hi && w.ID[m2] < 0) ++m2;
+            while (m2 <= hi && ID[m2] < 0) ++m2;
             if (m2 > hi) { hi = mid - 1; continue; }
-            const int v = w.ID[m2];
+            const int v = ID[m2];
             if (v == leaf_id) { best_leaf_slot = m2; break; }
             if (v < leaf_id) lo = m2 + 1; else hi = mid - 1;
         }
     }
-    c.best_leaf_slot = best_leaf_slot;
     // childless live nodes (forced_removal draws among them); kept incrementally afterwards
     int n_childless = 0;
-    if (prm->mode == RRTFND_MODE_FN) {
+    if (prm.mode == RRTFND_MODE_FN) {
         for (int base = 0; base < n_slots; base += 32) {
             const int s = base + lane;
-            n_childless += __popc(__ballot_sync(kFull, s < n_slots && w.NCHILD[s] == 0));
+            n_childless += __popc(__ballot_sync(kFull, s < n_slots && NCHILD[s] == 0));
         }
     }
-    c.n_childless = n_childless;
-    __syncwarp();
-}
 
-static __device__ __noinline__ void phase_store(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, unsigned char* smem_base) {
-    const Warp w = make_warp(prm, bt, smem_base);
-    const WarpCtx& c = *w.c;
-    __syncwarp();
-    if (w.lane == 0) {
-        rrtfnd_planner_t* PL = bt->planners + w.p;
-        PL->best_cost = c.best_cost; PL->cursor = w.rng->cursor; PL->attempts = c.attempts;
-        PL->n_edge_checks = c.n_edge_checks; PL->n_edge_checks_ref = c.n_edge_checks_ref;
-        PL->n_circle_tests += c.n_tests; PL->n_scan_nodes = c.n_scan_nodes; PL->n_chain_hops += c.n_hops;
-        PL->n_slots = c.n_slots; PL->n_live = c.n_live; PL->last_id = c.last_id; PL->iter = c.iter;
-        PL->root_slot = c.root_slot; PL->n_finish = c.n_finish; PL->best_len = c.best_len; PL->status = c.status;
-        PL->n_rewired = c.n_rewired; PL->n_removed = c.n_removed; PL->solution_found = c.solution_found;
-        PL->n_compactions = c.n_compactions; PL->fn_count = c.fn_count;
-    }
-}
+    const double r2 = dmul(prm.radius, prm.radius);
+    const double goal_thresh = dmul(2.0, prm.goal_node_radius);
+    const bool eval_cp = (prm.flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
+    const bool commit_cp = (prm.flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) != 0;
+    const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
 
-// WPB warps (= planners) per CTA; MINW = resident warps per SM the register allocation must allow (16 -> 128 registers,
-// 24 -> 80, 32 -> 64); NG = node-grid variant.
-template <int WPB, int MINW, bool NG>
-__global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const __grid_constant__ rrtfnd_params_t prm,
-                                                                    const __grid_constant__ rrtfnd_batch_t bt) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (blockIdx.x * WPB + wib >= bt.n_planners) return;      // whole warp leaves; warps never synchronise with each other
-    {
-        const int n_stages = prm.reserved;
-        unsigned char* ws = smem + (size_t)wib * warp_smem_bytes(prm, n_stages);
-        unsigned char* bars = ws + (size_t)n_stages * kTileBytes;
-        WarpCtx* c = reinterpret_cast<WarpCtx*>(bars + align_up((size_t)n_stages * 8, 16));
-        XYStream xs;
-        stream_init(xs, ws, bars, n_stages, lane);
-        c->xs = xs;
-        __syncwarp();
-    }
-    phase_load(&prm, &bt, smem);
     for (;;) {
-        int r = phase_attempt<NG>(&prm, &bt, smem);
-        if (r == kRetry) continue;
-        if (r == kStop) break;
-        r = phase_insert<NG>(&prm, &bt, smem);
-        if (r == kRetry) continue;
-        if (r == kStop) break;
-        if (phase_near<NG>(&prm, &bt, smem) == kStop) break;
-        WarpCtx* c = reinterpret_cast<WarpCtx*>(smem + (size_t)wib * warp_smem_bytes(prm, prm.reserved) +
-                                                (size_t)prm.reserved * kTileBytes + align_up((size_t)prm.reserved * 8, 16));
-        c->removed_id = -1;
-        if (prm.mode == RRTFND_MODE_FN && c->fn_count > prm.max_nodes)           // n_of_nodes > max_nodes (:233)
-            if (phase_fn_remove(&prm, &bt, smem) == kStop) break;
-        if (phase_goal(&prm, &bt, smem) == kStop) break;
+        // ================================================================ A. attempt header
+        if (iter >= prm.iter_num) { status = RRTFND_ST_DONE; break; }
+        if (prm.max_attempts > 0 && attempts >= prm.max_attempts) { status = RRTFND_ST_ATTEMPT_CAP; break; }
+        if (prm.stream_mode == RRTFND_STREAM_WORDS && (long long)rng.cursor + kReserveWords > prm.words_per_planner) {
+            status = RRTFND_ST_NEED_WORDS; break;
+        }
+        if (n_slots >= C) {
+            if (n_live >= n_slots || !can_compact(prm)) { status = RRTFND_ST_CAPACITY; break; }
+            // ---- A'. stable in-place compaction (FN only; rare)
+            compact_tree(XY, ECOST, PARENT, NCHILD, ID, NFLAG, FINISH, n_finish, n_slots, bm, pre, &root_slot, &best_leaf_slot, lane);
+            n_slots = n_live;
+            ++n_compactions;
+        }
+        ++attempts;
+        // Graph.random_node (src/graph.py:96-98)
+        double qx, qy;
+        if (next_random(rng) < prm.bias) { qx = gx; qy = gy; }
+        else {
+            qx = dadd(prm.x_lo, dmul(dsub(prm.x_hi, prm.x_lo), next_random(rng)));
+            qy = dadd(prm.y_lo, dmul(dsub(prm.y_hi, prm.y_lo), next_random(rng)));
+        }
+
+        // ================================================================ B. Map.is_occupied_c (src/map.py:38-47)
+        if (point_occupied_warp(ob, qx, qy, prm.node_radius, lane, my_tests)) continue;   // src/algorithm.py:39-40
+
+        // ================================================================ C. nearest visible node (:666-699)
+        // The reference asks the k-d tree for the 1st, 2nd, 3rd ... nearest node until one is visible. Round 0 here is
+        // that first query (plain argmin). If it is blocked, the remaining order is consumed in annuli of doubling
+        // squared radius: every node of an annulus is tested (one lane per segment) and the lowest (d2, slot) key among
+        // the visible ones is the node the reference would have stopped at, because everything in earlier annuli was
+        // blocked. A boxed-in sample therefore costs O(log N) scans instead of O(N).
+        int near_slot = -1;
+        {
+            double bd = CUDART_INF; int bs = kIntMax;
+            // what the scans below run over: the whole tree (TMA ring), or - node grid - the nodes of a window of cells
+            const int32_t* list = nullptr;
+            int n_items = n_slots, rho = 1;
+            bool covers_all = true;
+            const bool use_ng = NG && n_live >= ng.min_nodes;
+            for (;;) {      // (node grid: widen the window until the nearest node is certain; one pass when scanning)
+                if (use_ng) {
+                    int cx0, cx1, cy0, cy1;
+                    covers_all = ng_window(qx, qy, rho, cx0, cx1, cy0, cy1);
+                    const int n = ng_gather(HEAD, NEXT, ng.nx, cx0, cx1, cy0, cy1, CAND, ng.cand_cap, lane);
+                    if (n > ng.cand_cap) { list = nullptr; n_items = n_slots; covers_all = true; }
+                    else { list = CAND; n_items = n; }
+                }
+                bd = CUDART_INF; bs = kIntMax;
+                const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
+                if (!list) stream_begin(xs, XY, n_slots, lane);
+                for (int t = 0; t < n_tiles; ++t) {
+                    double2 v[4]; int sl[4];
+                    fetch_tile<NG>(xs, XY, list, n_items, t, lane, v, sl);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double d = dist2(v[u].x, v[u].y, qx, qy);                 // NaN for tombstones / padding
+                        if (d < bd || (NG && d == bd && sl[u] < bs)) { bd = d; bs = sl[u]; }
+                    }
+                }
+                warp_argmin(bd, bs);
+                n_scan_nodes += list ? n_items : n_live;
+                if (!list || covers_all || (bs != kIntMax && bd <= ng_complete_d2(rho))) break;
+                rho *= 2;
+            }
+            if (bs == kIntMax) continue;                                          // empty tree (cannot happen)
+            if (bd == 0.0) {                                                      // G.id_vertex[vertex] hit (:676-678)
+                const double2 e = XY[bs];
+                bool exact = (e.x == qx && e.y == qy);
+                if (!exact) exact = any_exact_match(XY, n_slots, qx, qy, lane);   // d2 underflowed to 0 without equality
+                if (exact) continue;                                              // rejected at :45
+            }
+            // through_obstacle(Line(q_rand, node)) — p1 = sample, p2 = node (:690-692); the warp shares the one segment
+            int rounds = 1;
+            {
+                const double2 nb = XY[bs];
+                const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, lane, 32);
+                my_tests += r >> 1;
+                if (!__any_sync(kFull, r & 1)) near_slot = bs;
+            }
+            if (near_slot < 0 && n_live > 1) {
+                double lo_d = bd; int lo_s = bs;                                  // keys <= (lo_d, lo_s) are known to be blocked
+                double T = bd;
+                const double t_floor = dmul(dmul(prm.step_length, prm.step_length), 0.0625);
+                rounds = n_live;                                                  // if nothing is visible every node was tried
+                for (;;) {
+                    T = dadd(T, T);
+                    if (T < t_floor) T = t_floor;
+                    if (NG && list && !covers_all && T > ng_complete_d2(rho)) {    // the window must hold every node within sqrt(T)
+                        rho = max(2 * rho, (int)(sqrt(T) * ng.inv_cell) + 1);
+                        int cx0, cx1, cy0, cy1;
+                        covers_all = ng_window(qx, qy, rho, cx0, cx1, cy0, cy1);
+                        const int n = ng_gather(HEAD, NEXT, ng.nx, cx0, cx1, cy0, cy1, CAND, ng.cand_cap, lane);
+                        if (n > ng.cand_cap) { list = nullptr; n_items = n_slots; covers_all = true; }
+                        else n_items = n;
+                    }
+                    double vd = CUDART_INF; int vs = kIntMax;                      // this lane's best visible key
+                    bool beyond = NG && list && !covers_all;
+                    int count = 0;
+                    const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
+                    if (!list) stream_begin(xs, XY, n_slots, lane);
+                    for (int t = 0; t < n_tiles; ++t) {
+                        double2 v[4]; int sl[4];
+                        fetch_tile<NG>(xs, XY, list, n_items, t, lane, v, sl);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int s = sl[u];
+                            const double d = dist2(v[u].x, v[u].y, qx, qy);
+                            beyond |= d > T;
+                            const bool in = (d > lo_d || (d == lo_d && s > lo_s)) && d <= T;
+                            const unsigned m = __ballot_sync(kFull, in);
+                            if (in) stage[count + __popc(m & lt_mask)] = s;
+                            count += __popc(m);
+                        }
+                        const bool last = t + 1 >= n_tiles;
+                        int head = 0;
+                        while (count - head >= 32 || (last && count > head)) {     // one lane per staged segment
+                            const int n = min(count - head, 32);
+                            __syncwarp();
+                            if (lane < n) {
+                                const int s = stage[head + lane];
+                                const double2 nb = XY[s];
+                                const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, 0, 1);
+                                my_tests += r >> 1;
+                                if (!(r & 1)) {
+                                    const double d = dist2(nb.x, nb.y, qx, qy);
+                                    if (d < vd || (d == vd && s < vs)) { vd = d; vs = s; }
+                                }
+                            }
+                            __syncwarp();
+                            head += n;
+                        }
+                        if (head > 0) {                                           // keep the (< 32) leftover at the front
+                            const int rem = count - head;
+                            const int t2 = lane < rem ? stage[head + lane] : 0;
+                            __syncwarp();
+                            if (lane < rem) stage[lane] = t2;
+                            count = rem;
+                            __syncwarp();
+                        }
+                    }
+                    n_scan_nodes += list ? n_items : n_live;
+                    warp_argmin(vd, vs);
+                    if (vs != kIntMax) {
+                        near_slot = vs;
+                        rounds = (NG && list) ? ng_key_rank(XY, list, n_items, qx, qy, vd, vs, lane)
+                                              : key_rank(XY, n_slots, qx, qy, vd, vs, lane);
+                        break;
+                    }
+                    if (!__any_sync(kFull, beyond)) break;                        // every node tried, none visible
+                    lo_d = T; lo_s = kIntMax;
+                }
+            }
+            n_edge_checks += rounds; n_edge_checks_ref += rounds;
+            if (near_slot < 0) continue;                                          // :45-46
+        }
+
+        // ================================================================ D. steer + insert (every lane computes, lane 0 stores)
+        const double2 nb = XY[near_slot];
+        double px = qx, py = qy;
+        {
+            const double d = dist_fma(qx, qy, nb.x, nb.y);                        // steer (:739)
+            const double ux = ddiv(dsub(qx, nb.x), d), uy = ddiv(dsub(qy, nb.y), d);
+            const double tx = dadd(nb.x, dmul(ux, prm.step_length)), ty = dadd(nb.y, dmul(uy, prm.step_length));
+            if (d > prm.step_length) { px = tx; py = ty; }
+        }
+        const int new_slot = n_slots++;
+        const int id_new = ++last_id;                                            // Graph.add_vertex (src/graph.py:57-61)
+        ++n_live; ++fn_count;                                                    // n_of_nodes += 1 (:221)
+        const double e0 = dist_fma(px, py, nb.x, nb.y);                          // :49
+        const bool reached = dist_fma(px, py, gx, gy) < goal_thresh;             // check_solution (:757-758)
+        if (lane == 0) {
+            XY[new_slot] = make_double2(px, py);
+            ID[new_slot] = id_new; PARENT[new_slot] = near_slot; ECOST[new_slot] = e0;   // :141-142
+            NCHILD[new_slot] = 0; NFLAG[new_slot] = 0;
+            if (NG) {                                                             // push onto its cell's list
+                const int c = grid_cell(py, ng.y0, ng.inv_cell, ng.ny) * ng.nx + grid_cell(px, ng.x0, ng.inv_cell, ng.nx);
+                NEXT[new_slot] = HEAD[c]; HEAD[c] = new_slot;
+            }
+        }
+        __syncwarp();
+
+        if (prm.mode == RRTFND_MODE_RRT) {
+            int L = 0; double cost = 0.0;
+            if (lane == 0) {
+                NCHILD[near_slot] += 1;                                           // add_edge (:76)
+                if (reached) {                                                    // :78-81, break before iter += 1
+                    int n = new_slot;
+                    while (n != root_slot && n >= 0) {
+                        if (L < prm.path_cap) BPATH[L] = ID[n];
+                        ++L; cost = dadd(cost, ECOST[n]); n = PARENT[n]; ++my_hops;
+                    }
+                    if (L < prm.path_cap) BPATH[L] = ID[root_slot];
+                    ++L;
+                }
+                if (TRACE && iter < prm.trace_cap) {
+                    rrtfnd_trace_t t; t.id_new = id_new; t.id_near = ID[near_slot]; t.n_near = 0; t.n_rewired = 0;
+                    t.removed_id = -1; t.cp_parent = -1; t.cp_cost = 0.0;
+                    TRACE[iter] = t;
+                }
+            }
+            __syncwarp();
+            if (reached) {
+                best_len = __shfl_sync(kFull, L, 0); best_cost = __shfl_sync(kFull, cost, 0);
+                best_leaf_slot = new_slot; solution_found = 1;
+                status = best_len > prm.path_cap ? RRTFND_ST_PATH_CAP : RRTFND_ST_DONE;
+                break;
+            }
+            ++iter;
+            continue;
+        }
+
+        // ================================================================ E. near set -> collision, costs, choose-parent, rewire
+        // The ball (query_ball_point, :837 / :893) is produced in ascending slot order by the scan and handed to the
+        // lanes in chunks of up to 32 candidates: lane i owns candidate i (its own segment test, its own parent-chain
+        // walk). In the first chunk lane 31 walks the new node's chain (Graph.get_cost(id_new)). Rewire decisions are
+        // taken against the pre-rewire tree and committed after the scan.
+        int n_rw = 0, k_total = 0;
+        int cp_slot = near_slot; double cp_cost = e0;
+        bool dup = false;
+        double cost_new = 0.0;
+        // node grid: the ball lies inside the window of cells within `radius` of q_new; its nodes, sorted by slot, replace the scan
+        const int32_t* nlist = nullptr;
+        int n_near_items = n_slots;
+        if (NG && n_live >= ng.min_nodes) {
+            int cx0, cx1, cy0, cy1;
+            ng_window(px, py, (int)(prm.radius * ng.inv_cell) + 1, cx0, cx1, cy0, cy1);
+            const int n = ng_gather(HEAD, NEXT, ng.nx, cx0, cx1, cy0, cy1, CAND, ng.cand_cap, lane);
+            if (n <= ng.cand_cap && n <= 512) { ng_sort(CAND, CAND + ng.cand_cap, n, lane); nlist = CAND + ng.cand_cap; n_near_items = n; }
+        }
+        const int n_pass = commit_cp ? 2 : 1;          // committing choose-parent needs its result before any rewire decision
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const bool do_cp = eval_cp && pass == 0;
+            const bool do_rw = pass == n_pass - 1;
+            const int walk_from = PARENT[new_slot];
+            const double walk_acc = ECOST[new_slot];
+            double cp_cn = 0.0;
+            int chain_depth = 0;
+            bool first = true;
+            int count = 0;
+            k_total = 0;
+            const int n_tiles = (n_near_items + kTileNodes - 1) / kTileNodes;
+            if (!nlist) stream_begin(xs, XY, n_slots, lane);
+            for (int t = 0; t < n_tiles; ++t) {
+                double2 v[4]; int sl[4];
+                fetch_tile<NG>(xs, XY, nlist, n_near_items, t, lane, v, sl);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int s = sl[u];
+                    const bool in = dist2(v[u].x, v[u].y, px, py) <= r2 && s != new_slot;
+                    const unsigned m = __ballot_sync(kFull, in);
+                    if (in) stage[count + __popc(m & lt_mask)] = s;
+                    count += __popc(m); k_total += __popc(m);
+                }
+                const bool last = t + 1 >= n_tiles;
+                int head = 0;
+                while (count - head >= (first ? 31 : 32) || (last && count > head)) {
+                    const int n = min(count - head, first ? 31 : 32);
+                    __syncwarp();
+                    // ---- one chunk: lane i < n owns candidate i; in the first chunk lane 31 walks the new node's chain
+                    int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
+                    int w_from = -1;
+                    if (lane < n) {
+                        s = stage[head + lane];
+                        const double2 c = XY[s];
+                        dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
+                        if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
+                        // Line(node, q_new): p1 = node (:846 / :903)
+                        const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
+                        my_tests += r >> 1;
+                        hit = r & 1;
+                        if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
+                    }
+                    // parent-chain walks, one loop for all lanes (Graph.get_cost, src/graph.py:41-46): lane 31 of the first
+                    // chunk walks the new node's chain, starts from its edge cost and records the addends
+                    const bool rec = first && lane == 31;
+                    int depth = 0;
+                    if (rec) { w_from = walk_from; cc = walk_acc; }
+                    if (w_from >= 0) {
+                        int wn = w_from, q = PARENT[wn];
+                        while (q >= 0) {
+                            const double e = ECOST[wn];
+                            if (rec && depth < kChainCap) chain[depth] = e;
+                            cc = dadd(cc, e);
+                            wn = q; q = PARENT[wn];
+                            ++depth;
+                        }
+                        my_hops += depth;
+                    }
+                    __syncwarp();
+                    if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; chain_depth = __shfl_sync(kFull, depth, 31); }
+                    if (do_cp) {
+                        // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
+                        unsigned open = __ballot_sync(kFull, lane < n && !hit);
+                        while (open) {
+                            const int i = __ffs(open) - 1;
+                            open &= open - 1;
+                            const double ci = __shfl_sync(kFull, cc, i), di = __shfl_sync(kFull, dpl, i);
+                            if (cp_cn > dadd(ci, di)) {
+                                cp_slot = __shfl_sync(kFull, s, i); cp_cost = di;
+                                // G.cost[id_new] = cost, parent untouched: the chain is still id_near's (:849)
+                                if (chain_depth <= kChainCap) {                       // re-sum the cached addends
+                                    cp_cn = di;
+                                    for (int h = 0; h < chain_depth; ++h) cp_cn = dadd(cp_cn, chain[h]);
+                                } else {
+                                    long long h = 0;
+                                    cp_cn = chain_walk(PARENT, ECOST, near_slot, di, h);   // every lane walks the same chain
+                                    if (lane == 0) my_hops += h;
+                                }
+                            }
+                        }
+                    }
+                    if (do_rw) {
+                        const bool rw = lane < n && !hit && cc > dadd(cost_new, dpl);   // :905, strict
+                        const unsigned m = __ballot_sync(kFull, rw);
+                        if (m) {   // remember the decision: short list in shared memory, overflow as a per-node flag bit
+                            const int pos = n_rw + __popc(m & lt_mask);
+                            if (rw) { if (pos < prm.near_cap) rwlist[pos] = s; else NFLAG[s] |= 2; }
+                            n_rw += __popc(m);
+                        }
+                    }
+                    first = false;
+                    __syncwarp();
+                    head += n;
+                }
+                if (head > 0) {                                                   // keep the (< 32) leftover at the front
+                    const int rem = count - head;
+                    const int t = lane < rem ? stage[head + lane] : 0;
+                    __syncwarp();
+                    if (lane < rem) stage[lane] = t;
+                    count = rem;
+                    __syncwarp();
+                }
+            }
+
+            if (pass == 0 && commit_cp && k_total > 0) {   // EXTENSION (not the shipped behaviour): adopt the returned edge
+                if (lane == 0) { PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost; }
+                __syncwarp();
+            }
+        }
+        if (__any_sync(kFull, dup)) { status = RRTFND_ST_DUPLICATE; break; }
+        n_scan_nodes += nlist ? n_near_items : n_live;
+        n_edge_checks += k_total;
+        n_edge_checks_ref += 2 * (long long)k_total + 2;   // each candidate twice + Line(q_new, q_new) twice
+
+        // ---- E4. commit: rewire_kdtree's re-parenting (:906-910) and G.add_edge(*best_edge) (:148), serial on lane 0
+        bool need_refresh = false;
+        {
+            int d_childless = 0, flagged = 0;
+            if (lane == 0) {
+                auto reparent = [&](int s) {
+                    const int oldp = PARENT[s];
+                    if (--NCHILD[oldp] == 0) ++d_childless;
+                    const double2 v = XY[s];
+                    PARENT[s] = new_slot;
+                    ECOST[s] = dist_plain(v.x, v.y, px, py);
+                    flagged |= NFLAG[s] & 1;
+                };
+                const int n_list = n_rw < prm.near_cap ? n_rw : prm.near_cap;
+                for (int i = 0; i < n_list; ++i) reparent(rwlist[i]);
+                if (n_rw > n_list) {          // more re-parented nodes than the list holds (rare): find the flagged rest
+                    for (int s = 0; s < new_slot; ++s)
+                        if (NFLAG[s] & 2) { NFLAG[s] &= (uint8_t)~2; reparent(s); }
+                }
+                NCHILD[new_slot] = n_rw;
+                if (n_rw == 0) ++d_childless;
+                if (NCHILD[PARENT[new_slot]]++ == 0) --d_childless;
+                if (flagged) {   // the moved subtree holds a goal-reaching node: mark its new ancestors
+                    int n = new_slot;
+                    while (n >= 0 && !(NFLAG[n] & 1)) { NFLAG[n] |= 1; n = PARENT[n]; }
+                }
+            }
+            __syncwarp();
+            n_childless += __shfl_sync(kFull, d_childless, 0);
+            need_refresh = __shfl_sync(kFull, flagged, 0) != 0;
+            n_rewired += n_rw;
+        }
+
+        const int cp_parent_id = eval_cp ? ID[cp_slot] : -1;   // read before forced_removal can delete that node
+
+        // ================================================================ F. forced_removal (:233-237, :800-819)
+        int removed_id = -1;
+        if (prm.mode == RRTFND_MODE_FN && fn_count > prm.max_nodes) {                 // n_of_nodes > max_nodes (:233)
+            const int leaf = best_leaf_slot;
+            const int total = n_childless;
+            int n_ok = total - (NCHILD[new_slot] == 0 ? 1 : 0);
+            if (leaf >= 0 && leaf != new_slot && NCHILD[leaf] == 0) --n_ok;
+            if (n_ok <= 0) { status = RRTFND_ST_NO_CHILDLESS; break; }
+            int pick = -1;
+            for (;;) {
+                const uint32_t r = next_randbelow(rng, (uint32_t)total);          // random.choice (:813 / :816)
+                if (rng.exhausted) { status = RRTFND_ST_STREAM_EXHAUSTED; break; }
+                // r-th childless node in ascending slot order (tombstones hold nchild = -1)
+                int running = 0; pick = -1;
+                for (int base = 0; base < n_slots; base += 32) {
+                    const int s = base + lane;
+                    const unsigned m = __ballot_sync(kFull, s < n_slots && NCHILD[s] == 0);
+                    const int c = __popc(m);
+                    if ((int)r < running + c) { pick = base + (int)__fns(m, 0, (int)r - running + 1); break; }
+                    running += c;
+                }
+                if (pick != new_slot && pick != leaf) break;                      // :815
+            }
+            if (status != RRTFND_ST_RUNNING) break;
+            // finish_nodes_of_path.remove(id_removed) (:235-236), order preserving
+            int fpos = -1;
+            for (int base = 0; base < n_finish; base += 32) {
+                const int f = base + lane;
+                const unsigned m = __ballot_sync(kFull, f < n_finish && FINISH[f] == pick);
+                if (m) { fpos = base + __ffs(m) - 1; break; }
+            }
+            if (fpos >= 0) {
+                for (int base = fpos; base < n_finish - 1; base += 32) {
+                    const int f = base + lane;
+                    const bool ok = f < n_finish - 1;
+                    const int v = ok ? FINISH[f + 1] : 0;
+                    __syncwarp();
+                    if (ok) FINISH[f] = v;
+                    __syncwarp();
+                }
+                --n_finish;
+            }
+            int d_childless = -1;                                                 // the removed node was childless
+            removed_id = ID[pick];
+            __syncwarp();
+            if (lane == 0) {                                                      // Graph.remove_vertex (src/graph.py:64-77)
+                const int par = PARENT[pick];
+                if (par >= 0 && --NCHILD[par] == 0) ++d_childless;
+                ID[pick] = -1; NCHILD[pick] = -1; PARENT[pick] = -1;
+                XY[pick] = nan2;
+            }
+            __syncwarp();
+            n_childless += __shfl_sync(kFull, d_childless, 0);
+            --n_live; --fn_count; ++n_removed;
+        }
+
+        // ================================================================ G. goal test and best path (:155-170, :240-251)
+        if (reached) {
+            if (n_finish >= prm.finish_cap) { status = RRTFND_ST_FINISH_CAP; break; }
+            int L = 0; double cost = 0.0;
+            if (lane == 0) {
+                FINISH[n_finish] = new_slot;
+                int n = new_slot;                                                 // mark the ancestors of the new finish node
+                while (n >= 0 && !(NFLAG[n] & 1)) { NFLAG[n] |= 1; n = PARENT[n]; }
+                if (prm.mode == RRTFND_MODE_STAR) {                               // unconditional overwrite (:160-161)
+                    n = new_slot;
+                    while (n != root_slot && n >= 0) {
+                        if (L < prm.path_cap) BPATH[L] = ID[n];
+                        ++L; cost = dadd(cost, ECOST[n]); n = PARENT[n]; ++my_hops;
+                    }
+                    if (L < prm.path_cap) BPATH[L] = ID[root_slot];
+                    ++L;
+                }
+            }
+            __syncwarp();
+            ++n_finish;
+            solution_found = 1;
+            if (prm.mode == RRTFND_MODE_STAR) {
+                best_len = __shfl_sync(kFull, L, 0); best_cost = __shfl_sync(kFull, cost, 0); best_leaf_slot = new_slot;
+                if (best_len > prm.path_cap) { status = RRTFND_ST_PATH_CAP; break; }
+            }
+        }
+        // The reference recomputes every finish node's path each iteration and keeps a strictly cheaper one
+        // (:166-170, :247-251). A path cost only changes when a node with a goal-reaching descendant is rewired, and
+        // the list only grows through a new finish node, so those are the only iterations in which it can have an effect.
+        if ((reached || need_refresh) && n_finish > 0) {
+            double bd = CUDART_INF; int bf = kIntMax;
+            for (int f = lane; f < n_finish; f += 32) {
+                const double cost = path_cost(PARENT, ECOST, FINISH[f], root_slot, my_hops);
+                if (cost < bd) { bd = cost; bf = f; }
+            }
+            __syncwarp();
+            warp_argmin(bd, bf);
+            if (bd < best_cost) {                                                 // strict (:168, :249)
+                const int leaf = FINISH[bf];
+                int L = 0;
+                if (lane == 0) {
+                    int n = leaf;
+                    while (n != root_slot && n >= 0) {
+                        if (L < prm.path_cap) BPATH[L] = ID[n];
+                        ++L; n = PARENT[n]; ++my_hops;
+                    }
+                    if (L < prm.path_cap) BPATH[L] = ID[root_slot];
+                    ++L;
+                }
+                __syncwarp();
+                best_len = __shfl_sync(kFull, L, 0); best_cost = bd; best_leaf_slot = leaf;
+                if (best_len > prm.path_cap) { status = RRTFND_ST_PATH_CAP; break; }
+            }
+        }
+
+        // ================================================================ H. end of iteration
+        if (TRACE && iter < prm.trace_cap && lane == 0) {
+            rrtfnd_trace_t t;
+            t.id_new = id_new; t.id_near = ID[near_slot]; t.n_near = k_total; t.n_rewired = n_rw;
+            t.removed_id = removed_id;
+            t.cp_parent = cp_parent_id; t.cp_cost = eval_cp ? cp_cost : 0.0;
+            TRACE[iter] = t;
+        }
+        ++iter;                                                                   // :173 / :254
     }
-    phase_store(&prm, &bt, smem);
+
+    // ---- write back
+    __syncwarp();
+    const long long hops = warp_sum(my_hops), tests = warp_sum(my_tests);
+    if (lane == 0) {
+        PL->best_cost = best_cost; PL->cursor = rng.cursor; PL->attempts = attempts;
+        PL->n_edge_checks = n_edge_checks; PL->n_edge_checks_ref = n_edge_checks_ref;
+        PL->n_circle_tests += tests; PL->n_scan_nodes = n_scan_nodes; PL->n_chain_hops += hops;
+        PL->n_slots = n_slots; PL->n_live = n_live; PL->last_id = last_id; PL->iter = iter;
+        PL->root_slot = root_slot; PL->n_finish = n_finish; PL->best_len = best_len; PL->status = status;
+        PL->n_rewired = n_rewired; PL->n_removed = n_removed; PL->solution_found = solution_found;
+        PL->n_compactions = n_compactions; PL->fn_count = fn_count;
+    }
 }
 
 // Graph.__init__ (src/graph.py:25-32): a tree holding only the start node, id 0.
