@@ -272,6 +272,15 @@ int rrtfnd_fnd_valid_path(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batc
 int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root_id,
                          double radius, int32_t* out_linked_id, void* stream);
 
+/* regrow + nearest_node + reconnect_ancestors (src/algorithm.py:482-543, :702-728): up to max_iter (500 in the reference)
+ * plain extensions of the root tree from the planner's word stream (planner cursor), each followed by an attempt to hang
+ * the separate tree - re-rooted at the first of its nodes, in ascending id, that the new node sees closer than
+ * step_length - under the new node. Uses the culling grid of the current obstacle table. out_reconnected[p] = 1 / 0,
+ * or a negative status; out_iters[p] (may be NULL) = extensions made. On success the stored best path / cost become
+ * find_path(path[0], root). */
+int rrtfnd_fnd_regrow(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root_id,
+                      int32_t max_iter, int32_t* out_reconnected, int32_t* out_iters, void* stream);
+
 /* ---- host-buffer entry point (what the Python drop-in and bench `e2e` call) -------------------- */
 
 /* Plan P independent problems given HOST buffers; allocates device memory, copies in, runs to completion,

@@ -64,6 +64,9 @@ def lib():
     L.orc_fnd_select_branch.argtypes = [vp, C.c_int]
     L.orc_fnd_valid_path.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int, ip]
     L.orc_fnd_reconnect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.orc_fnd_regrow.argtypes = [vp, C.POINTER(Params), vp, C.c_double, C.c_double, C.c_int, vp, C.c_int64, C.c_uint64, C.c_uint64,
+                                 C.c_int, ip]
+    L.orc_set_cursor.argtypes = [vp, C.c_uint64]
     L.orc_set_best_path.argtypes = [vp, vp, C.c_int]
     L.orc_get_root.argtypes = [vp]
     L.orc_cull_probe.restype = C.c_int64
@@ -176,6 +179,18 @@ class OracleTree:
     def reconnect(self, obstacles, separate_root, radius, last_node):
         ob = obst_table3(obstacles)
         return self.L.orc_fnd_reconnect(self.h, _ptr(ob), len(ob), int(separate_root), float(radius), int(last_node))
+
+    def regrow(self, prm: Params, obstacles, goal, separate_root, words=None, seed=0, stream_id=0, max_iter=500, cursor=None):
+        """regrow (src/algorithm.py:482-528): returns (reconnected or negative status, extensions made)."""
+        ob = obst_table3(obstacles)
+        prm.n_obst = len(ob)
+        w = None if words is None else np.ascontiguousarray(words, dtype=np.uint32)
+        if cursor is not None:
+            self.L.orc_set_cursor(self.h, int(cursor))
+        it = C.c_int(0)
+        r = self.L.orc_fnd_regrow(self.h, C.byref(prm), _ptr(ob), float(goal[0]), float(goal[1]), int(separate_root), _ptr(w),
+                                  0 if w is None else len(w), int(seed), int(stream_id), int(max_iter), C.byref(it))
+        return r, it.value
 
     def get_cost(self, id_):
         return self.L.orc_get_cost(self.h, int(id_))

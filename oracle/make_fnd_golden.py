@@ -80,6 +80,21 @@ def run_case(fc):
                     out["rcret_path"], out["rcret_cost"] = np.array(ret[0], np.int32), np.float64(ret[1])
                 for k, v in H.tree_arrays(G).items():
                     out[f"rc_{k}"] = v
+                if ret is None:
+                    # regrow (src/algorithm.py:482-528) on its own word stream, as test_select_branch calls it (:477-479)
+                    from .philox import WordStreamRandom
+                    words = philox_words(777, FND_CASES.index(fc), 80000)
+                    rng = WordStreamRandom(words)
+                    with H.patched_reference(rng, None):
+                        alg.get_distance_dict = lambda G_, node, idx=None: orig_gdd(G_, node, idx)
+                        alg.regrow(G=G, map=m, step_length=case["step_length"], radius=case["step_length"], id_root=root,
+                                   id_separate_root=sep, last_node=last_node, bias=0.02)
+                    out["rg_words_used"] = np.int64(rng.cursor)
+                    # regrow returns nothing; it has reconnected iff an old node now hangs under a node created by regrow
+                    old_last = int(out["rc_ids"].max())
+                    out["rg_reconnected"] = np.int32(any(p is not None and p > old_last for i, p in G.parent.items() if i <= old_last))
+                    for k, v in H.tree_arrays(G).items():
+                        out[f"rg_{k}"] = v
     finally:
         alg.get_distance_dict = orig_gdd
     return out
@@ -91,7 +106,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"fnd_{fc['name']}.npz"), **out)
         print(fc["name"], "path", len(out["path0"]), "->", len(out["path1"]), "nodes", len(out["sb_ids"]), "->",
               len(out["vp_ids"]), "sep", int(out["vp_sep"]), "err", int(out["vp_index_error"]),
-              "linked", int(out.get("rc_linked", -9)))
+              "linked", int(out.get("rc_linked", -9)), "regrow", int(out.get("rg_reconnected", -9)), int(out.get("rg_words_used", 0)),
+              len(out.get("rg_ids", [])))
 
 
 if __name__ == "__main__":

@@ -455,6 +455,98 @@ int orc_fnd_reconnect(orc_tree_t* t, const double* obst, int M, int sep, double 
     return -1;
 }
 
+
+/* reconnect_ancestors (src/algorithm.py:531-543): make `id` the root of its tree by reversing the parent pointers on
+ * its chain. Edge costs are NOT touched (the reference leaves G.cost as it was). Child COUNTS are kept consistent with
+ * the parents here; the reference's children lists are not, so they are not compared for regrow. */
+static void reconnect_ancestors(orc_tree_t* t, int id) {
+    int node = id, parent = t->parent[node];
+    if (parent < 0) return;
+    while (t->parent[parent] >= 0) {
+        int pp = t->parent[parent];
+        t->parent[parent] = node; t->nchild[node]++; t->nchild[parent]--;
+        node = parent; parent = pp;
+    }
+    t->parent[parent] = node; t->nchild[node]++; t->nchild[parent]--;
+}
+
+/* regrow (src/algorithm.py:482-528): grow the root tree with plain extensions (brute-force nearest_node :702-728 that
+ * skips the separate tree; choose_parent's return value is dropped at :505) until a new node sees a separate-tree node
+ * closer than step_length, then hang the separate tree (re-rooted at that node) under the new node. At most max_iter
+ * (500 in the reference) extensions. Returns 1 if reconnected, 0 if not, < 0 = status. *iters_out = extensions made. */
+int orc_fnd_regrow(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst, double gx, double gy, int sep_root,
+                   const uint32_t* words, int64_t n_words, uint64_t seed, uint64_t stream_id, int max_iter, int* iters_out) {
+    const int M = prm->n_obst;
+    unsigned char* in_sep = (unsigned char*)calloc((size_t)t->cap, 1);
+    for (int i = 0; i <= t->last_id; ++i) {              /* check_for_tree_associativity per node (:483) */
+        if (!t->alive[i]) continue;
+        int n = i;
+        while (t->parent[n] >= 0) n = t->parent[n];
+        in_sep[i] = (unsigned char)(n == sep_root);
+    }
+    orc_rng_t rng;
+    memset(&rng, 0, sizeof rng);
+    rng.mode = prm->stream_mode; rng.words = words; rng.n_words = n_words; rng.seed = seed; rng.stream = stream_id;
+    rng.cursor = t->cursor;
+    int iter = 0, reconnected = 0, status = 0;
+    while (iter < max_iter && !reconnected) {
+        if (rng.mode == RRTFND_STREAM_WORDS && (int64_t)rng.cursor + ORC_RESERVE_WORDS > n_words) { status = -RRTFND_ST_NEED_WORDS - 100; break; }
+        if (t->last_id + 1 >= t->cap) { status = RRTFND_ST_CAPACITY; break; }
+        ++t->attempts;
+        double qx, qy;
+        if (rng_random(&rng) < prm->bias) { qx = gx; qy = gy; }
+        else {
+            qx = prm->x_lo + (prm->x_hi - prm->x_lo) * rng_random(&rng);
+            qy = prm->y_lo + (prm->y_hi - prm->y_lo) * rng_random(&rng);
+        }
+        if (is_occupied(qx, qy, obst, M, prm->node_radius)) continue;           /* :493 */
+        int exact = 0, best = -1;
+        double bestd = INFINITY;
+        for (int i = 0; i <= t->last_id; ++i) if (t->alive[i] && t->x[i] == qx && t->y[i] == qy) exact = 1;   /* :712-714 then :495 */
+        if (exact) continue;
+        for (int i = 0; i <= t->last_id; ++i) {                                   /* :718-726 */
+            if (!t->alive[i] || in_sep[i]) continue;
+            if (through_obstacle(t->x[i], t->y[i], qx, qy, obst, M, 0)) continue; /* Line(ver, vertex): p1 = node */
+            double d = dist_fma(t->x[i], t->y[i], qx, qy);
+            if (d < bestd) { bestd = d; best = i; }
+        }
+        if (best < 0) continue;
+        double nx = t->x[best], ny = t->y[best];
+        double d = dist_fma(qx, qy, nx, ny);                                      /* steer (:496) */
+        double ux = (qx - nx) / d, uy = (qy - ny) / d;
+        double sx = nx + ux * prm->step_length, sy = ny + uy * prm->step_length;
+        double px = qx, py = qy;
+        if (d > prm->step_length) { px = sx; py = sy; }
+        if (is_occupied(px, py, obst, M, prm->node_radius)) continue;            /* :497 */
+        for (int i = 0; i <= t->last_id; ++i)
+            if (t->alive[i] && t->x[i] == px && t->y[i] == py) { status = RRTFND_ST_DUPLICATE; goto out; }
+        int id_new = ++t->last_id;
+        t->x[id_new] = px; t->y[id_new] = py; t->alive[id_new] = 1; t->nchild[id_new] = 0; in_sep[id_new] = 0;
+        t->n_live++;
+        t->parent[id_new] = best; t->ecost[id_new] = dist_fma(px, py, nx, ny);    /* :500-506 */
+        t->nchild[best]++;
+        ++iter;
+        for (int i = 0; i < id_new; ++i) {                                        /* :510-518, separate tree in ascending id */
+            if (!t->alive[i] || !in_sep[i]) continue;
+            if (through_obstacle(px, py, t->x[i], t->y[i], obst, M, 0)) continue; /* Line(q_new, node): p1 = q_new */
+            double dd = dist_fma(px, py, t->x[i], t->y[i]);
+            if (dd < prm->step_length) {
+                reconnect_ancestors(t, i);
+                t->parent[i] = id_new; t->nchild[id_new]++; t->ecost[i] = dd;
+                reconnected = 1;
+                break;
+            }
+        }
+    }
+out:
+    free(in_sep);
+    t->cursor = rng.cursor;
+    if (iters_out) *iters_out = iter;
+    if (status) return status;
+    if (reconnected && t->best_len > 0) t->best_cost = find_path(t, t->best_path[0], t->best_path, &t->best_len);
+    return reconnected;
+}
+
 int orc_set_best_path(orc_tree_t* t, const int* ids, int n) {
     if (n > t->path_cap) return -1;
     memcpy(t->best_path, ids, (size_t)n * sizeof(int));
@@ -462,6 +554,7 @@ int orc_set_best_path(orc_tree_t* t, const int* ids, int n) {
     return 0;
 }
 int orc_get_root(const orc_tree_t* t) { return t->root; }
+void orc_set_cursor(orc_tree_t* t, uint64_t c) { t->cursor = c; }
 
 /* --------------------------------------------------------------------------------- the planner */
 

@@ -13,7 +13,7 @@ EXPORTS = [
     "rrtfnd_abi_version", "rrtfnd_status_string", "rrtfnd_plan_smem_bytes", "rrtfnd_obst_grid_build_host",
     "rrtfnd_edges_vs_circles", "rrtfnd_points_occupied", "rrtfnd_edges_vs_circles_grid", "rrtfnd_points_occupied_grid", "rrtfnd_nearest_visible", "rrtfnd_near_set",
     "rrtfnd_chain_cost", "rrtfnd_plan_batch", "rrtfnd_init_batch",
-    "rrtfnd_fnd_select_branch", "rrtfnd_fnd_valid_path", "rrtfnd_fnd_reconnect",
+    "rrtfnd_fnd_select_branch", "rrtfnd_fnd_valid_path", "rrtfnd_fnd_reconnect", "rrtfnd_fnd_regrow",
     "rrtfnd_plan_host",
 ]
 
@@ -47,6 +47,7 @@ def _load():
     lib.rrtfnd_fnd_select_branch.argtypes = [PP, PB, vp, vp, vp]
     lib.rrtfnd_fnd_valid_path.argtypes = [PP, PB, vp, vp, vp, vp]
     lib.rrtfnd_fnd_reconnect.argtypes = [PP, PB, vp, dbl, vp, vp]
+    lib.rrtfnd_fnd_regrow.argtypes = [PP, PB, vp, i32, vp, vp, vp]
     lib.rrtfnd_plan_host.argtypes = [PP, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     lib.rrtfnd_obst_grid_build_host.argtypes = [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, C.POINTER(ObstGrid), vp, vp, vp, vp, vp]
     for name in EXPORTS:

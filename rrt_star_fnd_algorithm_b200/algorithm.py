@@ -201,6 +201,36 @@ def reconnect(G: Graph, path: list, map: Map, step_size: float, id_root: int, id
     return [int(i) for i in b.best_path(0)], np.float64(b.planners()[0]["best_cost"])
 
 
+def regrow(G: Graph, map: Map, step_length: float, radius: float, id_root: int, id_separate_root: int, last_node: int,
+           bias: float):
+    """Grow the root tree (at most 500 extensions, drawing from the global `random` like the planners) until a new node
+    can adopt the separated tree; returns None like the reference (src/algorithm.py:482-528). `radius` only feeds the
+    reference's choose_parent call whose result it drops."""
+    import torch
+    from .batch import PlannerBatch
+    ids, xy, parent, cost, root_id = G._export()
+    cap = len(ids) + 502
+    state = random.getstate()
+    words = _draw_words(16 * 500 + 256)
+    b = PlannerBatch("star", starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
+                     obstacles=map.obstacles_c, xy_range=G.xy_range, iter_num=1, step_length=step_length, radius=radius,
+                     node_radius=map.node_radius, bias=bias, capacity=cap, path_cap=max(64, cap), finish_cap=8,
+                     words=words[None, :])
+    b.reset()
+    b.load_tree(0, ids, xy, parent, cost, root_id, G.last_id)
+    b.set_best_path(0, [last_node])
+    r, _ = b.regrow([id_separate_root])
+    pl = b.planners()[0]
+    random.setstate(state)
+    if int(pl["cursor"]):
+        random.getrandbits(32 * int(pl["cursor"]))
+    if int(r[0]) < 0:
+        raise PlannerError(f"regrow stopped with status {int(r[0])}")
+    t = b.tree(0)
+    G._import(t["ids"], np.column_stack([t["x"], t["y"]]), t["parent"], t["cost"], int(pl["last_id"]), {i: G.vertices[i] for i in G.vertices})
+    return None
+
+
 # ---- helpers user code calls directly --------------------------------------------------------------------------------
 
 def calc_distance(p1: tuple, p2: tuple) -> float:

@@ -265,6 +265,28 @@ class PlannerBatch:
                                                      C.c_void_p(out.data_ptr()), self._stream()), "rrtfnd_fnd_reconnect")
         return out.cpu().numpy()
 
+    def regrow(self, separate_root_ids, max_iter=500):
+        """regrow for every planner (draws from each planner's word stream at its cursor). Returns (reconnected or negative
+        status, extensions made)."""
+        sep = self._ids_tensor(separate_root_ids)
+        out = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        its = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            b = self._batch()
+            _abi.check(_abi.lib.rrtfnd_fnd_regrow(C.byref(self.prm), C.byref(b), C.c_void_p(sep.data_ptr()), int(max_iter),
+                                                  C.c_void_p(out.data_ptr()), C.c_void_p(its.data_ptr()), self._stream()),
+                       "rrtfnd_fnd_regrow")
+        return out.cpu().numpy(), its.cpu().numpy()
+
+    def set_stream_words(self, words, cursor=0):
+        """Switch the planners to an explicit word buffer ([P][n] uint32) read from `cursor` on."""
+        w = np.ascontiguousarray(words, dtype=np.uint32).reshape(self.P, -1)
+        self.words = torch.from_numpy(w.view(np.int32)).to(self.device)
+        self.prm.stream_mode, self.prm.words_per_planner = STREAM_WORDS, w.shape[1]
+        pl = self.planners_t.cpu().numpy().reshape(-1).view(PLANNER_DTYPE).copy()
+        pl["cursor"] = cursor
+        self.planners_t = torch.from_numpy(pl.view(np.uint8).reshape(self.P, PLANNER_BYTES)).to(self.device)
+
     def slot_id(self, p: int, slot: int) -> int:
         return int(self.id[p, slot].item())
 

@@ -16,11 +16,13 @@
 #include "../../include/rrtfnd.h"
 #include "arith.cuh"
 #include "cull.cuh"
+#include "rng.cuh"
 
 namespace rrtfnd {
 
 constexpr int kFndWarps = 4;
-constexpr uint8_t kKeep = 4, kOnPath = 8, kOccupied = 16, kDelete = 32;
+constexpr uint8_t kKeep = 4, kOnPath = 8, kOccupied = 16, kDelete = 32, kSeparate = 64;
+constexpr int kReserveWordsFnd = 64;   // as in planner.cu
 
 struct PlannerView {
     double2* XY; double* ECOST; int32_t* PARENT; int32_t* NCHILD; int32_t* ID; uint8_t* NFLAG; int32_t* FINISH; int32_t* BPATH;
@@ -231,11 +233,155 @@ __global__ void __launch_bounds__(32 * kFndWarps) reconnect_kernel(const rrtfnd_
             const double2 q = v.XY[sep], c = v.XY[link];
             v.PARENT[sep] = link; v.NCHILD[link] += 1;                        // G.add_edge(id_separate_root, node, cost) (:389-390)
             v.ECOST[sep] = dist_fma(c.x, c.y, q.x, q.y);
+            if (v.NFLAG[sep] & 1)                                             // keep "has a goal-reaching descendant" closed upwards
+                for (int n = link; n >= 0 && !(v.NFLAG[n] & 1); n = v.PARENT[n]) v.NFLAG[n] |= 1;
             int L = 0; double cost = 0.0;                                     // find_path(G, last_node, id_root) (:400)
             rewrite_best_path(prm, v, leaf, root, &L, &cost);
             v.PL->best_len = L; v.PL->best_cost = cost;
         }
         out_linked_id[p] = link >= 0 ? v.ID[link] : -1;
+    }
+}
+
+
+// regrow (src/algorithm.py:482-528): extend the root tree with plain extensions — brute-force nearest_node (:702-728)
+// that skips the separate tree and tests Line(node, sample); choose_parent's return value is dropped at :505 — until a
+// new node sees a separate-tree node closer than step_length; that node becomes the root of the separate tree
+// (reconnect_ancestors, :531-543: the parent pointers on its chain are reversed, edge costs untouched) and is hung under
+// the new node. At most max_iter extensions (500 in the reference).
+__global__ void __launch_bounds__(32 * kFndWarps) regrow_kernel(const __grid_constant__ rrtfnd_params_t prm,
+                                                                const __grid_constant__ rrtfnd_batch_t bt,
+                                                                const int32_t* __restrict__ separate_root_id, int max_iter,
+                                                                int32_t* __restrict__ out_reconnected, int32_t* __restrict__ out_iters) {
+    __shared__ WordSrc rngs[kFndWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, p = blockIdx.x * kFndWarps + wib;
+    if (p >= bt.n_planners) return;
+    const PlannerView v = view_of(prm, bt, p);
+    WordSrc& rng = rngs[wib];
+    int n_slots = v.PL->n_slots, n_live = v.PL->n_live, last_id = v.PL->last_id;
+    long long attempts = v.PL->attempts;
+    const int root = v.PL->root_slot;
+    const double gx = v.PL->goal_x, gy = v.PL->goal_y;
+    const int sep = find_slot(v.ID, n_slots, separate_root_id[p], lane);
+    int iter = 0, result = 0;
+    if (sep < 0) { if (lane == 0) { out_reconnected[p] = RRTFND_E_BADARG; if (out_iters) out_iters[p] = 0; } return; }
+    for (int s = lane; s < n_slots; s += 32) {                                // separate_tree (:483)
+        if (v.ID[s] < 0) continue;
+        int n = s;
+        while (v.PARENT[n] >= 0) n = v.PARENT[n];
+        v.NFLAG[s] = (uint8_t)((v.NFLAG[s] & ~kSeparate) | (n == sep ? kSeparate : 0));
+    }
+    rng.mode = prm.stream_mode;
+    rng.words = bt.words ? bt.words + (size_t)p * prm.words_per_planner : nullptr;
+    rng.n_words = prm.words_per_planner;
+    rng.seed = v.PL->seed; rng.stream = v.PL->stream_id; rng.cursor = v.PL->cursor;
+    rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0;
+    __syncwarp();
+    const Obst ob = make_obst(bt.obst, prm.n_obst, &bt.grid);
+    long long tests = 0;
+    bool reconnected = false;
+    while (iter < max_iter && !reconnected) {
+        if (prm.stream_mode == RRTFND_STREAM_WORDS && (long long)rng.cursor + kReserveWordsFnd > prm.words_per_planner) { result = -RRTFND_ST_NEED_WORDS - 100; break; }
+        if (n_slots >= prm.capacity) { result = RRTFND_ST_CAPACITY; break; }
+        ++attempts;
+        double qx, qy;                                                        // Graph.random_node (src/graph.py:96-98)
+        if (next_random(rng) < prm.bias) { qx = gx; qy = gy; }
+        else {
+            qx = dadd(prm.x_lo, dmul(dsub(prm.x_hi, prm.x_lo), next_random(rng)));
+            qy = dadd(prm.y_lo, dmul(dsub(prm.y_hi, prm.y_lo), next_random(rng)));
+        }
+        if (point_occupied_warp(ob, qx, qy, prm.node_radius, lane, tests)) continue;          // :493
+        // nearest_node: an identical vertex is returned as is and rejected at :495; otherwise the closest (calc_distance,
+        // lowest id on ties) among the nodes outside the separate tree whose Line(node, sample) is free
+        bool exact = false;
+        double bd = CUDART_INF; int bs = 0x7fffffff;
+        for (int s = lane; s < n_slots; s += 32) {
+            if (v.ID[s] < 0) continue;
+            const double2 c = v.XY[s];
+            exact |= (c.x == qx && c.y == qy);
+            if (v.NFLAG[s] & kSeparate) continue;
+            if (seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, qx, qy, 0, 1) & 1) continue;
+            const double d = dist_fma(c.x, c.y, qx, qy);
+            if (d < bd) { bd = d; bs = s; }
+        }
+        __syncwarp();
+        if (__any_sync(kFull, exact)) continue;
+        {   // (value, slot) argmin over the warp
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double od = __shfl_xor_sync(kFull, bd, off); const int os = __shfl_xor_sync(kFull, bs, off);
+                if (key_less(od, os, bd, bs)) { bd = od; bs = os; }
+            }
+        }
+        if (bs == 0x7fffffff) continue;
+        const double2 nb = v.XY[bs];
+        double px = qx, py = qy;
+        {
+            const double d = dist_fma(qx, qy, nb.x, nb.y);                    // steer (:496)
+            const double ux = ddiv(dsub(qx, nb.x), d), uy = ddiv(dsub(qy, nb.y), d);
+            const double tx = dadd(nb.x, dmul(ux, prm.step_length)), ty = dadd(nb.y, dmul(uy, prm.step_length));
+            if (d > prm.step_length) { px = tx; py = ty; }
+        }
+        if (point_occupied_warp(ob, px, py, prm.node_radius, lane, tests)) continue;          // :497
+        bool dup = false;
+        for (int s = lane; s < n_slots; s += 32) { const double2 c = v.XY[s]; dup |= (c.x == px && c.y == py); }
+        if (__any_sync(kFull, dup)) { result = RRTFND_ST_DUPLICATE; break; }
+        const int new_slot = n_slots++;
+        ++last_id; ++n_live; ++iter;
+        if (lane == 0) {
+            v.XY[new_slot] = make_double2(px, py);
+            v.ID[new_slot] = last_id; v.PARENT[new_slot] = bs; v.ECOST[new_slot] = dist_fma(px, py, nb.x, nb.y);   // :500-506
+            v.NCHILD[new_slot] = 0; v.NFLAG[new_slot] = 0;
+            v.NCHILD[bs] += 1;
+        }
+        __syncwarp();
+        int link = -1;                                                        // :510-518, separate tree in ascending id
+        for (int base = 0; base < new_slot && link < 0; base += 32) {
+            const int s = base + lane;
+            bool ok = false;
+            if (s < new_slot && v.ID[s] >= 0 && (v.NFLAG[s] & kSeparate)) {
+                const double2 c = v.XY[s];
+                if (!(seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, px, py, c.x, c.y, 0, 1) & 1))   // Line(q_new, node)
+                    ok = dist_fma(px, py, c.x, c.y) < prm.step_length;
+            }
+            const unsigned m = __ballot_sync(kFull, ok);
+            if (m) link = base + __ffs(m) - 1;
+        }
+        if (link >= 0) {
+            if (lane == 0) {
+                int node = link, parent = v.PARENT[node];                     // reconnect_ancestors (:531-543), counts kept consistent
+                const uint8_t had = v.NFLAG[sep] & 1;
+                if (parent >= 0) {
+                    while (v.PARENT[parent] >= 0) {
+                        const int pp = v.PARENT[parent];
+                        v.PARENT[parent] = node; v.NCHILD[node] += 1; v.NCHILD[parent] -= 1;
+                        node = parent; parent = pp;
+                    }
+                    v.PARENT[parent] = node; v.NCHILD[node] += 1; v.NCHILD[parent] -= 1;
+                }
+                const double2 c = v.XY[link];
+                v.PARENT[link] = new_slot; v.NCHILD[new_slot] += 1;            // G.add_edge(node, id_new, distance) (:516)
+                v.ECOST[link] = dist_fma(px, py, c.x, c.y);
+                if (had) {                                                    // keep "has a goal-reaching descendant" closed upwards
+                    v.NFLAG[link] |= 1;
+                    for (int n = new_slot; n >= 0 && !(v.NFLAG[n] & 1); n = v.PARENT[n]) v.NFLAG[n] |= 1;
+                }
+            }
+            __syncwarp();
+            reconnected = true;
+        }
+    }
+    const int leaf = (reconnected && v.PL->best_len > 0) ? find_slot(v.ID, n_slots, v.BPATH[0], lane) : -1;
+    __syncwarp();
+    if (lane == 0) {
+        v.PL->n_slots = n_slots; v.PL->n_live = n_live; v.PL->last_id = last_id; v.PL->attempts = attempts; v.PL->cursor = rng.cursor;
+        if (leaf >= 0) {
+            int L = 0; double cost = 0.0;
+            rewrite_best_path(prm, v, leaf, root, &L, &cost);
+            v.PL->best_len = L; v.PL->best_cost = cost;
+        }
+        out_reconnected[p] = result ? result : (reconnected ? 1 : 0);
+        if (out_iters) out_iters[p] = iter;
     }
 }
 
@@ -276,5 +422,14 @@ extern "C" int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_bat
     if (fnd_check(prm, bt) || !separate_root_id || !out_linked_id || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
     const int blocks = (bt->n_planners + kFndWarps - 1) / kFndWarps;
     reconnect_kernel<<<blocks, 32 * kFndWarps, 0, (cudaStream_t)stream>>>(*prm, *bt, separate_root_id, radius, out_linked_id);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rrtfnd_fnd_regrow(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, const int32_t* separate_root_id,
+                                 int32_t max_iter, int32_t* out_reconnected, int32_t* out_iters, void* stream) {
+    if (fnd_check(prm, bt) || !separate_root_id || !out_reconnected || max_iter < 0 || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
+    if (prm->stream_mode == RRTFND_STREAM_WORDS && !bt->words) return RRTFND_E_BADARG;
+    const int blocks = (bt->n_planners + kFndWarps - 1) / kFndWarps;
+    regrow_kernel<<<blocks, 32 * kFndWarps, 0, (cudaStream_t)stream>>>(*prm, *bt, separate_root_id, max_iter, out_reconnected, out_iters);
     return (int)cudaGetLastError();
 }

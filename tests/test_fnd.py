@@ -50,6 +50,41 @@ def test_oracle_fnd_matches_reference_golden(fc):
         assert np.array_equal(t.best_path(), g["rcret_path"]) and t.planner().best_cost == float(g["rcret_cost"])
 
 
+REGROW = [fc for fc in FND_CASES if fc["name"] in ("float_c", "float_b", "star_b", "int_a")]
+
+
+def regrow_tree(g):
+    """regrow's golden tree: child counts recomputed from the parents (the reference's children lists are inconsistent
+    after reconnect_ancestors; parents, positions and edge costs are what is pinned)."""
+    t = stage_tree(g, "rg")
+    ids = list(t["ids"])
+    nc = np.zeros(len(ids), np.int32)
+    for p in t["parent"]:
+        if p >= 0:
+            nc[ids.index(int(p))] += 1
+    t["nchild"] = nc
+    return t
+
+
+def regrow_params(case):
+    prm = K.params_for(dict(case, bias=0.02), stream_mode=S.STREAM_WORDS, n_words=80000, flags=0)   # test_select_branch passes bias=0.02
+    return prm
+
+
+@pytest.mark.parametrize("fc", REGROW, ids=[f["name"] for f in REGROW])
+def test_oracle_regrow_matches_reference_golden(fc):
+    case, g = K.case_by_name(fc["case"]), load_npz(f"fnd_{fc['name']}.npz")
+    t = grown_oracle(case, extra=600)
+    assert t.select_branch(int(g["current"])) == 0
+    sep, err = t.valid_path(g["obstacles2"], case["node_radius"], int(g["current"]))
+    assert not err and t.reconnect(g["obstacles2"], sep, fc["radius"], int(g["path0"][0])) == -1
+    words = philox_words(777, FND_CASES.index(fc), 80000)
+    r, iters = t.regrow(regrow_params(case), g["obstacles2"], case["goal"], sep, words=words, cursor=0)
+    assert r == int(g["rg_reconnected"]) == 1
+    assert t.planner().cursor == int(g["rg_words_used"])
+    assert_tree_equal(t.export(), regrow_tree(g), "regrow")
+
+
 def test_select_branch_rejects_a_node_off_the_path():
     t = grown_oracle(K.case_by_name("float_fn"))
     off = next(int(i) for i in t.export()["ids"][::-1] if int(i) not in set(t.best_path().tolist()))
@@ -102,6 +137,32 @@ def test_gpu_fnd_matches_reference_golden(fc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fc", REGROW, ids=[f["name"] for f in REGROW])
+def test_gpu_regrow_matches_reference_golden(fc):
+    case, g = K.case_by_name(fc["case"]), load_npz(f"fnd_{fc['name']}.npz")
+    P = 2
+    b = grown_batch(case, P, capacity=case["iter_num"] + 700)
+    cur = [int(g["current"])] * P
+    assert list(b.select_branch(cur)) == [0] * P
+    b.set_obstacles([tuple(r) for r in g["obstacles2"]])
+    sep, err = b.valid_path(cur)
+    assert not err.any() and list(b.reconnect(sep, fc["radius"])) == [-1] * P
+    words = philox_words(777, FND_CASES.index(fc), 80000)
+    b.set_stream_words(np.stack([words] * P))
+    b.prm.bias = 0.02                                           # test_select_branch calls regrow with bias=0.02
+    r, iters = b.regrow(sep)
+    assert list(r) == [1] * P and iters[0] == iters[1] > 0
+    for p in range(P):
+        assert_tree_equal(b.tree(p), regrow_tree(g), f"regrow[{p}]")
+        assert int(b.planners()[p]["cursor"]) == int(g["rg_words_used"])
+    # the same against the oracle, including the re-derived best path
+    t = grown_oracle(case, extra=700)
+    t.select_branch(cur[0]); t.valid_path(g["obstacles2"], case["node_radius"], cur[0])
+    t.regrow(regrow_params(case), g["obstacles2"], case["goal"], int(sep[0]), words=words, cursor=0)
+    assert np.array_equal(b.best_path(0), t.best_path()) and b.planners()[0]["best_cost"] == t.planner().best_cost
+
+
+@pytest.mark.gpu
 def test_gpu_fnd_then_regrow_with_the_planner():
     """After the surgery the batch is a valid planner state: growing on from it equals the oracle doing the same."""
     fc = next(f for f in FND_CASES if f["name"] == "float_a")
@@ -146,3 +207,68 @@ def test_dropin_fnd_functions_on_graph_objects():
     ret = A.reconnect(G, new_path, m, fc["radius"], G.id_vertex[G.start], sep, path[0])
     assert ret is not None and list(ret[0]) == [int(i) for i in g["rcret_path"]] and float(ret[1]) == float(g["rcret_cost"])
     assert_tree_equal(graph_arrays(G), stage_tree(g, "rc"), "drop-in reconnect")
+
+
+@pytest.mark.gpu
+def test_gpu_fnd_batch_of_different_planners_matches_the_oracle():
+    """48 planners with their own start / goal / stream: re-root each at its own path node, invalidate, reconnect."""
+    case = dict(K.case_by_name("float_star"), iter_num=400)
+    rng = np.random.default_rng(12)
+    P = 48
+    starts, goals = [], []
+    while len(starts) < P:
+        s, t = rng.uniform(2, 98, 2), rng.uniform(2, 98, 2)
+        if O.is_occupied(s, case["obstacles"], 1) or O.is_occupied(t, case["obstacles"], 1) or np.hypot(*(s - t)) < 40:
+            continue
+        starts.append(tuple(s)); goals.append(tuple(t))
+    from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
+    b = PlannerBatch("star", starts=starts, goals=goals, obstacles=case["obstacles"], xy_range=case["xy_range"], iter_num=400,
+                     step_length=3, radius=6, node_radius=1, bias=0.05, seeds=[5] * P, stream_ids=list(range(P))).run()
+    b.check_status()
+    trees = []
+    prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0)
+    prm.bias = 0.05
+    for p in range(P):
+        t = O.OracleTree(starts[p], 402)
+        assert t.run(prm, case["obstacles"], goals[p], seed=5, stream_id=p)[0] == S.ST_DONE
+        trees.append(t)
+    cur, extra = [], list(case["obstacles"])
+    for p in range(P):
+        path = trees[p].best_path()
+        assert np.array_equal(path, b.best_path(p))
+        cur.append(int(path[-3]) if len(path) >= 6 else -7)          # planners without a (long enough) path get a bad id
+        if len(path) >= 6:
+            e = trees[p].export(); i = list(e["ids"]).index(int(path[len(path) // 2]))
+            if p % 3 == 0:
+                extra.append((float(e["x"][i]), float(e["y"][i]), 0.6))   # drop an obstacle on a mid-path node of every third planner
+    st = b.select_branch(cur)
+    b.set_obstacles(extra)
+    sep, err = b.valid_path(cur)
+    # reconnect only where a tree was really split off (linking a root to its own descendant would make a cycle)
+    linked = b.reconnect([int(sep[p]) if int(sep[p]) != cur[p] else -1 for p in range(P)], 9.0)
+    n_ok = n_split = 0
+    for p in range(P):
+        t = trees[p]
+        want = t.select_branch(cur[p])
+        assert int(st[p]) == want
+        if want != 0:
+            assert_tree_equal(b.tree(p), t.export(), f"untouched[{p}]")
+            continue
+        wsep, werr = t.valid_path(extra, 1, cur[p])
+        assert bool(err[p]) == werr
+        if werr:
+            assert_tree_equal(b.tree(p), t.export(), f"index-error[{p}]")
+            continue
+        assert int(sep[p]) == wsep
+        if wsep == cur[p]:
+            assert int(linked[p]) == -1
+            assert_tree_equal(b.tree(p), t.export(), f"not-split[{p}]")
+            n_ok += 1
+            continue
+        n_split += 1
+        wl = t.reconnect(extra, wsep, 9.0, int(t.best_path()[0]))
+        assert int(linked[p]) == wl
+        assert_tree_equal(b.tree(p), t.export(), f"reconnected[{p}]")
+        assert np.array_equal(b.best_path(p), t.best_path()) and b.planners()[p]["best_cost"] == t.planner().best_cost
+        n_ok += 1
+    assert n_ok >= P // 2 and n_split >= 4
