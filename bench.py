@@ -300,8 +300,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "plan_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src,
-                "note": "trees of resident planners are L1/L2/shared-memory resident, so DRAM traffic is far below "
-                        "the algorithmic bytes; the kernel is FP64-issue / latency bound (see profiles/)"}
+                "note": "algorithmic bytes (16 B per node visited by a scan + 12 B per parent-chain hop + 32 B per insert) over "
+                        "the kernel time; the scans are served from L2 through the TMA ring (DRAM traffic is `traffic`), "
+                        "the kernel is bound by per-warp instruction latency, not by HBM (profiles/)"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
