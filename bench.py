@@ -160,6 +160,16 @@ def cpu_baseline(w, budget_s):
                       f"{w['name']} on {cores} host threads, C port of the reference algorithm (oracle/rrt_oracle.c)"}
 
 
+def bench_config(w, P, world, args, capacity):
+    """The `config` object of the JSON line: identical for the B200 arm and the reference arm."""
+    return {"workload": f"{w['name']}: {w['mode']} x {P} planners per GPU ({P * world} total), "
+                        f"{len(w['obstacles'])} circular obstacles, {w['iter_num']} iterations each",
+            "planners_per_gpu": P, "iter_num": w["iter_num"],
+            "l2": f"per-step working set {P * capacity * 37 / 1e6:.0f} MB of tree state is re-initialised every step "
+                  "(larger than L2 for the default size; no explicit flush)",
+            "launch": args.launch, "near_cap": args.near_cap}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -182,8 +192,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{w['name']}: {w['mode']} planners, {len(w['obstacles'])} circular obstacles, "
-                                   f"{iters} of {w['iter_num']} iterations (bounded CPU sample)", "planners_per_step": count},
+            "config": bench_config(w, P, max(1, int(os.environ.get("WORLD_SIZE", "1"))), args,
+                                   (w["max_nodes"] + 2 + max(256, w["max_nodes"] // 4)) if w["mode"] == "fn" else w["iter_num"] + 2),
             "edge_checks_per_sec": edge_total / dt,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -315,11 +325,7 @@ def main():
         "metric": METRIC, "value": ext * rate,
         "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{w['name']}: {w['mode']} x {P} planners per GPU ({P * world} total), "
-                               f"{len(w['obstacles'])} circular obstacles, {w['iter_num']} iterations each",
-                   "planners_per_gpu": P, "iter_num": w["iter_num"], "l2": "per-step working set "
-                   f"{P * b.prm.capacity * 32 / 1e6:.0f} MB of tree state is re-initialised every step (larger than L2 "
-                   "for the default size; no explicit flush)", "launch": args.launch, "near_cap": args.near_cap},
+        "config": bench_config(w, P, world, args, b.prm.capacity),
         "edge_checks_per_sec": edges * rate,
         "edge_checks_ref_equiv_per_sec": edges_ref * rate,
         "circle_tests_per_sec": circles * rate,

@@ -86,3 +86,28 @@ def test_gather_records_world_size_2_gloo(tmp_path, all_inf):
     want = int(np.flatnonzero(costs == costs.min())[0])          # lowest global index on ties
     assert int(outs[0]["gidx"]) == want == 6                     # 100 - 6 is the minimum, first reached by planner 6 (rank 1)
     assert list(outs[0]["path"]) == list(np.arange(3 + want % 4) + 1000 * want)
+
+
+def test_workloads_are_deterministic_and_valid():
+    """Maps and problems are pure functions of (workload, planner index); starts and goals are outside inflated obstacles."""
+    import oracle as O
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    for name in ("c2", "c3", "c4"):
+        a, b = W.WORKLOADS[name](), W.WORKLOADS[name]()
+        assert a["obstacles"] == b["obstacles"] and len(a["obstacles"]) in (200, 500)
+        s, g, seeds, sids = W.planner_problems(a, 100, 6)
+        s2, g2, _, sids2 = W.planner_problems(b, 100, 6)
+        assert np.array_equal(s, s2) and np.array_equal(g, g2) and list(sids) == list(range(100, 106)) == list(sids2)
+        for p in range(6):
+            assert not O.is_occupied(s[p], a["obstacles"], a["node_radius"]) and not O.is_occupied(g[p], a["obstacles"], a["node_radius"])
+
+
+def test_bench_config_is_shared_by_both_arms():
+    import argparse, importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    args = argparse.Namespace(launch=0, near_cap=64)
+    c = bench.bench_config(W.c3(), 16384, 1, args, 5002)
+    assert c["workload"].startswith("c3: star x 16384 planners per GPU (16384 total), 500 circular obstacles, 5000 iterations")
+    assert bench.DEFAULT_PLANNERS["c3"] == 16384 and bench.METRIC == "rrt_star_tree_extensions_per_sec"
