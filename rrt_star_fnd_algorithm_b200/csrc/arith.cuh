@@ -47,10 +47,7 @@ struct Seg {
     double mk, kk;   // m*k, k*k (k**2)
     double a2, a4;   // 2*a, 4*a with a = 1 + m*m   (exact scalings)
     double lo, hi;   // min / max of the endpoint x (is_between, :632-633)
-    double inv2a;    // ~1 / (2a): only for the root pre-check below, never for a result
-    double e0;       // absolute slack of the pre-check: 1e-9 * (|lo| + |hi|)
     bool vertical;   // p2x == p1x (src/line.py:9)
-    bool pre;        // pre-check usable: finite, moderate slope
 };
 
 __device__ __forceinline__ Seg make_seg(double p1x, double p1y, double p2x, double p2y) {
@@ -66,9 +63,6 @@ __device__ __forceinline__ Seg make_seg(double p1x, double p1y, double p2x, doub
     s.a4 = dmul(4.0, a);
     s.lo = p1x < p2x ? p1x : p2x;
     s.hi = p1x < p2x ? p2x : p1x;
-    s.inv2a = 1.0 / s.a2;
-    s.e0 = 1e-9 * (fabs(s.lo) + fabs(s.hi)) + 1e-300;
-    s.pre = !s.vertical && fabs(s.m) <= 1048576.0;
     return s;
 }
 
@@ -80,21 +74,6 @@ __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double 
     const double c = dadd(dsub(K, dmul(dadd(oy, oy), s.k)), s.kk);              // :619
     const double delta = dsub(dmul(b, b), dmul(s.a4, c));                       // :620
     if (!(delta >= 0.0)) return false;                                          // :569 (NaN -> no hit as well)
-    // Pre-check (no effect on the result, DESIGN.md "Root pre-check"): the exact roots of the reference are within a
-    // few ulps of cx -+ w with cx = -b / 2a, w = sqrt(delta) / 2a. If both are provably <= lo, both >= hi, or they
-    // straddle [lo, hi] - each with a 1e-9 relative margin against the ~1e-16 rounding of either evaluation - neither can
-    // be strictly between lo and hi and the square root and the two divisions are skipped. Anything closer, and every
-    // actual hit, takes the reference's own arithmetic below. NaN / inf operands fail every comparison here.
-    if (s.pre) {
-        const double cx = -b * s.inv2a;
-        const double W = delta * s.inv2a * s.inv2a, Wl = W * (1.0 + 1e-9), Ws = W * (1.0 - 1e-9);
-        const double E = s.e0 + 1e-9 * fabs(cx);
-        const double A1 = (s.lo - cx) - E, A2 = (cx - s.hi) - E;              // distance of the centre outside the interval
-        if (A1 > 0.0 && Wl <= A1 * A1) return false;                           // both roots <= lo
-        if (A2 > 0.0 && Wl <= A2 * A2) return false;                           // both roots >= hi
-        const double B1 = (cx - s.lo) + E, B2 = (s.hi - cx) + E;
-        if ((B1 <= 0.0 || Ws >= B1 * B1) && (B2 <= 0.0 || Ws >= B2 * B2)) return false;   // x2 <= lo and x1 >= hi
-    }
     const double sq = dsqrt(delta);                                             // :602-603
     const double2 x = ddiv2(dadd(-b, sq), dsub(-b, sq), s.a2);                  // x1, x2 (:602-603)
     return (x.x > s.lo && x.x < s.hi) || (x.y > s.lo && x.y < s.hi);                // :576, :632-635

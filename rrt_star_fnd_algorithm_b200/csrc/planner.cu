@@ -209,9 +209,6 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
         for (int u = 0; u < 4; ++u) { const int i = base + 32 * u + lane; sl[u] = i < n_items ? list[i] : -1; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = sl[u] >= 0 ? XY[sl[u]] : nan2;
-    } else if (xs.n_stages == 0) {      // plain coalesced 16-byte loads, four in flight per lane
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; sl[u] = s; v[u] = s < n_items ? XY[s] : nan2; }
     } else {
         const double2* tile = stream_wait(xs, t);
 #pragma unroll
@@ -222,7 +219,10 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
 
 // WPB warps (= planners) per CTA; MINW = resident warps per SM the register allocation must allow (16 -> 128
 // registers, 24 -> 80, 32 -> 64): small batches get registers, large ones get occupancy.
-template <int WPB, int MINW, bool NG>
+// MODE >= 0 is a LEAN instance: that planner mode with choose-parent evaluated but not committed and no trace — the
+// configuration batches run in — so the other modes' code, the trace writes and the second near-set pass are not even
+// compiled in (the kernel's instruction footprint is what limits it, profiles/). MODE = -1 takes everything at run time.
+template <int WPB, int MINW, bool NG, int MODE>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     int32_t* FINISH = bt.finish + (size_t)p * prm.finish_cap;
     int32_t* BPATH = bt.best_path + (size_t)p * prm.path_cap;
     rrtfnd_planner_t* PL = bt.planners + p;
-    rrtfnd_trace_t* TRACE = bt.trace ? bt.trace + (size_t)p * prm.trace_cap : nullptr;
+    constexpr bool kLean = MODE >= 0;
+    const int mode = kLean ? MODE : prm.mode;
+    rrtfnd_trace_t* TRACE = (!kLean && bt.trace) ? bt.trace + (size_t)p * prm.trace_cap : nullptr;
 
     // per-warp shared memory
     const int n_stages = prm.reserved;                 // resolved by the host wrapper (2 or 4)
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     }
     // childless live nodes (forced_removal draws among them); kept incrementally afterwards
     int n_childless = 0;
-    if (prm.mode == RRTFND_MODE_FN) {
+    if (mode == RRTFND_MODE_FN) {
         for (int base = 0; base < n_slots; base += 32) {
             const int s = base + lane;
             n_childless += __popc(__ballot_sync(kFull, s < n_slots && NCHILD[s] == 0));
@@ -318,8 +320,8 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 
     const double r2 = dmul(prm.radius, prm.radius);
     const double goal_thresh = dmul(2.0, prm.goal_node_radius);
-    const bool eval_cp = (prm.flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
-    const bool commit_cp = (prm.flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) != 0;
+    const bool eval_cp = kLean || (prm.flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
+    const bool commit_cp = !kLean && (prm.flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) != 0;
     const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
 
     for (;;) {
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         }
         __syncwarp();
 
-        if (prm.mode == RRTFND_MODE_RRT) {
+        if (mode == RRTFND_MODE_RRT) {
             int L = 0; double cost = 0.0;
             if (lane == 0) {
                 NCHILD[near_slot] += 1;                                           // add_edge (:76)
@@ -705,7 +707,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 
         // ================================================================ F. forced_removal (:233-237, :800-819)
         int removed_id = -1;
-        if (prm.mode == RRTFND_MODE_FN && fn_count > prm.max_nodes) {                 // n_of_nodes > max_nodes (:233)
+        if (mode == RRTFND_MODE_FN && fn_count > prm.max_nodes) {                 // n_of_nodes > max_nodes (:233)
             const int leaf = best_leaf_slot;
             const int total = n_childless;
             int n_ok = total - (NCHILD[new_slot] == 0 ? 1 : 0);
@@ -767,7 +769,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 FINISH[n_finish] = new_slot;
                 int n = new_slot;                                                 // mark the ancestors of the new finish node
                 while (n >= 0 && !(NFLAG[n] & 1)) { NFLAG[n] |= 1; n = PARENT[n]; }
-                if (prm.mode == RRTFND_MODE_STAR) {                               // unconditional overwrite (:160-161)
+                if (mode == RRTFND_MODE_STAR) {                               // unconditional overwrite (:160-161)
                     n = new_slot;
                     while (n != root_slot && n >= 0) {
                         if (L < prm.path_cap) BPATH[L] = ID[n];
@@ -780,7 +782,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             __syncwarp();
             ++n_finish;
             solution_found = 1;
-            if (prm.mode == RRTFND_MODE_STAR) {
+            if (mode == RRTFND_MODE_STAR) {
                 best_len = __shfl_sync(kFull, L, 0); best_cost = __shfl_sync(kFull, cost, 0); best_leaf_slot = new_slot;
                 if (best_len > prm.path_cap) { status = RRTFND_ST_PATH_CAP; break; }
             }
@@ -863,11 +865,11 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int WPB, int MINW, bool NG = false>
+template <int WPB, int MINW, bool NG = false, int MODE = -1>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
     const size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
-    auto kern = plan_kernel<WPB, MINW, NG>;
+    auto kern = plan_kernel<WPB, MINW, NG, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     kern<<<(bt->n_planners + WPB - 1) / WPB, 32 * WPB, bytes, st>>>(*prm, *bt);
@@ -889,8 +891,7 @@ static PlanCfg choose_cfg(const rrtfnd_params_t& prm, int n_planners) {
     // measured on B200 (profiles/): trading registers for residency (80 / 64 registers) spills and halves throughput,
     // and a ring deeper than 2 tiles does not pay once a dozen warps share an SM
     if (c.minw != 16 && c.minw != 24 && c.minw != 32) c.minw = 16;
-    if (c.stages == 1) c.stages = 0;            // 1 = no ring: the scans use plain loads
-    else if (c.stages != 2 && c.stages != 4) c.stages = 2;
+    if (c.stages != 2 && c.stages != 4) c.stages = 2;
     return c;
 }
 
@@ -943,6 +944,11 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
             return RRTFND_E_BADARG;
         return launch_plan<1, 16, true>(&q, &b, (cudaStream_t)stream);
     }
+    // the configuration batches run in gets a lean kernel instance (one planner per CTA, 128 registers)
+    const bool lean = (q.flags & (RRTFND_FLAG_TRACE | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) == 0 && (q.flags & RRTFND_FLAG_EVAL_CHOOSE_PARENT) &&
+                      cfg.wpb == 1 && cfg.minw == 16;
+    if (lean && q.mode == RRTFND_MODE_STAR) return launch_plan<1, 16, false, RRTFND_MODE_STAR>(&q, &b, st);
+    if (lean && q.mode == RRTFND_MODE_FN) return launch_plan<1, 16, false, RRTFND_MODE_FN>(&q, &b, st);
     switch (cfg.wpb) {
         case 1: return launch_wpb<1>(&q, &b, cfg.minw, st);
         case 2: return launch_wpb<2>(&q, &b, cfg.minw, st);

@@ -1,4 +1,5 @@
 set -x
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 python scripts/perf_probe.py c3 16384 5000 1 0 64
 python scripts/perf_probe.py c2 4736 5000 1 0 64
-python scripts/perf_probe.py c3 16384 5000 1 $((1+16*1+256*16)) 64
+python scripts/perf_probe.py c3 2048 5000 1 0 64
