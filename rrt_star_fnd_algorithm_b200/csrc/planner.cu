@@ -199,7 +199,7 @@ static __device__ __noinline__ int ng_key_rank(const double2* XY, const int32_t*
 
 // One tile of 128 (slot, position) pairs for a scan body: from the TMA ring when scanning the whole tree, gathered
 // through a candidate list otherwise. Padding has slot -1 / position NaN, for which every predicate is false.
-template <bool NG>
+template <bool NG, bool RING>
 __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, const int32_t* list, int n_items, int t, int lane,
                                            double2 (&v)[4], int (&sl)[4]) {
     const int base = t * kTileNodes;
@@ -209,6 +209,9 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
         for (int u = 0; u < 4; ++u) { const int i = base + 32 * u + lane; sl[u] = i < n_items ? list[i] : -1; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = sl[u] >= 0 ? XY[sl[u]] : nan2;
+    } else if (!RING) {                 // plain coalesced 16-byte loads, four in flight per lane
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int s = base + 32 * u + lane; sl[u] = s; v[u] = s < n_items ? XY[s] : nan2; }
     } else {
         const double2* tile = stream_wait(xs, t);
 #pragma unroll
@@ -222,7 +225,7 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
 // MODE >= 0 is a LEAN instance: that planner mode with choose-parent evaluated but not committed and no trace — the
 // configuration batches run in — so the other modes' code, the trace writes and the second near-set pass are not even
 // compiled in (the kernel's instruction footprint is what limits it, profiles/). MODE = -1 takes everything at run time.
-template <int WPB, int MINW, bool NG, int MODE>
+template <int WPB, int MINW, bool NG, int MODE, bool RING>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -374,10 +377,10 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 }
                 bd = CUDART_INF; bs = kIntMax;
                 const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
-                if (!list) stream_begin(xs, XY, n_slots, lane);
+                if (RING && !list) stream_begin(xs, XY, n_slots, lane);
                 for (int t = 0; t < n_tiles; ++t) {
                     double2 v[4]; int sl[4];
-                    fetch_tile<NG>(xs, XY, list, n_items, t, lane, v, sl);
+                    fetch_tile<NG, RING>(xs, XY, list, n_items, t, lane, v, sl);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const double d = dist2(v[u].x, v[u].y, qx, qy);                 // NaN for tombstones / padding
@@ -424,10 +427,10 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     bool beyond = NG && list && !covers_all;
                     int count = 0;
                     const int n_tiles = (n_items + kTileNodes - 1) / kTileNodes;
-                    if (!list) stream_begin(xs, XY, n_slots, lane);
+                    if (RING && !list) stream_begin(xs, XY, n_slots, lane);
                     for (int t = 0; t < n_tiles; ++t) {
                         double2 v[4]; int sl[4];
-                        fetch_tile<NG>(xs, XY, list, n_items, t, lane, v, sl);
+                        fetch_tile<NG, RING>(xs, XY, list, n_items, t, lane, v, sl);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int s = sl[u];
@@ -567,10 +570,10 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             int count = 0;
             k_total = 0;
             const int n_tiles = (n_near_items + kTileNodes - 1) / kTileNodes;
-            if (!nlist) stream_begin(xs, XY, n_slots, lane);
+            if (RING && !nlist) stream_begin(xs, XY, n_slots, lane);
             for (int t = 0; t < n_tiles; ++t) {
                 double2 v[4]; int sl[4];
-                fetch_tile<NG>(xs, XY, nlist, n_near_items, t, lane, v, sl);
+                fetch_tile<NG, RING>(xs, XY, nlist, n_near_items, t, lane, v, sl);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int s = sl[u];
@@ -865,11 +868,11 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int WPB, int MINW, bool NG = false, int MODE = -1>
+template <int WPB, int MINW, bool NG = false, int MODE = -1, bool RING = true>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
     const size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
-    auto kern = plan_kernel<WPB, MINW, NG, MODE>;
+    auto kern = plan_kernel<WPB, MINW, NG, MODE, RING>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     kern<<<(bt->n_planners + WPB - 1) / WPB, 32 * WPB, bytes, st>>>(*prm, *bt);
@@ -947,8 +950,15 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     // the configuration batches run in gets a lean kernel instance (one planner per CTA, 128 registers)
     const bool lean = (q.flags & (RRTFND_FLAG_TRACE | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) == 0 && (q.flags & RRTFND_FLAG_EVAL_CHOOSE_PARENT) &&
                       cfg.wpb == 1 && cfg.minw == 16;
-    if (lean && q.mode == RRTFND_MODE_STAR) return launch_plan<1, 16, false, RRTFND_MODE_STAR>(&q, &b, st);
-    if (lean && q.mode == RRTFND_MODE_FN) return launch_plan<1, 16, false, RRTFND_MODE_FN>(&q, &b, st);
+    // Scans of large trees stream from L2 / HBM and are faster through the TMA ring (c3, 5,002 slots: +6 %); trees of a
+    // thousand nodes stay L1 / L2 resident and are faster with plain loads (c2, 1,508 slots: +7 %). The `stages` field
+    // of the launch word overrides: 1 = plain loads, 2 / 4 = ring.
+    const int stages_req = (prm->reserved >> 4) & 15;
+    const bool ring = stages_req == 1 ? false : (stages_req == 2 || stages_req == 4) ? true : prm->capacity > 2048;
+    if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<1, 16, false, RRTFND_MODE_STAR, true>(&q, &b, st)
+                                                        : launch_plan<1, 16, false, RRTFND_MODE_STAR, false>(&q, &b, st);
+    if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<1, 16, false, RRTFND_MODE_FN, true>(&q, &b, st)
+                                                      : launch_plan<1, 16, false, RRTFND_MODE_FN, false>(&q, &b, st);
     switch (cfg.wpb) {
         case 1: return launch_wpb<1>(&q, &b, cfg.minw, st);
         case 2: return launch_wpb<2>(&q, &b, cfg.minw, st);
