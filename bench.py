@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--planners", type=int, default=0, help="planners per GPU (0 = workload default)")
     ap.add_argument("--iters", type=int, default=0, help="iterations per planner (0 = workload default)")
     ap.add_argument("--launch", type=int, default=0)
@@ -55,7 +55,7 @@ def parse_args():
 # default planners per GPU. c3 at N=1 is BASELINE.json's config 3 as written (16,384 planners on one B200, 3 GB of tree
 # state); with weak scaling every further GPU gets a batch of the same size. 16,384 planners are ~7 waves of resident
 # warps per SM, which also evens out the planner-to-planner variance that leaves SMs idle at the end of a 1-wave launch.
-DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 16384, "c4": 1}
+DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 16384, "c4": 1, "c5": 4096}
 
 
 class ClockSampler:
@@ -135,6 +135,38 @@ def cpu_port_run(w, first, count, iters, threads):
     return out["iter"].sum() / dt, out["n_edge_checks"].sum() / dt, dt, out
 
 
+def cpu_c5_run(w, first, count, threads):
+    """Config 5 on the CPU: plan `count` planners with the C port, then step each through the replanning ticks
+    (oracle/fnd_loop.py). Returns (extensions/s, moves/s, seconds, extensions)."""
+    import oracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.fnd_loop import OracleReplanner
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    from rrt_star_fnd_algorithm_b200.fnd_loop import moved_obstacles
+    s, g, seeds, sids = W.planner_problems(w, first, count)
+    T = w["ticks"]
+    tables = [moved_obstacles(w["obstacles"], w["velocity"], k) for k in range(1, T + 1)]
+
+    def one(p):
+        prm = oracle_params(w, 0)
+        t = O.OracleTree(s[p], w["iter_num"] + 2 + T * w["regrow_iters"])
+        t.run(prm, w["obstacles"], g[p], seed=int(seeds[p]), stream_id=int(sids[p]))
+        ext, moves = t.planner().iter, 0
+        r = OracleReplanner(t, prm, g[p], seeds[p], sids[p], w["node_radius"], w["reconnect_radius"], w["regrow_iters"])
+        for ob in tables:
+            o = r.tick(ob)
+            ext += sum(o["regrow_iters"]); moves += o["current"] >= 0
+        t.close()
+        return ext, moves
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(one, range(count)))
+    dt = time.perf_counter() - t0
+    ext, moves = sum(r[0] for r in res), sum(r[1] for r in res)
+    return ext / dt, moves / dt, dt, ext
+
+
 def size_cpu_sample(w, budget_s, cores):
     """(planners, iterations) of a CPU sample that takes roughly budget_s on `cores` threads."""
     cpu_port_run(w, 0, 1, 20, 1)                          # load / build the checker outside the calibration
@@ -152,8 +184,19 @@ def size_cpu_sample(w, budget_s, cores):
 def cpu_baseline(w, budget_s):
     """Bounded sample of the same workload on all host cores (C port of the reference algorithm)."""
     cores = len(os.sched_getaffinity(0))
+    if w["name"] == "c5":
+        _, _, dt, _ = cpu_c5_run(w, 0, cores, cores)
+        count = int(min(4096, max(cores, cores * (budget_s // max(dt, 1e-3)))))
+        ext, moves, dt, _ = cpu_c5_run(w, 0, count, cores)
+        return {"value": ext, "unit": UNIT, "cores": cores, "kind": "port", "replan_moves_per_sec": moves, "seconds": dt,
+                "sample": f"{count} planners (global index 0..{count - 1}) of workload c5, full length ({w['iter_num']} iterations + "
+                          f"{w['ticks']} replanning ticks) on {cores} host threads, C port of the reference algorithm + "
+                          "oracle/fnd_loop.py"}
     count, iters = size_cpu_sample(w, budget_s, cores)
     ext, edge, dt, _ = cpu_port_run(w, 0, count, iters, cores)
+    if dt < 0.4 * budget_s:        # the calibration over-estimated: scale the sample up to the budget
+        count = int(min(16384, count * max(1.0, 0.8 * budget_s / max(dt, 1e-3))))
+        ext, edge, dt, _ = cpu_port_run(w, 0, count, iters, cores)
     return {"value": ext, "unit": UNIT, "cores": cores, "kind": "port",
             "edge_checks_per_sec": edge, "seconds": dt,
             "sample": f"{count} planners (global index 0..{count - 1}) x {iters} of {w['iter_num']} iterations of workload "
@@ -163,7 +206,8 @@ def cpu_baseline(w, budget_s):
 def bench_config(w, P, world, args, capacity):
     """The `config` object of the JSON line: identical for the B200 arm and the reference arm."""
     return {"workload": f"{w['name']}: {w['mode']} x {P} planners per GPU ({P * world} total), "
-                        f"{len(w['obstacles'])} circular obstacles, {w['iter_num']} iterations each",
+                        f"{len(w['obstacles'])} circular obstacles, {w['iter_num']} iterations each"
+                        + (f", then {w['ticks']} replanning ticks with moving obstacles" if "ticks" in w else ""),
             "planners_per_gpu": P, "iter_num": w["iter_num"],
             "l2": f"per-step working set {P * capacity * 37 / 1e6:.0f} MB of tree state is re-initialised every step "
                   "(larger than L2 for the default size; no explicit flush)",
@@ -177,14 +221,30 @@ def run_reference_arm(args):
     w, P = load_workload(args)
     cores = len(os.sched_getaffinity(0))
     # bounded sample per step, sized so that warmup + steps stay within a few minutes
-    count, iters = size_cpu_sample(w, 150.0 / max(1, args.steps + args.warmup), cores)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    if w["name"] == "c5":
+        _, _, dt1, _ = cpu_c5_run(w, 0, cores, cores)
+        count, iters = int(min(4096, max(cores, cores * (budget // max(dt1, 1e-3))))), w["iter_num"]
+
+        def run_once():
+            _, _, _, ext = cpu_c5_run(w, 0, count, cores)
+            return int(ext), 0
+    else:
+        count, iters = size_cpu_sample(w, budget, cores)
+        _, _, dt1, _ = cpu_port_run(w, 0, count, iters, cores)
+        if dt1 < 0.4 * budget:     # the calibration over-estimated: scale the sample up to the budget
+            count = int(min(16384, count * max(1.0, 0.8 * budget / max(dt1, 1e-3))))
+
+        def run_once():
+            _, _, _, out = cpu_port_run(w, 0, count, iters, cores)
+            return int(out["iter"].sum()), int(out["n_edge_checks"].sum())
     for _ in range(args.warmup):
-        cpu_port_run(w, 0, count, iters, cores)
+        run_once()
     t0 = time.perf_counter()
     ext_total, edge_total = 0, 0
     for _ in range(args.steps):
-        _, _, _, out = cpu_port_run(w, 0, count, iters, cores)
-        ext_total += int(out["iter"].sum()); edge_total += int(out["n_edge_checks"].sum())
+        a, e = run_once()
+        ext_total += a; edge_total += e
     dt = time.perf_counter() - t0
     val = ext_total / dt
     sample = (f"{count} planners x {iters} of {w['iter_num']} iterations of workload {w['name']} per step on {cores} host "
@@ -202,6 +262,9 @@ def run_reference_arm(args):
 
 def main():
     args = parse_args()
+    if os.environ.get("BENCH_DUMP_AFTER"):      # debugging aid: print every thread's Python stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_DUMP_AFTER"]), exit=True)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -237,13 +300,33 @@ def main():
         torch.cuda.synchronize()
 
     kern_ms = []
+    is_c5 = w["name"] == "c5"
+    tight = b.prm.capacity
+    replan = {"ms": [], "stats": None}
+    if is_c5:
+        from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner, moved_obstacles
+        tables = [moved_obstacles(w["obstacles"], w["velocity"], k) for k in range(1, w["ticks"] + 1)]
 
     def step(timed):
+        if is_c5:                         # back to the planning state: tight capacity, obstacles where they started
+            b.restore_problems()
+            b.reallocate(tight)
+            b.set_obstacles(w["obstacles"])
         b.reset()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         b.run()
         e1.record()
+        if is_c5:                         # replanning ticks: robot steps, obstacles move, invalidate, reconnect / regrow
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            b.grow_capacity(tight + w["ticks"] * w["regrow_iters"])
+            loop = FNDReplanner(b, w["reconnect_radius"], w["regrow_iters"])
+            for ob in tables:
+                loop.tick(ob)
+            r1.record()
+            if timed:
+                replan["ms"].append((r0, r1)); replan["stats"] = dict(loop.stats)
         if world > 1:
             gather_results(b, dist.group.WORLD)     # all_gather of the records + broadcast of the best path
         if timed:
@@ -270,6 +353,8 @@ def main():
 
     pl = b.planners()
     b.check_status()
+    if is_c5:                             # extensions of a step = the planning run + what regrow() added
+        pl["iter"][0] += replan["stats"]["regrow_extensions"]
     stats = torch.tensor([pl["iter"].sum(), pl["n_edge_checks"].sum(), pl["n_edge_checks_ref"].sum(),
                           pl["n_circle_tests"].sum(), pl["attempts"].sum(), pl["n_scan_nodes"].sum(),
                           pl["n_chain_hops"].sum(), pl["solution_found"].sum()], dtype=torch.float64, device=dev)
@@ -283,7 +368,7 @@ def main():
     # part (its own planners, collectives inside), so this must come before the non-zero ranks leave
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, w, P, first, b, dev)
+        e2e = run_e2e_c5(args, w, P, first, dev, kw) if is_c5 else run_e2e(args, w, P, first, b, dev)
 
     if rank != 0:
         if world > 1:
@@ -333,6 +418,13 @@ def main():
         "solved_planners": solved, "gpu_launches": 2 * args.steps,
         "roofline": roofline, "clocks": clk, "parity_spot_check": parity,
     }
+    if is_c5:
+        st, rms = replan["stats"], float(np.mean([a.elapsed_time(c) for a, c in replan["ms"]]))
+        line["replanning"] = dict(st, ticks=w["ticks"], ms_per_step=rms, plan_ms_per_step=k_ms,
+                                  moves_per_sec=st["moves"] / (rms / 1e3), note="rank 0; one step = RRT*-FN planning "
+                                  "(plan_kernel) + `ticks` replanning ticks (select_branch, valid_path, reconnect, regrow "
+                                  "kernels; obstacle tables and per-planner ids cross the host every tick)")
+        line["gpu_launches"] = int(args.steps * (2 + w["ticks"] * 4))
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
@@ -394,6 +486,50 @@ def run_e2e(args, w, P, first, b, dev):
             "api": "rrtfnd_plan_host (C ABI, pinned host buffers; whole trees + planner records + best paths copied back)"}
 
 
+def run_e2e_c5(args, w, P, first, dev, kw):
+    """Config 5 end to end: host problem arrays -> a fresh device batch -> planning -> replanning ticks -> whole trees,
+    records and paths back on the host; wall clock around all of it."""
+    import torch
+    import torch.distributed as dist
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
+    from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner, moved_obstacles
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    starts, goals, seeds, sids = W.planner_problems(w, first, P)
+    tables = [moved_obstacles(w["obstacles"], w["velocity"], k) for k in range(1, w["ticks"] + 1)]
+    sizes = {}
+
+    def call():
+        b = PlannerBatch(w["mode"], starts=starts, goals=goals, seeds=seeds, stream_ids=sids, device=dev, **kw).run()
+        b.grow_capacity(b.prm.capacity + w["ticks"] * w["regrow_iters"])
+        loop = FNDReplanner(b, w["reconnect_radius"], w["regrow_iters"])
+        for ob in tables:
+            loop.tick(ob)
+        out = [t.cpu() for t in (b.planners_t, b.xy, b.ecost, b.parent, b.nchild, b.id, b.best_path_t)]
+        sizes["d2h"] = sum(t.numel() * t.element_size() for t in out)
+        sizes["h2d"] = starts.nbytes + goals.nbytes + seeds.nbytes + sids.nbytes + (1 + len(tables)) * len(w["obstacles"]) * 32
+        return float(b.planners()["iter"].sum() + loop.stats["regrow_extensions"])
+
+    call()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    ext = 0.0
+    for _ in range(n):
+        ext = call()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt, ext], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(tt)
+        dt, ext = float(mx[0].item()), float(tt[1].item())
+    return {"value": ext * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(sizes["h2d"]), "d2h_bytes_per_step": int(sizes["d2h"]),
+            "steps": n, "ms_per_step": dt / n * 1e3,
+            "api": "PlannerBatch + FNDReplanner (Python host over the C ABI): problems from host arrays, obstacle tables per tick, "
+                   "whole trees + planner records + best paths copied back"}
+
+
 def spot_check(w, first, b):
     """Planner 0 of this rank vs the CPU oracle on the same Philox stream (bit-exact tree comparison)."""
     try:
@@ -401,8 +537,15 @@ def spot_check(w, first, b):
         from rrt_star_fnd_algorithm_b200 import _structs as S
         from rrt_star_fnd_algorithm_b200 import workloads as W
         s, g, seeds, sids = W.planner_problems(w, first, 1)
-        t = O.OracleTree(s[0], w["iter_num"] + 2)
+        t = O.OracleTree(s[0], w["iter_num"] + 2 + w.get("ticks", 0) * w.get("regrow_iters", 0))
         t.run(oracle_params(w, 0), w["obstacles"], g[0], seed=int(seeds[0]), stream_id=int(sids[0]))
+        if w["name"] == "c5":
+            from oracle.fnd_loop import OracleReplanner
+            from rrt_star_fnd_algorithm_b200.fnd_loop import moved_obstacles
+            r = OracleReplanner(t, oracle_params(w, 0), g[0], seeds[0], sids[0], w["node_radius"], w["reconnect_radius"],
+                                w["regrow_iters"])
+            for k in range(1, w["ticks"] + 1):
+                r.tick(moved_obstacles(w["obstacles"], w["velocity"], k))
         got, want = b.tree(0), t.export()
         ok = all(np.array_equal(got[k], want[k]) for k in want)
         ok = ok and float(b.planners()[0]["best_cost"]) == t.planner().best_cost

@@ -56,6 +56,11 @@ extern "C" {
 #define RRTFND_ST_NO_CHILDLESS (-6)/* forced_removal would spin forever (src/algorithm.py:815-816) */
 #define RRTFND_ST_STREAM_EXHAUSTED (-7) /* word buffer ran out inside forced_removal's redraw loop */
 
+/* rrtfnd_fnd_regrow gives up with RRTFND_ST_ATTEMPT_CAP after this many attempts per allowed extension
+ * (max_iter * RRTFND_REGROW_ATTEMPTS_PER_ITER in total): the reference's loop (src/algorithm.py:490-495) only counts
+ * successful extensions and spins forever when no sample can be connected to the root tree (root boxed in or gone). */
+#define RRTFND_REGROW_ATTEMPTS_PER_ITER 32
+
 /* library errors (negative return values) */
 #define RRTFND_E_BADARG (-100)
 #define RRTFND_E_NOGPU (-101)
@@ -276,7 +281,9 @@ int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch
  * plain extensions of the root tree from the planner's word stream (planner cursor), each followed by an attempt to hang
  * the separate tree - re-rooted at the first of its nodes, in ascending id, that the new node sees closer than
  * step_length - under the new node. Uses the culling grid of the current obstacle table. out_reconnected[p] = 1 / 0,
- * or a negative status; out_iters[p] (may be NULL) = extensions made. On success the stored best path / cost become
+ * RRTFND_ST_ATTEMPT_CAP (3) after max_iter * RRTFND_REGROW_ATTEMPTS_PER_ITER attempts, RRTFND_E_BADARG for a planner
+ * whose separate_root_id is not a live node (-1 = skip this planner), or a negative status; out_iters[p] (may be NULL) =
+ * extensions made. On success the stored best path / cost become
  * find_path(path[0], root). */
 int rrtfnd_fnd_regrow(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root_id,
                       int32_t max_iter, int32_t* out_reconnected, int32_t* out_iters, void* stream);

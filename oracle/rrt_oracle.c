@@ -489,7 +489,9 @@ int orc_fnd_regrow(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst
     rng.mode = prm->stream_mode; rng.words = words; rng.n_words = n_words; rng.seed = seed; rng.stream = stream_id;
     rng.cursor = t->cursor;
     int iter = 0, reconnected = 0, status = 0;
+    const int64_t attempt_cap = t->attempts + (int64_t)max_iter * RRTFND_REGROW_ATTEMPTS_PER_ITER;
     while (iter < max_iter && !reconnected) {
+        if (t->attempts >= attempt_cap) { status = RRTFND_ST_ATTEMPT_CAP; break; }   /* the reference would spin forever here */
         if (rng.mode == RRTFND_STREAM_WORDS && (int64_t)rng.cursor + ORC_RESERVE_WORDS > n_words) { status = -RRTFND_ST_NEED_WORDS - 100; break; }
         if (t->last_id + 1 >= t->cap) { status = RRTFND_ST_CAPACITY; break; }
         ++t->attempts;

@@ -106,6 +106,7 @@ class PlannerBatch:
             pl["seed"] = np.asarray(seeds if seeds is not None else np.arange(P), dtype=np.uint64)
             pl["stream_id"] = np.asarray(stream_ids if stream_ids is not None else np.zeros(P), dtype=np.uint64)
         self.planners_t = torch.from_numpy(pl.view(np.uint8).reshape(P, PLANNER_BYTES).copy()).to(dev)
+        self._problems_t = self.planners_t.clone()      # start / goal / stream keys as given (select_branch moves `start`)
         Cn = prm.capacity
         self.xy = torch.empty((P, Cn, 2), dtype=torch.float64, device=dev)
         self.ecost = torch.empty((P, Cn), dtype=torch.float64, device=dev)
@@ -122,6 +123,7 @@ class PlannerBatch:
         if grid and len(self.obst_host):
             pts = np.concatenate([starts, goals, np.asarray(xy_range, dtype=np.float64).T])
             bounds = (pts[:, 0].min(), pts[:, 0].max(), pts[:, 1].min(), pts[:, 1].max())
+            self._bounds = bounds
             g, arrs = build_obstacle_grid(self.obst_host[:, :3], prm.node_radius, bounds, grid_cell)
             if arrs is not None:
                 self._grid_t = [torch.from_numpy(a).to(dev) for a in arrs]
@@ -146,6 +148,7 @@ class PlannerBatch:
             prm.flags |= FLAG_NODE_GRID
         self.trace_t = torch.zeros((P, max(prm.trace_cap, 1) * TRACE_BYTES), dtype=torch.uint8, device=dev) if trace else None
         self._initialised = False
+        self._loaded = False     # load_tree() may bring coordinates from outside the box of xy_range / starts / goals
         smem = _abi.lib.rrtfnd_plan_smem_bytes(C.byref(prm))
         if smem < 0:
             raise _abi.LibraryError(f"planner does not fit in shared memory: {_abi.status_string(smem)}")
@@ -185,6 +188,7 @@ class PlannerBatch:
             raise ValueError("load_tree is not available with the node grid (it is filled by inserts only)")
         if not self._initialised:
             self.reset()
+        self._loaded = True
         ids = np.asarray(ids, dtype=np.int32)
         n = len(ids)
         if n > self.prm.capacity - 1:
@@ -205,6 +209,38 @@ class PlannerBatch:
         pl["n_slots"], pl["n_live"], pl["last_id"], pl["root_slot"] = n, n, int(last_id), slot_of[int(root_id)]
         self.planners_t[p] = torch.from_numpy(pl.view(np.uint8)).to(dev)
 
+    def grow_capacity(self, capacity: int):
+        """Re-allocate the per-node arrays with `capacity` slots per planner, keeping every tree (slot numbers are
+        planner-local, so nothing else changes). The replanning loop uses it to make room for regrow() after an RRT*-FN
+        run whose own capacity is kept tight (its scans cover the slots in use, tombstones included)."""
+        old, capacity = int(self.prm.capacity), int(capacity)
+        if capacity <= old:
+            return
+        if self.prm.flags & FLAG_NODE_GRID:
+            raise ValueError("grow_capacity is not available with the node grid")
+        for name in ("xy", "ecost", "parent", "nchild", "id", "nflags"):
+            t = getattr(self, name)
+            new = torch.zeros((self.P, capacity) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+            new[:, :old] = t
+            setattr(self, name, new)
+        self.prm.capacity = capacity
+
+    def restore_problems(self):
+        """Planner records back to the problems given at construction (select_branch re-roots a planner at the robot's
+        position, i.e. overwrites its `start`); reset() follows."""
+        self.planners_t.copy_(self._problems_t)
+        self._initialised = False
+
+    def reallocate(self, capacity: int):
+        """Fresh per-node arrays with `capacity` slots per planner; every tree is dropped (reset() follows)."""
+        if self.prm.flags & FLAG_NODE_GRID:
+            raise ValueError("reallocate is not available with the node grid")
+        for name in ("xy", "ecost", "parent", "nchild", "id", "nflags"):
+            t = getattr(self, name)
+            setattr(self, name, torch.zeros((self.P, int(capacity)) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device))
+        self.prm.capacity = int(capacity)
+        self._initialised = False
+
     # ------------------------------------------------------------------ FND tree surgery (src/algorithm.py:294-434)
     def _ids_tensor(self, ids):
         a = np.asarray(ids, dtype=np.int32).reshape(-1)
@@ -212,21 +248,27 @@ class PlannerBatch:
         return torch.from_numpy(a.copy()).to(self.device)
 
     def set_obstacles(self, obstacles, grid=True, grid_cell=0.0):
-        """Replace the obstacle table (a moved / extended map) and rebuild the culling grid."""
+        """Replace the obstacle table (a moved / extended map) and rebuild the culling grid.
+
+        The grid's box must bound every node: trees grown by the planners stay inside the box of xy_range, starts and
+        goals (a steered point lies between a node and a sample), so that box is reused; only after load_tree() are the
+        node coordinates themselves read back to bound them."""
         self.obst_host = obstacle_table(obstacles)
         self.prm.n_obst = len(self.obst_host)
         self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(self.device)
         self.grid, self._grid_t = ObstGrid(), None
         if grid and len(self.obst_host):
-            pl = self.planners()
-            pts = np.concatenate([np.column_stack([pl["start_x"], pl["start_y"]]), np.column_stack([pl["goal_x"], pl["goal_y"]]),
-                                  np.array([[self.prm.x_lo, self.prm.y_lo], [self.prm.x_hi, self.prm.y_hi]])])
-            n = pl["n_slots"]
-            xy = self.xy.cpu().numpy()
-            live = [xy[p, :int(n[p])] for p in range(self.P)]
-            allxy = np.concatenate(live + [pts])
-            allxy = allxy[~np.isnan(allxy).any(axis=1)]
-            bounds = (allxy[:, 0].min(), allxy[:, 0].max(), allxy[:, 1].min(), allxy[:, 1].max())
+            bounds = getattr(self, "_bounds", None)
+            if bounds is None or self._loaded:
+                pl = self.planners()
+                pts = np.concatenate([np.column_stack([pl["start_x"], pl["start_y"]]), np.column_stack([pl["goal_x"], pl["goal_y"]]),
+                                      np.array([[self.prm.x_lo, self.prm.y_lo], [self.prm.x_hi, self.prm.y_hi]])])
+                n = pl["n_slots"]
+                xy = self.xy.cpu().numpy()
+                live = [xy[p, :int(n[p])] for p in range(self.P)]
+                allxy = np.concatenate(live + [pts])
+                allxy = allxy[~np.isnan(allxy).any(axis=1)]
+                bounds = (allxy[:, 0].min(), allxy[:, 0].max(), allxy[:, 1].min(), allxy[:, 1].max())
             g, arrs = build_obstacle_grid(self.obst_host[:, :3], self.prm.node_radius, bounds, grid_cell)
             if arrs is not None:
                 self._grid_t = [torch.from_numpy(a).to(self.device) for a in arrs]

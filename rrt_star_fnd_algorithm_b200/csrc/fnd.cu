@@ -91,12 +91,22 @@ __global__ void __launch_bounds__(32 * kFndWarps) select_branch_kernel(const rrt
     if (cur < 0 || idx < 0) status = -1;                                     // ValueError in the reference
     else if (v.PARENT[cur] < 0) status = -2;                                 // G.children[None]: KeyError in the reference
     if (status) { if (lane == 0 && out_status) out_status[p] = status; return; }
-    // everything outside the subtree of `current` goes (stranded path nodes and what hangs off them, :315-323)
+    // remove_children(stranded node) for every path node on the root side of `current`, then the stranded nodes themselves
+    // (:315-323): a node goes iff its parent chain meets a stranded path node before it meets `current`. Trees that hang
+    // from neither (split off by an earlier valid_path and never mended) are not touched by the reference, nor here.
+    for (int s = lane; s < n_slots; s += 32) {
+        const int id = v.ID[s];
+        uint8_t f = v.NFLAG[s] & (uint8_t)~(kKeep | kOnPath);
+        if (id >= 0)
+            for (int i = idx + 1; i < best_len; ++i) if (v.BPATH[i] == id) { f |= kOnPath; break; }
+        v.NFLAG[s] = f;
+    }
+    __syncwarp();
     for (int s = lane; s < n_slots; s += 32) {
         if (v.ID[s] < 0) continue;
         int n = s;
-        while (n >= 0 && n != cur) n = v.PARENT[n];
-        v.NFLAG[s] = (uint8_t)((v.NFLAG[s] & ~kKeep) | (n == cur ? kKeep : 0));
+        while (n >= 0 && n != cur && !(v.NFLAG[n] & kOnPath)) n = v.PARENT[n];
+        if (n < 0 || n == cur) v.NFLAG[s] |= kKeep;
     }
     __syncwarp();
     int n_del = 0;
@@ -127,6 +137,10 @@ __global__ void __launch_bounds__(32 * kFndWarps) valid_path_kernel(const rrtfnd
     extern __shared__ int32_t fnd_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, p = blockIdx.x * kFndWarps + wib;
     if (p >= bt.n_planners) return;
+    if (previous_root_id[p] < 0) {                                           // negative id = leave this planner alone
+        if (lane == 0) { out_sep_id[p] = -1; if (out_index_error) out_index_error[p] = 0; }
+        return;
+    }
     int32_t* pslot = fnd_smem + (size_t)wib * prm.path_cap;                  // slot of path node i, -1 if it is gone
     const PlannerView v = view_of(prm, bt, p);
     const int n_slots = v.PL->n_slots, L = min(v.PL->best_len, prm.path_cap), M = prm.n_obst;
@@ -280,7 +294,9 @@ __global__ void __launch_bounds__(32 * kFndWarps) regrow_kernel(const __grid_con
     const Obst ob = make_obst(bt.obst, prm.n_obst, &bt.grid);
     long long tests = 0;
     bool reconnected = false;
+    const long long attempt_cap = attempts + (long long)max_iter * RRTFND_REGROW_ATTEMPTS_PER_ITER;
     while (iter < max_iter && !reconnected) {
+        if (attempts >= attempt_cap) { result = RRTFND_ST_ATTEMPT_CAP; break; }   // the reference would spin forever here
         if (prm.stream_mode == RRTFND_STREAM_WORDS && (long long)rng.cursor + kReserveWordsFnd > prm.words_per_planner) { result = -RRTFND_ST_NEED_WORDS - 100; break; }
         if (n_slots >= prm.capacity) { result = RRTFND_ST_CAPACITY; break; }
         ++attempts;
@@ -291,27 +307,43 @@ __global__ void __launch_bounds__(32 * kFndWarps) regrow_kernel(const __grid_con
             qy = dadd(prm.y_lo, dmul(dsub(prm.y_hi, prm.y_lo), next_random(rng)));
         }
         if (point_occupied_warp(ob, qx, qy, prm.node_radius, lane, tests)) continue;          // :493
-        // nearest_node: an identical vertex is returned as is and rejected at :495; otherwise the closest (calc_distance,
-        // lowest id on ties) among the nodes outside the separate tree whose Line(node, sample) is free
+        // nearest_node (:702-728): an identical vertex is returned as is and rejected at :495; otherwise the closest
+        // (calc_distance, lowest id on ties) among the nodes outside the separate tree whose Line(node, sample) is free.
+        // The reference tests the visibility of EVERY node; the same (distance, id) minimum is found here by testing nodes
+        // in ascending key order, 32 at a time: each lane proposes the nearest untested node of its own stride that still
+        // beats the best visible node found so far, all lanes test their proposals at once, repeat until none is left.
         bool exact = false;
-        double bd = CUDART_INF; int bs = 0x7fffffff;
         for (int s = lane; s < n_slots; s += 32) {
             if (v.ID[s] < 0) continue;
             const double2 c = v.XY[s];
             exact |= (c.x == qx && c.y == qy);
-            if (v.NFLAG[s] & kSeparate) continue;
-            if (seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, qx, qy, 0, 1) & 1) continue;
-            const double d = dist_fma(c.x, c.y, qx, qy);
-            if (d < bd) { bd = d; bs = s; }
         }
-        __syncwarp();
         if (__any_sync(kFull, exact)) continue;
-        {   // (value, slot) argmin over the warp
+        double bd = CUDART_INF; int bs = 0x7fffffff;                          // best visible so far (warp-uniform)
+        double ld = -1.0; int ls = -1;                                        // this lane's last tested key
+        for (;;) {
+            double cd = CUDART_INF; int cs = 0x7fffffff;
+            for (int s = lane; s < n_slots; s += 32) {
+                if (v.ID[s] < 0 || (v.NFLAG[s] & kSeparate)) continue;
+                const double2 c = v.XY[s];
+                const double d = dist_fma(c.x, c.y, qx, qy);
+                if (key_less(ld, ls, d, s) && key_less(d, s, cd, cs)) { cd = d; cs = s; }
+            }
+            const bool have = cs != 0x7fffffff && key_less(cd, cs, bd, bs);
+            if (!__any_sync(kFull, have)) break;
+            double pd = CUDART_INF; int ps = 0x7fffffff;
+            if (have) {
+                const double2 c = v.XY[cs];
+                ld = cd; ls = cs;
+                if (!(seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, qx, qy, 0, 1) & 1)) { pd = cd; ps = cs; }
+            }
+            __syncwarp();
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                const double od = __shfl_xor_sync(kFull, bd, off); const int os = __shfl_xor_sync(kFull, bs, off);
-                if (key_less(od, os, bd, bs)) { bd = od; bs = os; }
+                const double od = __shfl_xor_sync(kFull, pd, off); const int os = __shfl_xor_sync(kFull, ps, off);
+                if (key_less(od, os, pd, ps)) { pd = od; ps = os; }
             }
+            if (key_less(pd, ps, bd, bs)) { bd = pd; bs = ps; }
         }
         if (bs == 0x7fffffff) continue;
         const double2 nb = v.XY[bs];

@@ -58,7 +58,30 @@ def c4():
                 seed_base=4000, planners=1, node_grid=True)
 
 
-WORKLOADS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4}
+def c5():
+    """Config 5: RRT*-FND dynamic replanning. The config-2 problem (RRT*-FN, 1,000-node cap, 4,096 planners) with 50
+    circles r = U(1,3) that translate by a per-obstacle velocity U(-0.5,0.5)^2 every replanning tick; each tick the
+    robot steps to the next path node (select_branch), the moved obstacles invalidate path nodes (valid_path) and the
+    split-off tree is reconnected or regrown (fnd_loop.FNDReplanner)."""
+    start, goal, ticks, nr = (5.0, 5.0), (95.0, 95.0), 24, 1.0
+    rng = np.random.default_rng(5)
+    obst, vel = [], []
+    while len(obst) < 50:
+        c, r, v = rng.uniform(2, 98, 2), rng.uniform(1.0, 3.0), rng.uniform(-0.5, 0.5, 2)
+        k = np.arange(ticks + 1)[:, None]
+        track = c[None, :] + k * v[None, :]
+        # clear of the start now, and of the goal region (goal-reaching leaves lie within 2 * node_radius of it) at every
+        # tick: a covered goal-side leaf ends a planner's run (the reference raises IndexError there, src/algorithm.py:358)
+        if np.hypot(*(c - start)) < nr + r or (np.hypot(track[:, 0] - goal[0], track[:, 1] - goal[1]) < 3 * nr + r + 0.5).any():
+            continue
+        obst.append((float(c[0]), float(c[1]), float(r))); vel.append((float(v[0]), float(v[1])))
+    vel = np.asarray(vel)
+    return dict(name="c5", mode="fn", obstacles=obst, velocity=vel, xy_range=[[0.0, 100.0], [0.0, 100.0]], iter_num=5000,
+                step_length=3.0, radius=6.0, node_radius=1.0, bias=0.01, max_nodes=1000, start=start, goal=goal,
+                seed_base=5000, planners=4096, ticks=ticks, reconnect_radius=15.0, regrow_iters=100)
+
+
+WORKLOADS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
 
 
 def planner_problems(w, first, count):

@@ -1,0 +1,217 @@
+"""RRT*-FND replanning loop (BASELINE.json config 5; rrt_star_fnd_algorithm_b200/fnd_loop.py).
+
+The reference ships the steps (select_branch / valid_path / reconnect / regrow, pinned on reference goldens in
+tests/test_fnd.py) but not the loop (RRT_STAR_FND stops at a stub, src/algorithm.py:283-291). Here the device loop is
+compared, tick by tick and bit for bit, with the same composition of the CPU oracle's steps (oracle/fnd_loop.py)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import cases as K
+from oracle.fnd_loop import OracleReplanner, MOVING, ARRIVED, LOST
+from rrt_star_fnd_algorithm_b200 import _structs as S
+from rrt_star_fnd_algorithm_b200 import workloads as W
+from rrt_star_fnd_algorithm_b200.fnd_loop import moved_obstacles
+
+from util import assert_tree_equal
+
+
+def small_c5(iter_num=1500, max_nodes=400):
+    w = W.c5()
+    w.update(iter_num=iter_num, max_nodes=max_nodes)
+    return w
+
+
+def oracle_planners(w, P, ticks):
+    s, g, seeds, sids = W.planner_problems(w, 0, P)
+    prm = K.params_for(w, stream_mode=S.STREAM_PHILOX, flags=0)
+    out = []
+    for p in range(P):
+        t = O.OracleTree(s[p], w["iter_num"] + 2 + ticks * w["regrow_iters"])
+        assert t.run(prm, w["obstacles"], g[p], seed=int(seeds[p]), stream_id=int(sids[p]))[0] == S.ST_DONE
+        out.append(OracleReplanner(t, prm, g[p], seeds[p], sids[p], w["node_radius"], w["reconnect_radius"], w["regrow_iters"]))
+    return out
+
+
+def check_forest(e, path, root):
+    """Child counts agree with the parents; the stored path follows parent links from the goal-side leaf to the root."""
+    ids = [int(i) for i in e["ids"]]
+    par = dict(zip(ids, [int(q) for q in e["parent"]]))
+    cnt = {i: 0 for i in ids}
+    for i, q in par.items():
+        if q >= 0:
+            assert q in par, f"node {i} hangs from the deleted node {q}"
+            cnt[q] += 1
+    assert [cnt[i] for i in ids] == [int(c) for c in e["nchild"]]
+    for a, b in zip(path[:-1], path[1:]):
+        assert par[int(a)] == int(b)
+    assert int(path[-1]) == root and par[root] == -1
+
+
+def test_c5_workload_keeps_the_goal_region_clear_and_is_deterministic():
+    a, b = W.c5(), W.c5()
+    assert a["obstacles"] == b["obstacles"] and np.array_equal(a["velocity"], b["velocity"]) and len(a["obstacles"]) == 50
+    for k in range(a["ticks"] + 1):
+        ob = np.asarray(moved_obstacles(a["obstacles"], a["velocity"], k))
+        d = np.hypot(ob[:, 0] - a["goal"][0], ob[:, 1] - a["goal"][1])
+        assert (d >= ob[:, 2] + 3 * a["node_radius"]).all()
+    ob1 = np.asarray(moved_obstacles(a["obstacles"], a["velocity"], 1))
+    assert np.array_equal(ob1[:, 0], np.asarray(a["obstacles"])[:, 0] + a["velocity"][:, 0])
+
+
+def test_oracle_loop_exercises_every_branch_and_keeps_a_consistent_forest():
+    w = small_c5()
+    P, T = 12, w["ticks"]
+    reps = oracle_planners(w, P, T)
+    n = dict(split=0, linked=0, regrown=0, lost=0, arrived=0, multi=0)
+    for k in range(1, T + 1):
+        ob = moved_obstacles(w["obstacles"], w["velocity"], k)
+        for r in reps:
+            before = r.phase
+            o = r.tick(ob)
+            if before != MOVING:
+                assert o["current"] == -1
+                continue
+            if o["separate_root"] >= 0 and o["separate_root"] != o["current"]:
+                n["split"] += 1
+                n["linked"] += sum(v >= 0 for v in o["linked"])
+                n["regrown"] += sum(v == 1 for v in o["regrow"])
+                n["multi"] += (o["linked"][1] >= 0) or (o["regrow"][1] != 0)
+            e = r.t.export()
+            assert r.t.planner().n_live == len(e["ids"])
+            if r.phase != LOST:
+                check_forest(e, r.t.best_path(), o["current"])
+    n["lost"] = sum(r.phase == LOST for r in reps)
+    assert n["split"] >= 20 and n["linked"] >= 10 and n["regrown"] >= 3 and n["multi"] >= 1 and n["lost"] < P, n
+
+
+class OracleBackedBatch:
+    """The slice of PlannerBatch that FNDReplanner drives, answered by oracle trees: lets the host logic of the product
+    loop run on the CPU against the oracle loop (the device kernels themselves are covered by the gpu test below)."""
+
+    def __init__(self, w, P, ticks):
+        import torch
+        self.torch, self.w, self.P, self.device = torch, w, P, torch.device("cpu")
+        self.reps = oracle_planners(w, P, ticks)          # only their trees are used
+        self.obstacles = w["obstacles"]
+        self._refresh()
+
+    def _refresh(self):
+        torch = self.torch
+        rows, paths, rec = [], [], np.zeros(self.P, dtype=S.PLANNER_DTYPE)
+        for p, r in enumerate(self.reps):
+            ids = [int(i) for i in r.t.export()["ids"]] + [-1]
+            root = r.t.root()
+            rec[p]["root_slot"] = ids.index(root) if root in ids[:-1] else len(ids) - 1
+            path = [int(i) for i in r.t.best_path()]
+            rec[p]["best_len"] = len(path)
+            rows.append(ids); paths.append(path)
+        n = max(len(r) for r in rows)
+        self.id = torch.tensor([r + [-1] * (n - len(r)) for r in rows], dtype=torch.int32)
+        m = max(2, max(len(q) for q in paths))
+        self.best_path_t = torch.tensor([q + [0] * (m - len(q)) for q in paths], dtype=torch.int32)
+        self._rec = rec
+
+    def planners(self):
+        return self._rec.copy()
+
+    def set_obstacles(self, obstacles):
+        self.obstacles = obstacles
+
+    def select_branch(self, cur):
+        out = np.array([r.t.select_branch(int(c)) if c >= 0 else -1 for r, c in zip(self.reps, cur)], np.int32)
+        self._refresh()
+        return out
+
+    def valid_path(self, prev):
+        sep, err = np.full(self.P, -1, np.int32), np.zeros(self.P, np.int32)
+        for p, (r, c) in enumerate(zip(self.reps, prev)):
+            if c >= 0:
+                s_, e_ = r.t.valid_path(self.obstacles, self.w["node_radius"], int(c))
+                sep[p], err[p] = (-1 if e_ else s_), int(e_)
+        self._refresh()
+        return sep, err
+
+    def reconnect(self, ids, radius):
+        out = np.array([r.t.reconnect(self.obstacles, int(i), radius, int(r.t.best_path()[0])) if i >= 0 else -1
+                        for r, i in zip(self.reps, ids)], np.int32)
+        self._refresh()
+        return out
+
+    def regrow(self, ids, max_iter):
+        res, its = np.full(self.P, S.E_BADARG if hasattr(S, "E_BADARG") else -100, np.int32), np.zeros(self.P, np.int32)
+        for p, (r, i) in enumerate(zip(self.reps, ids)):
+            if i >= 0:
+                res[p], its[p] = r.t.regrow(r.prm, self.obstacles, r.goal, int(i), seed=r.seed, stream_id=r.stream_id, max_iter=max_iter)
+        self._refresh()
+        return res, its
+
+
+def test_product_loop_host_logic_equals_the_oracle_loop_on_oracle_trees():
+    from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner
+    w = small_c5()
+    P, T = 10, w["ticks"]
+    fake = OracleBackedBatch(w, P, T)
+    loop = FNDReplanner(fake, w["reconnect_radius"], w["regrow_iters"])
+    reps = oracle_planners(w, P, T)
+    assert list(loop.phase) == [r.phase for r in reps]
+    for k in range(1, T + 1):
+        ob = moved_obstacles(w["obstacles"], w["velocity"], k)
+        got = loop.tick(ob)
+        for p, r in enumerate(reps):
+            want = r.tick(ob)
+            what = f"tick {k}, planner {p}"
+            assert int(got["current"][p]) == want["current"] and int(got["phase"][p]) == want["phase"], what
+            if want["current"] < 0:
+                continue
+            assert int(got["status"][p]) == want["status"] and int(got["separate_root"][p]) == want["separate_root"], what
+            assert list(got["linked"][p]) == want["linked"] and list(got["regrow"][p]) == want["regrow"], what
+            assert list(got["regrow_iters"][p]) == want["regrow_iters"], what
+            assert_tree_equal(fake.reps[p].t.export(), r.t.export(), what)
+    assert loop.stats["splits"] >= 15 and loop.stats["regrown"] >= 2 and loop.stats["moves"] > 5 * P
+
+
+@pytest.mark.gpu
+def test_gpu_fnd_loop_matches_the_oracle_loop_tick_by_tick():
+    from rrt_star_fnd_algorithm_b200.batch import PlannerBatch, fn_capacity
+    from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner
+    w = small_c5()
+    P, T = 16, w["ticks"]
+    s, g, seeds, sids = W.planner_problems(w, 0, P)
+    b = PlannerBatch("fn", starts=s, goals=g, obstacles=w["obstacles"], xy_range=w["xy_range"], iter_num=w["iter_num"],
+                     step_length=w["step_length"], radius=w["radius"], node_radius=w["node_radius"], bias=w["bias"],
+                     max_nodes=w["max_nodes"], seeds=seeds, stream_ids=sids).run()
+    b.check_status()
+    b.grow_capacity(fn_capacity(w["max_nodes"]) + T * w["regrow_iters"])      # room for the regrow() extensions
+    reps = oracle_planners(w, P, T)
+    for p in range(P):
+        assert_tree_equal(b.tree(p), reps[p].t.export(), f"planned[{p}]")
+    loop = FNDReplanner(b, w["reconnect_radius"], w["regrow_iters"])
+    assert list(loop.phase) == [r.phase for r in reps]
+    seen = dict(linked=0, regrown=0)
+    for k in range(1, T + 1):
+        ob = moved_obstacles(w["obstacles"], w["velocity"], k)
+        got = loop.tick(ob)
+        pl = b.planners()
+        for p, r in enumerate(reps):
+            was = r.phase
+            want = r.tick(ob)
+            what = f"tick {k}, planner {p}"
+            assert int(got["current"][p]) == want["current"], what
+            assert int(got["phase"][p]) == want["phase"], what
+            if was != MOVING or want["current"] < 0:
+                continue
+            assert int(got["status"][p]) == want["status"], what
+            assert int(got["index_error"][p]) == want["index_error"] and int(got["separate_root"][p]) == want["separate_root"], what
+            assert list(got["linked"][p]) == want["linked"], what
+            assert list(got["regrow"][p]) == want["regrow"] and list(got["regrow_iters"][p]) == want["regrow_iters"], what
+            seen["linked"] += sum(v >= 0 for v in want["linked"])
+            seen["regrown"] += sum(v == 1 for v in want["regrow"])
+            assert_tree_equal(b.tree(p), r.t.export(), what)
+            op = r.t.planner()
+            assert int(pl[p]["cursor"]) == op.cursor and int(pl[p]["last_id"]) == op.last_id and int(pl[p]["n_live"]) == op.n_live, what
+            if want["phase"] != LOST:
+                assert np.array_equal(b.best_path(p), r.t.best_path()), what
+                assert pl[p]["best_cost"] == op.best_cost, what
+    assert seen["linked"] >= 10 and seen["regrown"] >= 3, seen
+    assert loop.stats["splits"] >= 20 and loop.stats["reconnected"] == seen["linked"] and loop.stats["regrown"] == seen["regrown"]
