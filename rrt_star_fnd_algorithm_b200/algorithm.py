@@ -231,6 +231,38 @@ def regrow(G: Graph, map: Map, step_length: float, radius: float, id_root: int, 
     return None
 
 
+# ---- plotting (src/algorithm.py:638-663, :763-775): matplotlib is imported on use, like every visual part ------------
+
+def plot_graph(G: Graph, obstacles: list, xy_range: tuple = None):
+    """Draw the tree, start / goal and the circular obstacles (src/algorithm.py:638-663)."""
+    import matplotlib.pyplot as plt
+    xr, yr = (G.xy_range if xy_range is None else xy_range)
+    for i, q in G.parent.items():
+        if q is not None:
+            (x0, y0), (x1, y1) = G.vertices[i], G.vertices[q]
+            plt.plot((x0, x1), (y0, y1), color="orange", marker="o", markersize=2)
+    ax = plt.gca()
+    for centre, r in obstacles:
+        ax.add_patch(plt.Circle((float(centre[0]), float(centre[1])), float(r), color="black"))
+    ax.add_patch(plt.Circle(G.start, 2, color="blue"))
+    ax.add_patch(plt.Circle(G.goal, 2, color="green"))
+    ax.set_aspect("equal", adjustable="box")
+    plt.xlim(xr[0], xr[1])
+    plt.ylim(yr[0], yr[1])
+
+
+def plot_path(G: Graph, path: list, title: str = "", cost: float = float("inf")):
+    """Draw `path` (ids, goal side first) starting from the goal position, and put the cost in the title
+    (src/algorithm.py:763-775)."""
+    import matplotlib.pyplot as plt
+    prev = G.goal
+    for node in path:
+        pos = G.vertices[node]
+        plt.plot((prev[0], pos[0]), (prev[1], pos[1]), c="#057af7", linewidth=2)
+        prev = pos
+    plt.title(title + f" cost: {round(cost, 2)}")
+
+
 # ---- helpers user code calls directly --------------------------------------------------------------------------------
 
 def calc_distance(p1: tuple, p2: tuple) -> float:

@@ -373,6 +373,20 @@ class PlannerBatch:
                     parent=parent[live], cost=self.ecost[p, :n].cpu().numpy()[live],
                     nchild=self.nchild[p, :n].cpu().numpy()[live])
 
+    def graph(self, p: int, xy_range=None):
+        """Planner p as a `Graph` (src/graph.py:8-98), built on demand from the device arrays: ids, positions, parent /
+        children / cost dictionaries, `last_id`, `start` = the current root. Batches stay on the device; only the
+        planners a caller looks at are turned into dictionaries."""
+        from .graph import Graph
+        pl = self.planners()[p]
+        rng = xy_range if xy_range is not None else [[self.prm.x_lo, self.prm.x_hi], [self.prm.y_lo, self.prm.y_hi]]
+        G = Graph((np.float64(pl["start_x"]), np.float64(pl["start_y"])), (np.float64(pl["goal_x"]), np.float64(pl["goal_y"])),
+                  0, 0, rng)
+        t = self.tree(p)
+        G._import(t["ids"], np.column_stack([t["x"], t["y"]]), t["parent"], t["cost"], int(pl["last_id"]))
+        G.start = G.vertices[self.slot_id(p, int(pl["root_slot"]))] if self.slot_id(p, int(pl["root_slot"])) in G.vertices else G.start
+        return G
+
     def best_path(self, p: int) -> np.ndarray:
         n = int(self.planners()[p]["best_len"])
         return self.best_path_t[p, :n].cpu().numpy().copy()

@@ -126,3 +126,25 @@ def test_through_obstacle_batch_matches_the_oracle():
     hit = through_obstacle_batch(p1, p2, obst)
     assert all(bool(hit[i]) == O.through_obstacle(p1[i], p2[i], case["obstacles"]) for i in range(3000))
     assert through_obstacle_batch(np.zeros((0, 2)), np.zeros((0, 2)), obst).shape == (0,)
+
+
+def test_plot_helpers_walk_the_graph_dictionaries(monkeypatch):
+    """plot_graph / plot_path (src/algorithm.py:638-663, :763-775) only need the dictionaries; matplotlib is stubbed."""
+    import sys
+    import types
+    from unittest.mock import MagicMock
+    plt = MagicMock()
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    from rrt_star_fnd_algorithm_b200 import algorithm as A
+    from rrt_star_fnd_algorithm_b200.graph import Graph
+    G = Graph((0.0, 0.0), (9.0, 9.0), 10, 10, [[0, 10], [0, 10]])
+    a = G.add_vertex((1.0, 1.0)); G.add_edge(a, 0, 1.5)
+    b = G.add_vertex((2.0, 2.5)); G.add_edge(b, a, 1.75)
+    A.plot_graph(G, [[(5.0, 5.0), 1.0]])
+    assert plt.plot.call_count == 2                      # one segment per edge
+    plt.reset_mock()
+    A.plot_path(G, [b, a, 0], "demo", 3.25)
+    assert plt.plot.call_count == 3 and plt.title.call_args[0][0] == "demo cost: 3.25"

@@ -174,3 +174,17 @@ def test_node_grid_large_tree_matches_the_oracle():
     for f in ("cursor", "attempts", "best_cost", "n_rewired", "n_edge_checks", "n_edge_checks_ref"):
         assert pl[f] == getattr(opl, f), f
     assert pl["n_scan_nodes"] < 0.05 * opl.n_scan_nodes           # the point of the grid
+
+
+def test_batch_planner_as_a_graph_object():
+    """PlannerBatch.graph(p): the reference's Graph dictionaries built on demand from the device arrays."""
+    from rrt_star_fnd_algorithm_b200.algorithm import find_path
+    case, g = K.case_by_name("float_star"), load_golden("float_star")
+    b = make_batch(case, seeds=[case["seed"]], stream_ids=[case["stream_id"]], trace=False).run()
+    G = b.graph(0)
+    assert sorted(G.vertices) == [int(i) for i in g["ids"]] and G.last_id == int(g["last_id"])
+    assert G.start == (case["start"][0], case["start"][1]) and G.parent[0] is None
+    path, cost = find_path(G, int(g["best_path"][0]), 0)
+    assert path == [int(i) for i in g["best_path"]] and cost == float(g["best_cost"])
+    assert G.get_cost(int(g["best_path"][0])) == float(g["best_cost"])
+    assert sum(len(c) for c in G.children.values()) == len(G.vertices) - 1
