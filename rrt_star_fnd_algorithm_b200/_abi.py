@@ -6,7 +6,7 @@ import os
 from ._structs import ABI_VERSION, Batch, ObstGrid, Params, Planner
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librrtfnd.so")
+LIB_PATH = os.environ.get("RRTFND_LIB") or os.path.join(_HERE, "librrtfnd.so")   # RRTFND_LIB: an A/B build of the same sources
 
 # every symbol include/rrtfnd.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [

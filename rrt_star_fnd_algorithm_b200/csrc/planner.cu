@@ -27,6 +27,25 @@
 #include "rng.cuh"
 #include "stream.cuh"
 
+// annulus schedule of the nearest-visible search: squared-distance multiplier of the first and of the later annuli.
+// Measured on B200 (profiles/r01_phase_clocks.md): 2 / 2 is the best of 2/2, 8/4, 24/8, 64/8 - wider annuli save scans but
+// stage more, longer segments, and the segment tests are what the search costs.
+#ifndef RRTFND_ANN_FIRST
+#define RRTFND_ANN_FIRST 2
+#endif
+#ifndef RRTFND_ANN_GROW
+#define RRTFND_ANN_GROW 2
+#endif
+
+// Diagnostic build (-DRRTFND_PHASE_CLOCKS): lane 0 of every warp accumulates clock64() deltas per phase of the iteration,
+// summed over the grid into g_phase_clocks and read back by rrtfnd_debug_phase_clocks(). Not compiled into the product.
+#ifdef RRTFND_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clocks[16];
+#define PH_MARK(i) do { __syncwarp(); const long long ph_now = clock64(); if (lane == 0) ph_acc[(i)] += ph_now - ph_last; ph_last = ph_now; } while (0)
+#else
+#define PH_MARK(i) do { } while (0)
+#endif
+
 namespace rrtfnd {
 
 constexpr int kReserveWords = 64;   // must equal RESERVE_WORDS in _structs.py / ORC_RESERVE_WORDS
@@ -326,8 +345,16 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     const bool eval_cp = kLean || (prm.flags & (RRTFND_FLAG_EVAL_CHOOSE_PARENT | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) != 0;
     const bool commit_cp = !kLean && (prm.flags & RRTFND_FLAG_COMMIT_CHOOSE_PARENT) != 0;
     const double2 nan2 = make_double2(CUDART_NAN, CUDART_NAN);
+#ifdef RRTFND_PHASE_CLOCKS
+    __shared__ long long ph_smem[WPB][12];
+    long long* ph_acc = ph_smem[wib];
+    if (lane == 0) for (int i = 0; i < 12; ++i) ph_acc[i] = 0;
+    long long ph_last = clock64();
+    __syncwarp();
+#endif
 
     for (;;) {
+        PH_MARK(9);                                                               // tail of the previous iteration / rejected attempt
         // ================================================================ A. attempt header
         if (iter >= prm.iter_num) { status = RRTFND_ST_DONE; break; }
         if (prm.max_attempts > 0 && attempts >= prm.max_attempts) { status = RRTFND_ST_ATTEMPT_CAP; break; }
@@ -351,7 +378,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         }
 
         // ================================================================ B. Map.is_occupied_c (src/map.py:38-47)
-        if (point_occupied_warp(ob, qx, qy, prm.node_radius, lane, my_tests)) continue;   // src/algorithm.py:39-40
+        const bool occ_ = point_occupied_warp(ob, qx, qy, prm.node_radius, lane, my_tests);
+        PH_MARK(0);                                                               // sample + occupancy
+        if (occ_) continue;                                                       // src/algorithm.py:39-40
 
         // ================================================================ C. nearest visible node (:666-699)
         // The reference asks the k-d tree for the 1st, 2nd, 3rd ... nearest node until one is visible. Round 0 here is
@@ -388,6 +417,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     }
                 }
                 warp_argmin(bd, bs);
+                PH_MARK(1);                                                       // nearest scan
                 n_scan_nodes += list ? n_items : n_live;
                 if (!list || covers_all || (bs != kIntMax && bd <= ng_complete_d2(rho))) break;
                 rho *= 2;
@@ -407,13 +437,17 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 my_tests += r >> 1;
                 if (!__any_sync(kFull, r & 1)) near_slot = bs;
             }
+            PH_MARK(2);                                                           // segment test of the nearest node
             if (near_slot < 0 && n_live > 1) {
                 double lo_d = bd; int lo_s = bs;                                  // keys <= (lo_d, lo_s) are known to be blocked
                 double T = bd;
                 const double t_floor = dmul(dmul(prm.step_length, prm.step_length), 0.0625);
                 rounds = n_live;                                                  // if nothing is visible every node was tried
+                bool first_annulus = true;
                 for (;;) {
-                    T = dadd(T, T);
+                    // any schedule of thresholds is exact; it trades full scans (one per annulus) against segment tests
+                    T = dmul(T, first_annulus ? (double)RRTFND_ANN_FIRST : (double)RRTFND_ANN_GROW);
+                    first_annulus = false;
                     if (T < t_floor) T = t_floor;
                     if (NG && list && !covers_all && T > ng_complete_d2(rho)) {    // the window must hold every node within sqrt(T)
                         rho = max(2 * rho, (int)(sqrt(T) * ng.inv_cell) + 1);
@@ -481,6 +515,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 }
             }
             n_edge_checks += rounds; n_edge_checks_ref += rounds;
+            PH_MARK(3);                                                           // annulus search
             if (near_slot < 0) continue;                                          // :45-46
         }
 
@@ -539,6 +574,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             continue;
         }
 
+        PH_MARK(4);                                                               // steer + insert
         // ================================================================ E. near set -> collision, costs, choose-parent, rewire
         // The ball (query_ball_point, :837 / :893) is produced in ascending slot order by the scan and handed to the
         // lanes in chunks of up to 32 candidates: lane i owns candidate i (its own segment test, its own parent-chain
@@ -584,6 +620,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 }
                 const bool last = t + 1 >= n_tiles;
                 int head = 0;
+                PH_MARK(5);                                                       // near-set scan + staging
                 while (count - head >= (first ? 31 : 32) || (last && count > head)) {
                     const int n = min(count - head, first ? 31 : 32);
                     __syncwarp();
@@ -605,6 +642,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     // chunk walks the new node's chain, starts from its edge cost and records the addends
                     const bool rec = first && lane == 31;
                     int depth = 0;
+                    PH_MARK(6);                                                   // per-candidate segment tests
                     if (rec) { w_from = walk_from; cc = walk_acc; }
                     if (w_from >= 0) {
                         int wn = w_from, q = PARENT[wn];
@@ -618,6 +656,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         my_hops += depth;
                     }
                     __syncwarp();
+                    PH_MARK(7);                                                   // parent-chain walks
                     if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; chain_depth = __shfl_sync(kFull, depth, 31); }
                     if (do_cp) {
                         // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
@@ -651,6 +690,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     }
                     first = false;
                     __syncwarp();
+                    PH_MARK(8);                                                   // choose-parent evaluation + rewire decisions
                     head += n;
                 }
                 if (head > 0) {                                                   // keep the (< 32) leftover at the front
@@ -706,6 +746,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             n_rewired += n_rw;
         }
 
+        PH_MARK(10);                                                              // rewire commit
         const int cp_parent_id = eval_cp ? ID[cp_slot] : -1;   // read before forced_removal can delete that node
 
         // ================================================================ F. forced_removal (:233-237, :800-819)
@@ -832,6 +873,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 
     // ---- write back
     __syncwarp();
+#ifdef RRTFND_PHASE_CLOCKS
+    if (lane == 0) for (int i = 0; i < 12; ++i) atomicAdd(&g_phase_clocks[i], (unsigned long long)ph_acc[i]);
+#endif
     const long long hops = warp_sum(my_hops), tests = warp_sum(my_tests);
     if (lane == 0) {
         PL->best_cost = best_cost; PL->cursor = rng.cursor; PL->attempts = attempts;
@@ -924,6 +968,18 @@ static int check_params(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
                             bt->grid.ny <= 0)) return RRTFND_E_BADARG;
     return 0;
 }
+
+#ifdef RRTFND_PHASE_CLOCKS
+// diagnostic builds only: copy (and optionally clear) the per-phase clock sums
+extern "C" int rrtfnd_debug_phase_clocks(unsigned long long* out_host, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out_host, g_phase_clocks, sizeof(unsigned long long) * 16);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(g_phase_clocks, z, sizeof z);
+    }
+    return (int)e;
+}
+#endif
 
 extern "C" int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm) {
     if (!prm) return RRTFND_E_BADARG;
