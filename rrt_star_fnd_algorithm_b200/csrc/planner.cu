@@ -805,6 +805,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             --n_live; --fn_count; ++n_removed;
         }
 
+        PH_MARK(11);                                                              // forced removal
         // ================================================================ G. goal test and best path (:155-170, :240-251)
         if (reached) {
             if (n_finish >= prm.finish_cap) { status = RRTFND_ST_FINISH_CAP; break; }

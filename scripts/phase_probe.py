@@ -7,8 +7,8 @@ from rrt_star_fnd_algorithm_b200 import _abi, workloads as W
 from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
 
 NAMES = ["sample+occupancy", "nearest scan", "nearest segment test", "annulus search", "steer+insert", "near-set scan+staging",
-         "candidate segment tests", "parent-chain walks", "choose-parent eval + rewire decisions", "iteration tail (goal, FN removal, trace)",
-         "rewire commit", "-"]
+         "candidate segment tests", "parent-chain walks", "choose-parent eval + rewire decisions", "iteration tail (goal test, best-path refresh, trace)",
+         "rewire commit", "forced removal"]
 name, P = sys.argv[1], int(sys.argv[2])
 w = W.WORKLOADS[name]()
 if len(sys.argv) > 3: w["iter_num"] = int(sys.argv[3])
