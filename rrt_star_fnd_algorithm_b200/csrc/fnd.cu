@@ -372,9 +372,11 @@ __global__ void __launch_bounds__(32 * kFndWarps) regrow_kernel(const __grid_con
             const int s = base + lane;
             bool ok = false;
             if (s < new_slot && v.ID[s] >= 0 && (v.NFLAG[s] & kSeparate)) {
+                // the reference tests the segment first and the distance second (:512-514); the first node in id order
+                // that passes both is the same either way, and the distance leaves a handful of segments to test
                 const double2 c = v.XY[s];
-                if (!(seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, px, py, c.x, c.y, 0, 1) & 1))   // Line(q_new, node)
-                    ok = dist_fma(px, py, c.x, c.y) < prm.step_length;
+                if (dist_fma(px, py, c.x, c.y) < prm.step_length)
+                    ok = !(seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, px, py, c.x, c.y, 0, 1) & 1);   // Line(q_new, node)
             }
             const unsigned m = __ballot_sync(kFull, ok);
             if (m) link = base + __ffs(m) - 1;
