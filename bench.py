@@ -389,7 +389,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"{args.workload}")
+            # measured for the workload's default launch size only
+            traffic = json.load(open(tpath)).get(f"{args.workload}") if P == DEFAULT_PLANNERS[args.workload] and not args.iters else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

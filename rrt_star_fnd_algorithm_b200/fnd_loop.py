@@ -22,18 +22,10 @@ All device work goes through the C ABI (rrtfnd_fnd_*); the host logic here is in
 import numpy as np
 import torch
 
+from .workloads import moved_obstacles  # noqa: F401  (re-exported: the loop's callers take it from here)
+
 
 MOVING, ARRIVED, LOST = 0, 1, 2
-
-
-def moved_obstacles(base, velocity, tick):
-    """Obstacle list (ox, oy, r) after `tick` ticks of straight-line motion: centre + tick * velocity (fp64, one multiply
-    and one add per coordinate, the same expression for every consumer)."""
-    b = np.asarray(base, dtype=np.float64).reshape(-1, 3)
-    v = np.asarray(velocity, dtype=np.float64).reshape(-1, 2)
-    x = b[:, 0] + float(tick) * v[:, 0]
-    y = b[:, 1] + float(tick) * v[:, 1]
-    return [(float(x[i]), float(y[i]), float(b[i, 2])) for i in range(len(b))]
 
 
 MAX_ROUNDS = 4   # separate trees mended per tick (one per occupied stretch of the path), goal side first

@@ -58,6 +58,16 @@ def c4():
                 seed_base=4000, planners=1, node_grid=True)
 
 
+def moved_obstacles(base, velocity, tick):
+    """Obstacle list (ox, oy, r) after `tick` ticks of straight-line motion: centre + tick * velocity (fp64, one multiply
+    and one add per coordinate, the same expression for every consumer)."""
+    b = np.asarray(base, dtype=np.float64).reshape(-1, 3)
+    v = np.asarray(velocity, dtype=np.float64).reshape(-1, 2)
+    x = b[:, 0] + float(tick) * v[:, 0]
+    y = b[:, 1] + float(tick) * v[:, 1]
+    return [(float(x[i]), float(y[i]), float(b[i, 2])) for i in range(len(b))]
+
+
 def c5():
     """Config 5: RRT*-FND dynamic replanning. The config-2 problem (RRT*-FN, 1,000-node cap, 4,096 planners) with 50
     circles r = U(1,3) that translate by a per-obstacle velocity U(-0.5,0.5)^2 every replanning tick; each tick the

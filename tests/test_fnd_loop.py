@@ -215,3 +215,101 @@ def test_gpu_fnd_loop_matches_the_oracle_loop_tick_by_tick():
                 assert pl[p]["best_cost"] == op.best_cost, what
     assert seen["linked"] >= 10 and seen["regrown"] >= 3, seen
     assert loop.stats["splits"] >= 20 and loop.stats["reconnected"] == seen["linked"] and loop.stats["regrown"] == seen["regrown"]
+
+
+# ---- the composition against the UNMODIFIED reference functions (oracle/make_fndloop_golden.py) ------------------------
+
+from oracle.make_fndloop_golden import LOOP_CASES, REGROW_ITERS  # noqa: E402
+from oracle.fnd_loop import MAX_ROUNDS  # noqa: E402
+from util import load_npz  # noqa: E402
+
+
+def golden_tree(g, k, regrown):
+    t = {key: g[f"t{k}_{key}"] for key in ("ids", "x", "y", "parent", "cost", "nchild")}
+    if regrown:      # the reference's children lists are inconsistent after reconnect_ancestors
+        ids = list(t["ids"])
+        nc = np.zeros(len(ids), np.int32)
+        for q in t["parent"]:
+            if q >= 0:
+                nc[ids.index(int(q))] += 1
+        t["nchild"] = nc
+    return t
+
+
+def check_loop_against_golden(lc, g, tick_fn, tree_fn, path_fn, cost_fn, cursor_fn):
+    n = int(g["n_ticks"])
+    assert n >= 1
+    seen = dict(splits=0, linked=0, regrown=0, multi=0)
+    for k in range(1, n + 1):
+        got = tick_fn(g[f"obst_{k}"])
+        what = f"{lc['name']} tick {k}"
+        assert got["current"] == int(g[f"t{k}_current"]), what
+        assert got["index_error"] == int(g[f"t{k}_index_error"]), what
+        lost = int(g[f"t{k}_lost"])
+        assert (got["phase"] == LOST) == bool(lost), what
+        if not got["index_error"]:
+            assert got["separate_root"] == int(g[f"t{k}_separate_root"]), what
+        assert list(got["linked"]) == [int(v) for v in g[f"t{k}_linked"]], what
+        assert [int(v == 1) for v in got["regrow"]] == [int(v) for v in g[f"t{k}_regrow"]], what
+        regrown = bool(g[f"t{k}_regrow"].any())
+        assert_tree_equal(tree_fn(), golden_tree(g, k, regrown), what)
+        assert cursor_fn() == int(g[f"t{k}_cursor"]), what
+        if not lost:
+            assert [int(i) for i in path_fn()] == [int(i) for i in g[f"t{k}_path"]], what
+            if f"t{k}_path_cost" in g:
+                assert cost_fn() == float(g[f"t{k}_path_cost"]), what
+        split = got["separate_root"] not in (-1, got["current"])
+        seen["splits"] += split; seen["linked"] += sum(v >= 0 for v in got["linked"]); seen["regrown"] += regrown
+        seen["multi"] += got["linked"][1] >= 0 or got["regrow"][1] != 0
+    return seen
+
+
+@pytest.mark.parametrize("lc", LOOP_CASES, ids=[c["name"] for c in LOOP_CASES])
+def test_oracle_loop_equals_the_reference_functions_composed(lc):
+    case, g = K.case_by_name(lc["case"]), load_npz(f"fndloop_{lc['name']}.npz")
+    prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0)
+    t = O.OracleTree(case["start"], case["iter_num"] + 2 + (lc["ticks"] + 1) * REGROW_ITERS)
+    assert t.run(prm, case["obstacles"], case["goal"], seed=case["seed"], stream_id=case["stream_id"])[0] == S.ST_DONE
+    assert np.array_equal(t.best_path(), g["path0"]) and t.planner().cursor == int(g["cursor0"])
+    rep = OracleReplanner(t, prm, case["goal"], case["seed"], case["stream_id"], case["node_radius"], lc["radius"], REGROW_ITERS)
+    check_loop_against_golden(lc, g, rep.tick, t.export, t.best_path, lambda: t.planner().best_cost, lambda: t.planner().cursor)
+
+
+def test_loop_goldens_cover_the_interesting_states():
+    tot = dict(ticks=0, splits=0, linked=0, regrown=0, multi=0, lost=0)
+    for lc in LOOP_CASES:
+        g = load_npz(f"fndloop_{lc['name']}.npz")
+        n = int(g["n_ticks"])
+        tot["ticks"] += n
+        for k in range(1, n + 1):
+            tot["splits"] += int(g[f"t{k}_separate_root"]) not in (-1, int(g[f"t{k}_current"]))
+            tot["linked"] += int((g[f"t{k}_linked"] >= 0).sum()); tot["regrown"] += int(g[f"t{k}_regrow"].sum())
+            tot["multi"] += int(g[f"t{k}_linked"][1] >= 0 or g[f"t{k}_regrow"][1] != 0)
+        tot["lost"] += int(g[f"t{n}_lost"])
+    assert tot["ticks"] >= 40 and tot["splits"] >= 15 and tot["linked"] >= 12 and tot["regrown"] >= 2 and tot["multi"] >= 1, tot
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lc", LOOP_CASES, ids=[c["name"] for c in LOOP_CASES])
+def test_gpu_loop_equals_the_reference_functions_composed(lc):
+    """The device loop against the goldens recorded from the unmodified reference's own functions."""
+    from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
+    from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner
+    case, g = K.case_by_name(lc["case"]), load_npz(f"fndloop_{lc['name']}.npz")
+    b = PlannerBatch(case["mode"], starts=[case["start"]], goals=[case["goal"]], obstacles=case["obstacles"],
+                     xy_range=case["xy_range"], iter_num=case["iter_num"], step_length=case["step_length"],
+                     radius=case["radius"], node_radius=case["node_radius"], bias=case["bias"], max_nodes=case["max_nodes"],
+                     seeds=[case["seed"]], stream_ids=[case["stream_id"]]).run()
+    b.check_status()
+    assert np.array_equal(b.best_path(0), g["path0"]) and int(b.planners()[0]["cursor"]) == int(g["cursor0"])
+    b.grow_capacity(b.prm.capacity + (int(g["n_ticks"]) + 1) * REGROW_ITERS)
+    loop = FNDReplanner(b, lc["radius"], REGROW_ITERS)
+
+    def tick(obst):
+        out = loop.tick([(float(r[0]), float(r[1]), float(r[2])) for r in obst])
+        return dict(current=int(out["current"][0]), index_error=int(out["index_error"][0]), phase=int(out["phase"][0]),
+                    separate_root=int(out["separate_root"][0]), linked=[int(v) for v in out["linked"][0]],
+                    regrow=[int(v) for v in out["regrow"][0]])
+
+    check_loop_against_golden(lc, g, tick, lambda: b.tree(0), lambda: b.best_path(0),
+                              lambda: b.planners()[0]["best_cost"], lambda: int(b.planners()[0]["cursor"]))
