@@ -138,7 +138,42 @@ static double dist2(double nx, double ny, double qx, double qy) {
 /* K = ((-(r**2)) + ox**2) + oy**2, the circle-only part of `c` (:619), is evaluated by the Python side with the
  * reference's own expression on the caller's number types (`**` is libm pow there, which differs from r*r by an ulp
  * for a few radii), exactly as the product's obstacle table is built. */
+#ifdef ORC_POW_AUDIT
+/* Audit build (make audit): every predicate is ALSO evaluated with libm pow() at the reference's `**` sites
+ * (src/algorithm.py:602-603, :617, :619-620; src/map.py:44) - the arithmetic CPython and numpy scalars really perform -
+ * and compared with the x*x / sqrt form the oracle and the CUDA path use. Counters: [0] circle tests, [1] tests in which
+ * some intermediate differs, [2] tests whose BOOLEAN differs, [3..5] the same for Map.is_occupied_c. */
+static long long g_pow_audit[6];
+void orc_pow_audit(long long* out, int reset) {
+    for (int i = 0; i < 6; ++i) { out[i] = __atomic_load_n(&g_pow_audit[i], __ATOMIC_RELAXED); if (reset) __atomic_store_n(&g_pow_audit[i], 0, __ATOMIC_RELAXED); }
+}
+static int seg_hits_circle_plain(double p1x, double p1y, double p2x, double p2y, double ox, double oy, double r, double K);
 static int seg_hits_circle(double p1x, double p1y, double p2x, double p2y, double ox, double oy, double r, double K) {
+    const int plain = seg_hits_circle_plain(p1x, p1y, p2x, p2y, ox, oy, r, K);
+    if (p2x == p1x) return plain;
+    double m = (p2y - p1y) / (p2x - p1x), k = p1y - m * p1x;
+    double a = 1.0 + pow(m, 2.0);
+    double b = 2.0 * ((-ox + m * k) - m * oy);
+    double c = (K - (2.0 * oy) * k) + pow(k, 2.0);
+    double delta = pow(b, 2.0) - (4.0 * a) * c;
+    int res = 0, differs = (a != 1.0 + m * m) || (c != (K - (2.0 * oy) * k) + k * k) || (delta != b * b - (4.0 * (1.0 + m * m)) * ((K - (2.0 * oy) * k) + k * k));
+    if (!(delta < 0.0)) {
+        double s = pow(delta, 0.5);
+        differs = differs || (s != sqrt(delta));
+        double x1 = (-b + s) / (2.0 * a), x2 = (-b - s) / (2.0 * a);
+        double lo = p1x < p2x ? p1x : p2x, hi = p1x < p2x ? p2x : p1x;
+        res = (x1 > lo && x1 < hi) || (x2 > lo && x2 < hi);
+    }
+    __atomic_fetch_add(&g_pow_audit[0], 1, __ATOMIC_RELAXED);
+    if (differs) __atomic_fetch_add(&g_pow_audit[1], 1, __ATOMIC_RELAXED);
+    if (res != plain) __atomic_fetch_add(&g_pow_audit[2], 1, __ATOMIC_RELAXED);
+    return plain;
+}
+#define seg_hits_circle_impl seg_hits_circle_plain
+#else
+#define seg_hits_circle_impl seg_hits_circle
+#endif
+static int seg_hits_circle_impl(double p1x, double p1y, double p2x, double p2y, double ox, double oy, double r, double K) {
     if (p2x == p1x) {                         /* src/line.py:9; src/algorithm.py:563-567 */
         return fabs(ox - p1x) <= r;
     }
@@ -172,6 +207,12 @@ static int is_occupied(double px, double py, const double* obst, int M, double n
     for (int j = 0; j < M; ++j) {
         double dx = px - obst[4 * j], dy = py - obst[4 * j + 1];
         double d = sqrt(dx * dx + dy * dy);
+#ifdef ORC_POW_AUDIT
+        double d2 = sqrt(pow(dx, 2.0) + pow(dy, 2.0));     /* np.sqrt((..)**2 + (..)**2), src/map.py:44 */
+        __atomic_fetch_add(&g_pow_audit[3], 1, __ATOMIC_RELAXED);
+        if (d2 != d) __atomic_fetch_add(&g_pow_audit[4], 1, __ATOMIC_RELAXED);
+        if ((d2 < node_radius + obst[4 * j + 2]) != (d < node_radius + obst[4 * j + 2])) __atomic_fetch_add(&g_pow_audit[5], 1, __ATOMIC_RELAXED);
+#endif
         if (d < node_radius + obst[4 * j + 2]) return 1;
     }
     return 0;
