@@ -18,15 +18,15 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def main():
+def run(name="c3", P=64, iters=2000, threads=None):
+    """Grow P planners of workload `name` with the audit build; returns (extensions, bad planners, the six counters)."""
+    import subprocess
+    subprocess.check_call(["make", "-C", HERE, "-s", "audit"])
     sys.path.insert(0, os.path.join(HERE, ".."))
     import bench
     from rrt_star_fnd_algorithm_b200 import _structs as S, workloads as W
     import oracle as O
-    name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-    P = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
-    threads = int(sys.argv[4]) if len(sys.argv) > 4 else len(os.sched_getaffinity(0))
+    threads = threads or len(os.sched_getaffinity(0))
     L = C.CDLL(os.path.join(HERE, "_build", "librrt_oracle_audit.so"))
     vp = C.c_void_p
     L.orc_run_batch.argtypes = [C.POINTER(S.Params), C.c_int, vp, vp, vp, vp, C.c_int]
@@ -39,11 +39,21 @@ def main():
     ob = O.obst_table3(w["obstacles"])
     out = np.zeros(P, dtype=S.PLANNER_DTYPE)
     p = lambda a: a.ctypes.data_as(vp)
-    t0 = time.time()
-    bad = L.orc_run_batch(C.byref(prm), P, p(sg), p(sd), p(ob), p(out), threads)
     cnt = np.zeros(6, np.int64)
     L.orc_pow_audit(p(cnt), 1)
-    print(f"{name}: {P} planners x {iters} iterations on {threads} threads, {int(out['iter'].sum())} extensions, {time.time() - t0:.0f} s, "
+    bad = L.orc_run_batch(C.byref(prm), P, p(sg), p(sd), p(ob), p(out), threads)
+    L.orc_pow_audit(p(cnt), 1)
+    return int(out["iter"].sum()), int(bad), cnt
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
+    threads = int(sys.argv[4]) if len(sys.argv) > 4 else len(os.sched_getaffinity(0))
+    t0 = time.time()
+    ext, bad, cnt = run(name, P, iters, threads)
+    print(f"{name}: {P} planners x {iters} iterations on {threads} threads, {ext} extensions, {time.time() - t0:.0f} s, "
           f"bad planners {bad}")
     print(f"  circle tests   {cnt[0]:>14,d}   an intermediate differs {cnt[1]:>12,d} ({100 * cnt[1] / max(cnt[0], 1):.3f} %)   boolean differs {cnt[2]}")
     print(f"  occupancy tests{cnt[3]:>14,d}   the distance differs    {cnt[4]:>12,d} ({100 * cnt[4] / max(cnt[3], 1):.3f} %)   boolean differs {cnt[5]}")

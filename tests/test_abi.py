@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -80,3 +81,19 @@ def test_obstacle_grid_builder_lists_every_circle_near_a_cell():
     # no obstacles -> culling disabled
     g0, arrs0 = build_obstacle_grid(np.zeros((0, 3)), 1.0, (0.0, 1.0, 0.0, 1.0))
     assert g0.nx == 0 and arrs0 is None
+
+
+def test_planner_kernel_sass_streams_the_tree_through_tma():
+    """The built library's planner kernel holds the bulk-copy (TMA) and mbarrier instructions of the xy ring
+    (csrc/stream.cuh): UBLKCP + SYNCS in the SASS of the lean RRT* instance, compiled for sm_100a."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    from rrt_star_fnd_algorithm_b200 import _abi
+    out = subprocess.run([tool, "-sass", "-fun", "_ZN6rrtfnd11plan_kernelILi1ELi16ELb0ELi1ELb1EEEv13rrtfnd_params12rrtfnd_batch",
+                          _abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out and "SYNCS.ARRIVE.TRANS64" in out and "SYNCS.PHASECHK" in out
+    assert out.count("DADD") > 100 and out.count("DMUL") > 50     # fp64 arithmetic as separately rounded adds and multiplies

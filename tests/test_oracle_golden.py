@@ -123,3 +123,14 @@ def test_batch_driver_matches_single_runs():
     for f in ("iter", "attempts", "best_cost", "cursor", "n_live", "n_rewired", "n_edge_checks"):
         assert np.array_equal(out1[f], out3[f]), f
     assert (out1["iter"] == 200).all()
+
+
+def test_libm_pow_at_the_reference_sites_changes_no_predicate():
+    """The reference's `** 2` / `** 0.5` are libm pow(), the restatement and the CUDA path use x*x / sqrt.
+    The audit build evaluates every circle / occupancy test both ways while growing real trees: intermediates do differ
+    (so the audit is live), booleans do not. The long runs are recorded in DESIGN.md section 2."""
+    from oracle import pow_audit
+    ext, bad, cnt = pow_audit.run("c2", 8, 300, 4)
+    assert bad == 0 and ext == 8 * 300
+    assert cnt[0] > 1_000_000 and cnt[1] > 100 and cnt[4] > 10      # a one-ulp difference in ~0.1 % of the evaluations
+    assert cnt[2] == 0 and cnt[5] == 0
