@@ -240,6 +240,12 @@ int rrtfnd_near_set(const rrtfnd_batch_t* batch, int32_t capacity, const double*
 int rrtfnd_chain_cost(const rrtfnd_batch_t* batch, int32_t capacity, const int32_t* planner_idx,
                       const int32_t* slot, int64_t n, double* out_cost, void* stream);
 
+/* `x ** 2` (which = 0) or `x ** 0.5` (which = 1) for n values as the reference's interpreter evaluates them: libm pow() of
+ * glibc 2.39 x86-64 (FMA build), which is not fl(x*x) / sqrt(x) in ~0.1 % of arguments (src/algorithm.py:602-603, :617,
+ * :619-620; src/map.py:44; csrc/libm_pow.h). The planners use x*x / sqrt (no predicate changed in 4.2 G audited
+ * evaluations); this operator is the device half of closing that gap by construction. */
+int rrtfnd_pow_libm(const double* x, int64_t n, int32_t which, double* out, void* stream);
+
 /* ---- fused planner driver ---------------------------------------------------------------------- */
 
 /* Advance every planner of the batch until iter == prm->iter_num (or a status other than RUNNING).

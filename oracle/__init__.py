@@ -30,6 +30,7 @@ def build(force: bool = False) -> str:
         os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    subprocess.check_call(["make", "-C", _HERE, "-s", "powcheck"])      # csrc/libm_pow.h compiled for the host (checker)
     return _SO
 
 

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RRTFND_LIB") or os.path.join(_HERE, "librrtfnd.so")  
 EXPORTS = [
     "rrtfnd_abi_version", "rrtfnd_status_string", "rrtfnd_plan_smem_bytes", "rrtfnd_obst_grid_build_host",
     "rrtfnd_edges_vs_circles", "rrtfnd_points_occupied", "rrtfnd_edges_vs_circles_grid", "rrtfnd_points_occupied_grid", "rrtfnd_nearest_visible", "rrtfnd_near_set",
-    "rrtfnd_chain_cost", "rrtfnd_plan_batch", "rrtfnd_init_batch",
+    "rrtfnd_chain_cost", "rrtfnd_pow_libm", "rrtfnd_plan_batch", "rrtfnd_init_batch",
     "rrtfnd_fnd_select_branch", "rrtfnd_fnd_valid_path", "rrtfnd_fnd_reconnect", "rrtfnd_fnd_regrow",
     "rrtfnd_plan_host",
 ]
@@ -42,6 +42,7 @@ def _load():
     lib.rrtfnd_nearest_visible.argtypes = [PB, i32, vp, i32, vp, vp, vp]
     lib.rrtfnd_near_set.argtypes = [PB, i32, vp, dbl, i32, vp, vp, vp]
     lib.rrtfnd_chain_cost.argtypes = [PB, i32, vp, vp, i64, vp, vp]
+    lib.rrtfnd_pow_libm.argtypes = [vp, i64, i32, vp, vp]
     lib.rrtfnd_plan_batch.argtypes = [PP, PB, vp]
     lib.rrtfnd_init_batch.argtypes = [PP, PB, vp]
     lib.rrtfnd_fnd_select_branch.argtypes = [PP, PB, vp, vp, vp]

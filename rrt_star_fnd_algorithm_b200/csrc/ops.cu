@@ -332,3 +332,23 @@ extern "C" int rrtfnd_chain_cost(const rrtfnd_batch_t* bt, int32_t capacity, con
     chain_cost_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*bt, capacity, planner_idx, slot, n, out_cost);
     return (int)cudaGetLastError();
 }
+
+// ---- `**` as the reference's interpreter evaluates it (libm pow of glibc 2.39, csrc/libm_pow.h) --------------------------
+#include "libm_pow.h"
+
+namespace rrtfnd {
+__global__ void pow_libm_kernel(const double* __restrict__ x, long long n, int which, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = which ? rrtfnd_libm_pow_half(x[i]) : rrtfnd_libm_pow2(x[i]);
+}
+}  // namespace rrtfnd
+
+extern "C" int rrtfnd_pow_libm(const double* x, int64_t n, int32_t which, double* out, void* stream) {
+    if (n < 0 || (n > 0 && (!x || !out)) || (which != 0 && which != 1)) return RRTFND_E_BADARG;
+    if (n == 0) return 0;
+    const int nt = 256;
+    const long long want = (n + nt - 1) / nt;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);             // grid-stride over a multiple of the SM count
+    rrtfnd::pow_libm_kernel<<<blocks, nt, 0, (cudaStream_t)stream>>>(x, (long long)n, which, out);
+    return (int)cudaGetLastError();
+}
