@@ -73,6 +73,7 @@ def lib():
     L.orc_cull_probe.restype = C.c_int64
     L.orc_cull_probe.argtypes = [C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int64)]
     L.orc_run_batch.argtypes = [C.POINTER(Params), C.c_int, vp, vp, vp, vp, C.c_int]
+    L.orc_set_libm_pow.argtypes = [C.c_int]
     _lib = L
     return L
 
@@ -234,6 +235,12 @@ def run_batch(prm: Params, starts_goals, seeds, obstacles, n_threads=1):
     out = np.zeros(len(sg), dtype=PLANNER_DTYPE)
     bad = lib().orc_run_batch(C.byref(prm), len(sg), _ptr(sg), _ptr(sd), _ptr(ob), _ptr(out), int(n_threads))
     return out, bad
+
+
+def set_libm_pow(on: bool):
+    """Evaluate the reference's `** 2` / `** 0.5` as the libm pow() they call (csrc/libm_pow.h) instead of x*x / sqrt —
+    process-wide switch of the oracle; the CUDA planners compute the x*x / sqrt form."""
+    lib().orc_set_libm_pow(int(bool(on)))
 
 
 def cull_probe(seed, n_trials, coord_max, slope_max, margin, scale=1.0):

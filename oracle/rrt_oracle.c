@@ -115,6 +115,15 @@ static uint32_t rng_randbelow(orc_rng_t* r, uint32_t n) {
 
 /* --------------------------------------------------------------------------------- arithmetic */
 
+/* `x ** 2` / `x ** 0.5` of the reference (src/algorithm.py:602-603, :617, :619-620; src/map.py:44): fl(x*x) / sqrt(x) by
+ * default — what the CUDA planners compute — or, after orc_set_libm_pow(1), the restatement of the libm pow() those
+ * expressions really call (csrc/libm_pow.h, bit-equal to glibc 2.39's pow on 2 x 10^10 checked arguments). */
+#include "../rrt_star_fnd_algorithm_b200/csrc/libm_pow.h"
+static int g_libm_pow = 0;
+void orc_set_libm_pow(int on) { g_libm_pow = on; }
+static inline double pow2_ref(double x) { return g_libm_pow ? rrtfnd_libm_pow2(x) : x * x; }
+static inline double pow_half_ref(double x) { return g_libm_pow ? rrtfnd_libm_pow_half(x) : sqrt(x); }
+
 /* calc_distance (src/algorithm.py:954-961): np.linalg.norm of a 1-D vector = sqrt(x.dot(x)); OpenBLAS
  * ddot's tail loop is compiled with FMA, giving sqrt(fma(dy, dy, fl(dx*dx))) (pinned by the goldens). */
 static double dist_fma(double px, double py, double qx, double qy) {
@@ -179,12 +188,12 @@ static int seg_hits_circle_impl(double p1x, double p1y, double p2x, double p2y, 
     }
     double m = (p2y - p1y) / (p2x - p1x);     /* src/line.py:15 */
     double k = p1y - m * p1x;                 /* src/line.py:16 */
-    double a = 1.0 + m * m;                   /* src/algorithm.py:617 */
+    double a = 1.0 + pow2_ref(m);             /* src/algorithm.py:617 */
     double b = 2.0 * ((-ox + m * k) - m * oy);            /* :618 */
-    double c = (K - (2.0 * oy) * k) + k * k; /* :619 */
-    double delta = b * b - (4.0 * a) * c;     /* :620 */
+    double c = (K - (2.0 * oy) * k) + pow2_ref(k); /* :619 */
+    double delta = pow2_ref(b) - (4.0 * a) * c;     /* :620 */
     if (delta < 0.0) return 0;                /* :569 */
-    double s = sqrt(delta);                   /* :602-603 */
+    double s = pow_half_ref(delta);           /* :602-603 */
     double x1 = (-b + s) / (2.0 * a);
     double x2 = (-b - s) / (2.0 * a);
     double lo = p1x < p2x ? p1x : p2x;        /* :632-633 */
@@ -206,7 +215,7 @@ static int through_obstacle(double p1x, double p1y, double p2x, double p2y, cons
 static int is_occupied(double px, double py, const double* obst, int M, double node_radius) {
     for (int j = 0; j < M; ++j) {
         double dx = px - obst[4 * j], dy = py - obst[4 * j + 1];
-        double d = sqrt(dx * dx + dy * dy);
+        double d = sqrt(pow2_ref(dx) + pow2_ref(dy));
 #ifdef ORC_POW_AUDIT
         double d2 = sqrt(pow(dx, 2.0) + pow(dy, 2.0));     /* np.sqrt((..)**2 + (..)**2), src/map.py:44 */
         __atomic_fetch_add(&g_pow_audit[3], 1, __ATOMIC_RELAXED);

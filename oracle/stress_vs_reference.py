@@ -1,7 +1,7 @@
 """Stress run: the C oracle against the UNMODIFIED Python reference on many fresh random planners — TEST
 INFRASTRUCTURE, build container only (the reference is ~100 extensions/s per core).
 
-    python -m oracle.stress_vs_reference [planners=240] [iterations=400] [processes=8]
+    python -m oracle.stress_vs_reference [planners=240] [iterations=400] [processes=8] [libm]
 
 Every planner gets its own random map (float circles, so nothing is exactly representable), start / goal, mode
 (RRT* / RRT*-FN / RRT) and Philox stream; the run fails on the first tree, best path, cost, word cursor or
@@ -16,7 +16,7 @@ import time
 import numpy as np
 
 
-def one(idx, iters):
+def one(idx, iters, libm_pow=False):
     import oracle as O
     from oracle import cases as K
     from oracle import refharness as H
@@ -40,6 +40,7 @@ def one(idx, iters):
                           iter_num=iters, step_length=step, radius=case["radius"], node_radius=nr, bias=case["bias"],
                           max_nodes=case["max_nodes"], record=True)
     prm = K.params_for(case, n_words=len(words), flags=0)
+    O.set_libm_pow(libm_pow)       # the reference's `**` as libm pow() (by construction) instead of x*x / sqrt
     t = O.OracleTree(start, iters + 2)
     st, _ = t.run(prm, obst, goal, words=words)
     got, pl = t.export(), t.planner()
@@ -57,12 +58,13 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 240
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 400
     procs = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    libm = len(sys.argv) > 4 and sys.argv[4] == "libm"
     t0 = time.time()
     with mp.get_context("fork").Pool(procs) as pool:
-        res = pool.starmap(one, [(i, iters) for i in range(n)], chunksize=1)
+        res = pool.starmap(one, [(i, iters, libm) for i in range(n)], chunksize=1)
     bad = [r for r in res if r[4]]
     ext = sum(r[2] for r in res)
-    print(f"{n} planners x {iters} iterations: {ext} extensions, {sum(r[3] for r in res)} through_obstacle calls, "
+    print(f"[oracle `**` = {'libm pow emulation' if libm else 'x*x / sqrt'}] {n} planners x {iters} iterations: {ext} extensions, {sum(r[3] for r in res)} through_obstacle calls, "
           f"{len(bad)} planners differ, {time.time() - t0:.0f} s")
     for r in bad[:10]:
         print("  DIFFERS:", r)

@@ -134,3 +134,21 @@ def test_libm_pow_at_the_reference_sites_changes_no_predicate():
     assert bad == 0 and ext == 8 * 300
     assert cnt[0] > 1_000_000 and cnt[1] > 100 and cnt[4] > 10      # a one-ulp difference in ~0.1 % of the evaluations
     assert cnt[2] == 0 and cnt[5] == 0
+
+
+@pytest.mark.parametrize("name", ["float_fn", "float_star", "int_star"])
+def test_libm_pow_mode_of_the_oracle_reproduces_the_goldens(name):
+    """With the reference's `**` evaluated as the libm pow() it calls (csrc/libm_pow.h) the oracle is the reference by
+    construction; the goldens must come out the same as with x*x / sqrt."""
+    import oracle as O
+    case, g = K.case_by_name(name), load_golden(name)
+    words = philox_words(case["seed"], case["stream_id"], K.words_needed(case))
+    prm = K.params_for(case, stream_mode=S.STREAM_WORDS, n_words=len(words), flags=0)
+    O.set_libm_pow(True)
+    try:
+        t = O.OracleTree(case["start"], case["iter_num"] + 2)
+        assert t.run(prm, case["obstacles"], case["goal"], words=words)[0] == S.ST_DONE
+        assert_tree_equal(t.export(), g, name)
+        assert t.planner().cursor == int(g["words_used"]) and t.planner().best_cost == float(g["best_cost"])
+    finally:
+        O.set_libm_pow(False)
