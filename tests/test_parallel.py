@@ -111,3 +111,19 @@ def test_bench_config_is_shared_by_both_arms():
     c = bench.bench_config(W.c3(), 16384, 1, args, 5002)
     assert c["workload"].startswith("c3: star x 16384 planners per GPU (16384 total), 500 circular obstacles, 5000 iterations")
     assert bench.DEFAULT_PLANNERS["c3"] == 16384 and bench.METRIC == "rrt_star_tree_extensions_per_sec"
+
+
+def test_bench_cpu_legs_run_on_small_samples():
+    """The CPU legs of bench.py (cpu_baseline / --impl reference): the C port on a few planners of c3 and the whole config-5
+    step (planning + replanning ticks through oracle/fnd_loop.py) on a few planners."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    from rrt_star_fnd_algorithm_b200 import workloads as W
+    ext, edge, dt, out = bench.cpu_port_run(W.c3(), 0, 4, 200, 2)
+    assert int(out["iter"].sum()) == 800 and ext > 0 and edge > ext
+    w = W.c5()
+    ext, moves, dt, total = bench.cpu_c5_run(dict(w, iter_num=1500, max_nodes=400), 0, 4, 2)
+    assert total >= 4 * 1500 and moves > 0
+    cfg = bench.bench_config(w, 4096, 1, __import__("argparse").Namespace(launch=0, near_cap=64), 1258)
+    assert "24 replanning ticks" in cfg["workload"]
