@@ -39,6 +39,24 @@ __device__ __forceinline__ double dist_plain(double nx, double ny, double qx, do
     return dsqrt(dist2(nx, ny, qx, qy));
 }
 
+// The reference's `x ** 2` / `x ** 0.5` sites (src/algorithm.py:602-603, :617, :619-620; src/map.py:44). Default: fl(x*x) and
+// sqrt(x). A build with -DRRTFND_LIBM_POW=1 evaluates them as the libm pow() the interpreter calls (libm_pow.h, bit-equal
+// to glibc 2.39's pow on 2 x 10^10 checked arguments): bit-exact to the reference by construction at ~60 fp64 operations
+// and two table reads per site. Compile-time so that the default kernels are untouched; see DESIGN.md section 2.
+#ifndef RRTFND_LIBM_POW
+#define RRTFND_LIBM_POW 0
+#endif
+#if RRTFND_LIBM_POW
+}  // namespace rrtfnd
+#include "libm_pow.h"
+namespace rrtfnd {
+static __device__ __noinline__ double pow2_ref(double x) { return rrtfnd_libm_pow2(x); }
+static __device__ __noinline__ double pow_half_ref(double x) { return rrtfnd_libm_pow_half(x); }
+#else
+__device__ __forceinline__ double pow2_ref(double x) { return dmul(x, x); }
+__device__ __forceinline__ double pow_half_ref(double x) { return dsqrt(x); }
+#endif
+
 // Line(p1, p2) in slope / intercept form (src/line.py:5-16) plus the per-segment terms of calc_delta
 // (src/algorithm.py:607-621) that do not depend on the circle.
 struct Seg {
@@ -57,8 +75,8 @@ __device__ __forceinline__ Seg make_seg(double p1x, double p1y, double p2x, doub
     s.m = ddiv(dsub(p2y, p1y), dsub(p2x, p1x));            // src/line.py:15
     s.k = dsub(p1y, dmul(s.m, p1x));                       // src/line.py:16 (uses p1)
     s.mk = dmul(s.m, s.k);
-    s.kk = dmul(s.k, s.k);
-    const double a = dadd(1.0, dmul(s.m, s.m));            // src/algorithm.py:617
+    s.kk = pow2_ref(s.k);                                  // line.const_term ** 2 (src/algorithm.py:619)
+    const double a = dadd(1.0, pow2_ref(s.m));             // 1 + line.dir ** 2 (:617)
     s.a2 = dadd(a, a);
     s.a4 = dmul(4.0, a);
     s.lo = p1x < p2x ? p1x : p2x;
@@ -72,9 +90,9 @@ __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double 
     if (s.vertical) return fabs(dsub(ox, s.p1x)) <= r;                          // :563-567
     const double b = dmul(2.0, dsub(dadd(-ox, s.mk), dmul(s.m, oy)));           // :618
     const double c = dadd(dsub(K, dmul(dadd(oy, oy), s.k)), s.kk);              // :619
-    const double delta = dsub(dmul(b, b), dmul(s.a4, c));                       // :620
+    const double delta = dsub(pow2_ref(b), dmul(s.a4, c));                      // b ** 2 - 4 * a * c (:620)
     if (!(delta >= 0.0)) return false;                                          // :569 (NaN -> no hit as well)
-    const double sq = dsqrt(delta);                                             // :602-603
+    const double sq = pow_half_ref(delta);                                      // delta ** 0.5 (:602-603)
     const double2 x = ddiv2(dadd(-b, sq), dsub(-b, sq), s.a2);                  // x1, x2 (:602-603)
     return (x.x > s.lo && x.x < s.hi) || (x.y > s.lo && x.y < s.hi);                // :576, :632-635
 }
@@ -83,7 +101,7 @@ __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double 
 __device__ __forceinline__ bool point_in_inflated(double px, double py, double ox, double oy, double r,
                                                   double node_radius) {
     const double dx = dsub(px, ox), dy = dsub(py, oy);
-    return dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))) < dadd(node_radius, r);
+    return dsqrt(dadd(pow2_ref(dx), pow2_ref(dy))) < dadd(node_radius, r);      // np.sqrt((..) ** 2 + (..) ** 2)
 }
 
 // lexicographic (d2, slot) order: nearest first, lowest slot (= lowest id) on ties
