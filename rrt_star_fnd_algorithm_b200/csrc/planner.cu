@@ -37,6 +37,13 @@
 #define RRTFND_ANN_GROW 2
 #endif
 
+// Experiment knob (-DRRTFND_RANK_IN_NEAR=1, default off, unmeasured): after an annulus search the reference-equivalent
+// edge-check count needs the winner's rank among all nodes, today a separate pass over the tree (key_rank); the near-set
+// scan of the same iteration touches every node anyway and can count it on the side.
+#ifndef RRTFND_RANK_IN_NEAR
+#define RRTFND_RANK_IN_NEAR 0
+#endif
+
 // Diagnostic build (-DRRTFND_PHASE_CLOCKS): lane 0 of every warp accumulates clock64() deltas per phase of the iteration,
 // summed over the grid into g_phase_clocks and read back by rrtfnd_debug_phase_clocks(). Not compiled into the product.
 #ifdef RRTFND_PHASE_CLOCKS
@@ -500,6 +507,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         // the visible ones is the node the reference would have stopped at, because everything in earlier annuli was
         // blocked. A boxed-in sample therefore costs O(log N) scans instead of O(N).
         int near_slot = -1;
+#if RRTFND_RANK_IN_NEAR
+        bool rank_pending = false; double rank_d = 0.0; int rank_s = 0; int my_rank = 0;
+#endif
         {
             double bd = CUDART_INF; int bs = kIntMax;
             // what the scans below run over: the whole tree (TMA ring), or - node grid - the nodes of a window of cells
@@ -617,6 +627,10 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     warp_argmin(vd, vs);
                     if (vs != kIntMax) {
                         near_slot = vs;
+#if RRTFND_RANK_IN_NEAR
+                        if (!NG && mode != RRTFND_MODE_RRT) { rank_pending = true; rank_d = vd; rank_s = vs; rounds = 0; }
+                        else
+#endif
                         rounds = (NG && list) ? ng_key_rank(XY, list, n_items, qx, qy, vd, vs, lane)
                                               : key_rank(XY, n_slots, qx, qy, vd, vs, lane);
                         break;
@@ -724,6 +738,12 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int s = sl[u];
+#if RRTFND_RANK_IN_NEAR
+                    if (rank_pending && pass == 0) {                              // nodes with key <= the annulus winner's (NaN: false)
+                        const double dq = dist2(v[u].x, v[u].y, qx, qy);
+                        my_rank += ((dq < rank_d || (dq == rank_d && s <= rank_s)) && s != new_slot) ? 1 : 0;
+                    }
+#endif
                     const bool in = dist2(v[u].x, v[u].y, px, py) <= r2 && s != new_slot;
                     const unsigned m = __ballot_sync(kFull, in);
                     if (in) stage[count + __popc(m & lt_mask)] = s;
@@ -820,6 +840,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             }
         }
         if (__any_sync(kFull, dup)) { status = RRTFND_ST_DUPLICATE; break; }
+#if RRTFND_RANK_IN_NEAR
+        if (rank_pending) { const int rk = (int)warp_sum((long long)my_rank); n_edge_checks += rk; n_edge_checks_ref += rk; }
+#endif
         n_scan_nodes += nlist ? n_near_items : n_live;
         n_edge_checks += k_total;
         n_edge_checks_ref += 2 * (long long)k_total + 2;   // each candidate twice + Line(q_new, q_new) twice
