@@ -43,6 +43,12 @@
 #ifndef RRTFND_RANK_IN_NEAR
 #define RRTFND_RANK_IN_NEAR 0
 #endif
+// Experiment knob (-DRRTFND_SPLIT_CANDIDATES=1, default off, unmeasured): lane i owns candidate i, so a chunk of 12 ball nodes
+// leaves 20 lanes idle while 12 lanes walk ~10 circles each; with <= 16 (<= 8) candidates two (four) lanes share one
+// candidate's circle list (seg_blocked's first / stride pair) and the hit bits are folded back to the owner lane.
+#ifndef RRTFND_SPLIT_CANDIDATES
+#define RRTFND_SPLIT_CANDIDATES 0
+#endif
 
 // Diagnostic build (-DRRTFND_PHASE_CLOCKS): lane 0 of every warp accumulates clock64() deltas per phase of the iteration,
 // summed over the grid into g_phase_clocks and read back by rrtfnd_debug_phase_clocks(). Not compiled into the product.
@@ -764,11 +770,30 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
                         if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
                         // Line(node, q_new): p1 = node (:846 / :903)
+#if !RRTFND_SPLIT_CANDIDATES
                         const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
                         my_tests += r >> 1;
                         hit = r & 1;
                         if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
+#endif
                     }
+#if RRTFND_SPLIT_CANDIDATES
+                    {
+                        const int gl = n <= 8 ? 4 : n <= 16 ? 2 : 1;              // lanes per candidate (warp-uniform)
+                        const int ci = lane / gl, sub = lane % gl;
+                        int r = 0;
+                        if (ci < n) {
+                            const double2 c2 = XY[stage[head + ci]];
+                            r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c2.x, c2.y, px, py, sub, gl);
+                        }
+                        my_tests += r >> 1;
+                        const unsigned hits = __ballot_sync(kFull, r & 1);
+                        if (lane < n) {
+                            hit = ((hits >> (lane * gl)) & ((1u << gl) - 1u)) != 0;
+                            if (!hit) w_from = s;                                 // Graph.get_cost(id) (:848 / :905)
+                        }
+                    }
+#endif
                     // parent-chain walks, one loop for all lanes (Graph.get_cost, src/graph.py:41-46): lane 31 of the first
                     // chunk walks the new node's chain, starts from its edge cost and records the addends
                     const bool rec = first && lane == 31;

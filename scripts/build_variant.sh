@@ -3,6 +3,7 @@
 # travels with gpurun); select it at run time with RRTFND_LIB=<path>.
 #   scripts/build_variant.sh libm_pow -DRRTFND_LIBM_POW=1
 #   scripts/build_variant.sh rank_near -DRRTFND_RANK_IN_NEAR=1
+#   scripts/build_variant.sh split -DRRTFND_SPLIT_CANDIDATES=1
 #   scripts/build_variant.sh phase -DRRTFND_PHASE_CLOCKS          (scripts/phase_probe.py)
 set -e
 name=$1; shift
