@@ -22,3 +22,13 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "reference" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _oracle_pow_mode():
+    """RRTFND_ORACLE_LIBM_POW=1 runs every oracle comparison with the reference's `**` evaluated as libm pow() (csrc/libm_pow.h):
+    the setting that goes with a -DRRTFND_LIBM_POW=1 build of the library selected through RRTFND_LIB (scripts/gpu_variants.sh)."""
+    if os.environ.get("RRTFND_ORACLE_LIBM_POW") == "1":
+        import oracle
+        oracle.set_libm_pow(True)
+    yield
