@@ -118,13 +118,13 @@ static __device__ __noinline__ int point_occupied_lane(const double2* tab, const
     int j = 0, e = M;
     if (cull) {
         const int c = grid_cell(py, g->y0, g->inv_cell, g->ny) * g->nx + grid_cell(px, g->x0, g->inv_cell, g->nx);
-        j = __ldg(g->pt_start + c);
-        e = __ldg(g->pt_start + c + 1);
+        j = RRTFND_TAB_LD(g->pt_start + c);
+        e = RRTFND_TAB_LD(g->pt_start + c + 1);
     }
     int tests = 0;
     for (; j < e; ++j) {
         double ox, oy, r, K;
-        load_obst(tab, cull ? __ldg(g->pt_items + j) : j, ox, oy, r, K);
+        load_obst(tab, cull ? RRTFND_TAB_LD(g->pt_items + j) : j, ox, oy, r, K);
         ++tests;
         if (point_in_inflated(px, py, ox, oy, r, node_radius)) return 2 * tests + 1;
     }
@@ -339,6 +339,37 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
     }
 }
 
+#if RRTFND_SMEM_TABLES
+__device__ unsigned g_plan_queue[1];      // next planner index of the running launch (reset by the host wrapper; one launch at a time)
+
+// bytes of the shared-memory copy of the tables: obstacle rows, then seg_start / seg_items / pt_start / pt_items
+__host__ __device__ inline size_t table_smem_bytes(int n_obst, int n_cells, int n_seg, int n_pt) {
+    return align_up((size_t)n_obst * 32, 16) + 2 * align_up((size_t)(n_cells + 1) * 4, 16) + align_up((size_t)n_seg * 4, 16) +
+           align_up((size_t)n_pt * 4, 16);
+}
+// Whole CTA: copy the tables behind `base`, publish a grid descriptor whose pointers address the copies; returns the bytes used.
+__device__ size_t stage_tables(const rrtfnd_batch_t& bt, int n_obst, unsigned char* base, rrtfnd_obst_grid_t* sg) {
+    const rrtfnd_obst_grid_t& g = bt.grid;
+    const int nc = g.nx * g.ny;
+    const int n_seg = nc > 0 ? __ldg(g.seg_start + nc) : 0, n_pt = nc > 0 ? __ldg(g.pt_start + nc) : 0;
+    double* tab = reinterpret_cast<double*>(base);
+    int32_t* ss = reinterpret_cast<int32_t*>(base + align_up((size_t)n_obst * 32, 16));
+    int32_t* ps = ss + align_up((size_t)(nc + 1) * 4, 16) / 4;
+    int32_t* si = ps + align_up((size_t)(nc + 1) * 4, 16) / 4;
+    int32_t* pi = si + align_up((size_t)n_seg * 4, 16) / 4;
+    for (int i = threadIdx.x; i < n_obst * 4; i += blockDim.x) tab[i] = bt.obst[i];
+    for (int i = threadIdx.x; i <= nc && nc > 0; i += blockDim.x) { ss[i] = g.seg_start[i]; ps[i] = g.pt_start[i]; }
+    for (int i = threadIdx.x; i < n_seg; i += blockDim.x) si[i] = g.seg_items[i];
+    for (int i = threadIdx.x; i < n_pt; i += blockDim.x) pi[i] = g.pt_items[i];
+    if (threadIdx.x == 0) {
+        *sg = g;
+        if (nc > 0) { sg->seg_start = ss; sg->seg_items = si; sg->pt_start = ps; sg->pt_items = pi; }
+    }
+    __syncthreads();
+    return table_smem_bytes(n_obst, nc, n_seg, n_pt);
+}
+#endif
+
 // WPB warps (= planners) per CTA; MINW = resident warps per SM the register allocation must allow (16 -> 128
 // registers, 24 -> 80, 32 -> 64): small batches get registers, large ones get occupancy.
 // MODE >= 0 is a LEAN instance: that planner mode with choose-parent evaluated but not committed and no trace — the
@@ -348,8 +379,27 @@ template <int WPB, int MINW, bool NG, int MODE, bool RING>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#if RRTFND_SMEM_TABLES
+    // Persistent CTA: the obstacle table and both culling lists are copied into shared memory once, then every warp pulls
+    // planners from a queue until it is empty (a finished planner's warp slot is reused at once, as with one planner per CTA).
+    __shared__ rrtfnd_obst_grid_t sgrid;
+    unsigned char* const warp_base = smem + stage_tables(bt, prm.n_obst, smem, &sgrid);
+    const double* const obst_tab = reinterpret_cast<const double*>(smem);
+    const rrtfnd_obst_grid_t* const obst_grid = &sgrid;
+    for (;;) {
+    __syncwarp();
+    int p = 0;
+    if (lane == 0) p = (int)atomicAdd(&g_plan_queue[0], 1u);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= bt.n_planners) break;
+#else
+    unsigned char* const warp_base = smem;
+    const double* const obst_tab = bt.obst;
+    const rrtfnd_obst_grid_t* const obst_grid = &bt.grid;
     const int p = blockIdx.x * WPB + wib;
     if (p >= bt.n_planners) return;                       // whole warp leaves; warps never synchronise with each other
+    {
+#endif
     const int C = prm.capacity;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -373,7 +423,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 
     // per-warp shared memory
     const int n_stages = prm.reserved;                 // resolved by the host wrapper (2 or 4)
-    unsigned char* ws = smem + (size_t)wib * warp_smem_bytes(prm, n_stages);
+    unsigned char* ws = warp_base + (size_t)wib * warp_smem_bytes(prm, n_stages);
     unsigned char* wp = ws + (size_t)n_stages * kTileBytes;
     XYStream xs;
     stream_init(xs, ws, wp, n_stages, lane);
@@ -389,7 +439,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     uint32_t* bm = reinterpret_cast<uint32_t*>(rwlist + align_up((size_t)prm.near_cap * 4, 16) / 4);
     uint32_t* pre = bm + align_up((size_t)bitmap_words(prm) * 4, 16) / 4;
 
-    const Obst ob = make_obst(bt.obst, prm.n_obst, &bt.grid);
+    const Obst ob = make_obst(obst_tab, prm.n_obst, obst_grid);
     // node grid (NG kernels only)
     const rrtfnd_node_grid_t& ng = bt.node_grid;
     int32_t* HEAD = NG ? ng.head + (size_t)p * ng.nx * ng.ny : nullptr;
@@ -1046,6 +1096,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         PL->n_rewired = n_rewired; PL->n_removed = n_removed; PL->solution_found = solution_found;
         PL->n_compactions = n_compactions; PL->fn_count = fn_count;
     }
+    }   // one planner (RRTFND_SMEM_TABLES: next planner of the queue)
 }
 
 // Graph.__init__ (src/graph.py:25-32): a tree holding only the start node, id 0.
@@ -1074,12 +1125,42 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 template <int WPB, int MINW, bool NG = false, int MODE = -1, bool RING = true>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
-    const size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
-    if (bytes > kMaxSmem) return RRTFND_E_SMEM;
+    size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
     auto kern = plan_kernel<WPB, MINW, NG, MODE, RING>;
+    int blocks = (bt->n_planners + WPB - 1) / WPB;
+#if RRTFND_SMEM_TABLES
+    {   // table sizes (two words back from the device: an experiment build can afford the synchronisation), queue reset,
+        // persistent grid of as many CTAs as fit
+        const int nc = bt->grid.nx * bt->grid.ny;
+        int n_seg = 0, n_pt = 0;
+        cudaError_t e0 = cudaSuccess;
+        if (nc > 0) {
+            e0 = cudaMemcpyAsync(&n_seg, bt->grid.seg_start + nc, 4, cudaMemcpyDeviceToHost, st);
+            if (e0 == cudaSuccess) e0 = cudaMemcpyAsync(&n_pt, bt->grid.pt_start + nc, 4, cudaMemcpyDeviceToHost, st);
+            if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(st);
+        }
+        if (e0 != cudaSuccess) return (int)e0;
+        bytes += table_smem_bytes(prm->n_obst, nc, n_seg, n_pt);
+        const unsigned zero = 0;
+        e0 = cudaMemcpyToSymbolAsync(g_plan_queue, &zero, 4, 0, cudaMemcpyHostToDevice, st);
+        if (e0 != cudaSuccess) return (int)e0;
+    }
+#endif
+    if (bytes > kMaxSmem) return RRTFND_E_SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    kern<<<(bt->n_planners + WPB - 1) / WPB, 32 * WPB, bytes, st>>>(*prm, *bt);
+#if RRTFND_SMEM_TABLES
+    {
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WPB, bytes);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return RRTFND_E_SMEM;
+        if (blocks > sms * per_sm) blocks = sms * per_sm;
+    }
+#endif
+    kern<<<blocks, 32 * WPB, bytes, st>>>(*prm, *bt);
     return (int)cudaGetLastError();
 }
 
@@ -1171,6 +1252,13 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     // of the launch word overrides: 1 = plain loads, 2 / 4 = ring.
     const int stages_req = (prm->reserved >> 4) & 15;
     const bool ring = stages_req == 1 ? false : (stages_req == 2 || stages_req == 4) ? true : prm->capacity > 2048;
+#if RRTFND_SMEM_TABLES
+    // the tables are shared by the 8 warps of a persistent CTA, two CTAs per SM
+    if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<8, 16, false, RRTFND_MODE_STAR, true>(&q, &b, st)
+                                                        : launch_plan<8, 16, false, RRTFND_MODE_STAR, false>(&q, &b, st);
+    if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<8, 16, false, RRTFND_MODE_FN, true>(&q, &b, st)
+                                                      : launch_plan<8, 16, false, RRTFND_MODE_FN, false>(&q, &b, st);
+#endif
     if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<1, 16, false, RRTFND_MODE_STAR, true>(&q, &b, st)
                                                         : launch_plan<1, 16, false, RRTFND_MODE_STAR, false>(&q, &b, st);
     if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<1, 16, false, RRTFND_MODE_FN, true>(&q, &b, st)
