@@ -49,6 +49,12 @@
 #ifndef RRTFND_SPLIT_CANDIDATES
 #define RRTFND_SPLIT_CANDIDATES 0
 #endif
+// Experiment knob (-DRRTFND_LANE_MIN_HINT=1, default off, unmeasured): when the nearest node is blocked, every lane still holds
+// the nearest node of its own stride from the argmin scan; the lanes whose candidate lies within 8x the nearest distance test
+// theirs in parallel, and the nearest VISIBLE one bounds the search: one pass over (nearest, bound] replaces the doubling annuli.
+#ifndef RRTFND_LANE_MIN_HINT
+#define RRTFND_LANE_MIN_HINT 0
+#endif
 
 // Diagnostic build (-DRRTFND_PHASE_CLOCKS): lane 0 of every warp accumulates clock64() deltas per phase of the iteration,
 // summed over the grid into g_phase_clocks and read back by rrtfnd_debug_phase_clocks(). Not compiled into the product.
@@ -568,6 +574,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 #endif
         {
             double bd = CUDART_INF; int bs = kIntMax;
+#if RRTFND_LANE_MIN_HINT
+            double lane_d = CUDART_INF; int lane_s = kIntMax;
+#endif
             // what the scans below run over: the whole tree (TMA ring), or - node grid - the nodes of a window of cells
             const int32_t* list = nullptr;
             int n_items = n_slots, rho = 1;
@@ -593,6 +602,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         if (d < bd || (NG && d == bd && sl[u] < bs)) { bd = d; bs = sl[u]; }
                     }
                 }
+#if RRTFND_LANE_MIN_HINT
+                lane_d = bd; lane_s = bs;                                         // this lane's own nearest, before the reduction
+#endif
                 warp_argmin(bd, bs);
                 PH_MARK(1);                                                       // nearest scan
                 n_scan_nodes += list ? n_items : n_live;
@@ -621,8 +633,28 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 const double t_floor = dmul(dmul(prm.step_length, prm.step_length), 0.0625);
                 rounds = n_live;                                                  // if nothing is visible every node was tried
                 bool first_annulus = true;
+#if RRTFND_LANE_MIN_HINT
+                double hint_T = 0.0;                                              // squared distance of the nearest visible lane candidate
+                {
+                    bool vis = false;
+                    if (lane_s != kIntMax && lane_s != bs && lane_d <= dmul(bd, 64.0)) {
+                        const double2 c = XY[lane_s];
+                        const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, c.x, c.y, 0, 1);
+                        my_tests += r >> 1;
+                        vis = !(r & 1);
+                    }
+                    double hd = vis ? lane_d : CUDART_INF; int hs = vis ? lane_s : kIntMax;
+                    __syncwarp();
+                    warp_argmin(hd, hs);
+                    if (hs != kIntMax) hint_T = hd;
+                }
+#endif
                 for (;;) {
                     // any schedule of thresholds is exact; it trades full scans (one per annulus) against segment tests
+#if RRTFND_LANE_MIN_HINT
+                    if (first_annulus && hint_T > 0.0) T = hint_T;                 // the bound itself is staged and visible: one pass
+                    else
+#endif
                     T = dmul(T, first_annulus ? (double)RRTFND_ANN_FIRST : (double)RRTFND_ANN_GROW);
                     first_annulus = false;
                     if (T < t_floor) T = t_floor;

@@ -5,6 +5,7 @@
 #   scripts/build_variant.sh rank_near -DRRTFND_RANK_IN_NEAR=1
 #   scripts/build_variant.sh split -DRRTFND_SPLIT_CANDIDATES=1
 #   scripts/build_variant.sh smem_tables -DRRTFND_SMEM_TABLES=1
+#   scripts/build_variant.sh lane_hint -DRRTFND_LANE_MIN_HINT=1
 #   scripts/build_variant.sh phase -DRRTFND_PHASE_CLOCKS          (scripts/phase_probe.py)
 set -e
 name=$1; shift

@@ -3,6 +3,7 @@
 #   scripts/build_variant.sh rank_near -DRRTFND_RANK_IN_NEAR=1
 #   scripts/build_variant.sh split -DRRTFND_SPLIT_CANDIDATES=1
 #   scripts/build_variant.sh smem_tables -DRRTFND_SMEM_TABLES=1
+#   scripts/build_variant.sh lane_hint -DRRTFND_LANE_MIN_HINT=1
 #   scripts/build_variant.sh libm_pow -DRRTFND_LIBM_POW=1
 # then: gpurun --timeout 900 -- 'bash scripts/gpu_variants.sh'
 set -x
@@ -10,7 +11,7 @@ V=$PWD/rrt_star_fnd_algorithm_b200/_variants
 timeout 120 python -m pytest tests/test_libm_pow.py -x -q -m gpu 2>&1 | tail -2            # the -0 / subnormal fix of rrtfnd_pow_libm
 python scripts/perf_probe.py c3 16384 5000 1 0 64 | cut -c1-140                           # baseline of this box
 python scripts/perf_probe.py c2 4096 5000 1 0 64 | cut -c1-140
-for v in rank_near split smem_tables; do
+for v in rank_near split lane_hint smem_tables; do
   [ -f $V/$v.so ] || continue
   echo "== $v"
   RRTFND_LIB=$V/$v.so timeout 300 python -m pytest tests/test_gpu_planner.py tests/test_fnd_loop.py -x -q -m gpu 2>&1 | tail -2
