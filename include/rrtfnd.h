@@ -42,6 +42,7 @@ extern "C" {
 #define RRTFND_FLAG_COMMIT_CHOOSE_PARENT 2 /* EXTENSION: use that return value as the new node's edge (the reference drops it, :146/:224) */
 #define RRTFND_FLAG_TRACE 4                /* write one rrtfnd_trace_t per successful iteration */
 #define RRTFND_FLAG_NODE_GRID 8            /* answer nearest / near-set queries of large trees through batch.node_grid (RRT, RRT* only) */
+#define RRTFND_FLAG_OBST_HAS_K 16          /* rrtfnd_plan_host only: obst_host rows are (ox, oy, r, K) instead of (ox, oy, r) */
 
 /* per-planner status (rrtfnd_planner_t.status) */
 #define RRTFND_ST_RUNNING 0        /* iter < iter_num, can be resumed */
@@ -55,6 +56,8 @@ extern "C" {
 #define RRTFND_ST_DUPLICATE (-5)   /* steered point coincides with an existing vertex (src/graph.py:54-56 corner) */
 #define RRTFND_ST_NO_CHILDLESS (-6)/* forced_removal would spin forever (src/algorithm.py:815-816) */
 #define RRTFND_ST_STREAM_EXHAUSTED (-7) /* word buffer ran out inside forced_removal's redraw loop */
+#define RRTFND_ST_REGROW_NEED_WORDS (-8) /* rrtfnd_fnd_regrow: word buffer exhausted at an attempt boundary; the planner state is
+                                          * consistent - refill and call again with the remaining iterations */
 
 /* rrtfnd_fnd_regrow gives up with RRTFND_ST_ATTEMPT_CAP after this many attempts per allowed extension
  * (max_iter * RRTFND_REGROW_ATTEMPTS_PER_ITER in total): the reference's loop (src/algorithm.py:490-495) only counts
@@ -298,9 +301,12 @@ int rrtfnd_fnd_regrow(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, c
 
 /* Plan P independent problems given HOST buffers; allocates device memory, copies in, runs to completion,
  * copies results back. starts_goals_host is [P][4] (sx, sy, gx, gy); seeds_host is [P][2] (seed, stream_id);
- * obst_host is [M][3] (ox, oy, r). Outputs (all host, may be NULL to skip): planners_host [P];
- * tree arrays xy [P][capacity][2], ecost, parent (slot), nchild, id [P][capacity]; best_path_host
- * [P][path_cap]. The obstacle grid is built inside the call. */
+ * obst_host is [M][3] (ox, oy, r): the per-circle constant K = -r ** 2 + ox ** 2 + oy ** 2 (src/algorithm.py:619) is
+ * then evaluated inside with the C library's pow(), the call the reference's `**` makes on floats; with
+ * RRTFND_FLAG_OBST_HAS_K obst_host is [M][4] (ox, oy, r, K) and the caller's K is used (integer-valued obstacles of
+ * Map.generate_obstacles, src/map.py:59-60, are squared exactly by the interpreter). Outputs (all host, may be NULL to
+ * skip): planners_host [P]; tree arrays xy [P][capacity][2], ecost, parent (slot), nchild, id [P][capacity];
+ * best_path_host [P][path_cap]. The obstacle grid is built inside the call. */
 int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t n_planners, const double* starts_goals_host,
                      const uint64_t* seeds_host, const double* obst_host, const uint32_t* words_host,
                      rrtfnd_planner_t* planners_host, double* xy_host, double* ecost_host,

@@ -24,6 +24,10 @@ DROPIN_CASES = [
     # two calls on one Graph, and a goal radius different from the map's node radius
     dict(name="rrt_then_star", seed=11, case="int_star", calls=[("RRT", 40), ("RRT_star", 200)], node_radius_arg=8),
     dict(name="star_then_fn", seed=12, case="float_star", calls=[("RRT_star", 120), ("RRT_star_FN", 300)], node_radius_arg=1),
+    # RRT*-FN on a Graph that already holds more nodes than the slack of a fresh FN run: RRT_star_FN counts only its own
+    # insertions (n_of_nodes starts at 1, src/algorithm.py:209), so the live count peaks at 401 + 350
+    dict(name="star_then_fn_big", seed=13, case="float_star", calls=[("RRT_star", 400), ("RRT_star_FN", 900)], node_radius_arg=1,
+         max_nodes=350),
 ]
 
 
@@ -36,13 +40,13 @@ def build_objects(ref_graph, ref_map, case):
     return g, m
 
 
-def call_planner(mod, name, G, m, case, iters, node_radius_arg):
+def call_planner(mod, name, G, m, case, iters, node_radius_arg, max_nodes=None):
     if name == "RRT":
         return mod.RRT(G, iters, m, case["step_length"], node_radius_arg, bias=case["bias"])
     if name == "RRT_star":
         return mod.RRT_star(G, iters, m, case["step_length"], case["radius"] or 30, node_radius_arg, bias=case["bias"])
-    return mod.RRT_star_FN(G, iters, m, case["step_length"], case["radius"], node_radius_arg, max_nodes=case["max_nodes"],
-                           bias=case["bias"])
+    return mod.RRT_star_FN(G, iters, m, case["step_length"], case["radius"], node_radius_arg,
+                           max_nodes=case["max_nodes"] if max_nodes is None else max_nodes, bias=case["bias"])
 
 
 def graph_arrays(G):
@@ -58,8 +62,11 @@ def graph_arrays(G):
 
 
 def main():
-    import contextlib, io
+    import contextlib, io, sys
+    only = set(sys.argv[1:])                      # optional: names of the cases to (re)generate
     for dc in DROPIN_CASES:
+        if only and dc["name"] not in only:
+            continue
         case = K.case_by_name(dc["case"])
         with patched_reference(random, ascending_ball=True) as ref:     # rng = the real module: nothing is injected
             G, m = build_objects(ref.graph, ref.map, case)
@@ -67,7 +74,7 @@ def main():
             rets = []
             with contextlib.redirect_stdout(io.StringIO()):
                 for name, iters in dc["calls"]:
-                    rets.append(call_planner(ref.algorithm, name, G, m, case, iters, dc["node_radius_arg"]))
+                    rets.append(call_planner(ref.algorithm, name, G, m, case, iters, dc["node_radius_arg"], dc.get("max_nodes")))
             nxt = random.random()
         out = graph_arrays(G)
         out["next_random"] = np.float64(nxt)

@@ -542,7 +542,7 @@ int orc_fnd_regrow(orc_tree_t* t, const rrtfnd_params_t* prm, const double* obst
     const int64_t attempt_cap = t->attempts + (int64_t)max_iter * RRTFND_REGROW_ATTEMPTS_PER_ITER;
     while (iter < max_iter && !reconnected) {
         if (t->attempts >= attempt_cap) { status = RRTFND_ST_ATTEMPT_CAP; break; }   /* the reference would spin forever here */
-        if (rng.mode == RRTFND_STREAM_WORDS && (int64_t)rng.cursor + ORC_RESERVE_WORDS > n_words) { status = -RRTFND_ST_NEED_WORDS - 100; break; }
+        if (rng.mode == RRTFND_STREAM_WORDS && (int64_t)rng.cursor + ORC_RESERVE_WORDS > n_words) { status = RRTFND_ST_REGROW_NEED_WORDS; break; }
         if (t->last_id + 1 >= t->cap) { status = RRTFND_ST_CAPACITY; break; }
         ++t->attempts;
         double qx, qy;

@@ -5,10 +5,10 @@ ABI_VERSION = 2
 
 MODE_RRT, MODE_STAR, MODE_FN = 0, 1, 2
 STREAM_WORDS, STREAM_PHILOX = 0, 1
-FLAG_EVAL_CHOOSE_PARENT, FLAG_COMMIT_CHOOSE_PARENT, FLAG_TRACE, FLAG_NODE_GRID = 1, 2, 4, 8
+FLAG_EVAL_CHOOSE_PARENT, FLAG_COMMIT_CHOOSE_PARENT, FLAG_TRACE, FLAG_NODE_GRID, FLAG_OBST_HAS_K = 1, 2, 4, 8, 16
 
 ST_RUNNING, ST_DONE, ST_NEED_WORDS, ST_ATTEMPT_CAP = 0, 1, 2, 3
-ST_CAPACITY, ST_NEAR_CAP, ST_FINISH_CAP, ST_PATH_CAP, ST_DUPLICATE, ST_NO_CHILDLESS, ST_STREAM_EXHAUSTED = -1, -2, -3, -4, -5, -6, -7
+ST_CAPACITY, ST_NEAR_CAP, ST_FINISH_CAP, ST_PATH_CAP, ST_DUPLICATE, ST_NO_CHILDLESS, ST_STREAM_EXHAUSTED, ST_REGROW_NEED_WORDS = -1, -2, -3, -4, -5, -6, -7, -8
 
 STATUS_NAMES = {
     ST_RUNNING: "running", ST_DONE: "done", ST_NEED_WORDS: "need-words", ST_ATTEMPT_CAP: "attempt-cap",
@@ -17,6 +17,7 @@ STATUS_NAMES = {
     ST_DUPLICATE: "steered point coincides with an existing vertex",
     ST_NO_CHILDLESS: "forced_removal has no removable childless node",
     ST_STREAM_EXHAUSTED: "random word buffer exhausted inside forced_removal",
+    ST_REGROW_NEED_WORDS: "regrow: random word buffer exhausted, refill and call again",
 }
 
 RESERVE_WORDS = 64  # words that must remain when an attempt starts in STREAM_WORDS mode

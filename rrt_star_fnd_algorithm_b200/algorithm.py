@@ -21,7 +21,7 @@ import numpy as np
 
 from .graph import Graph
 from .map import Map
-from ._structs import ST_DONE, ST_NEED_WORDS, STATUS_NAMES
+from ._structs import ST_DONE, ST_NEED_WORDS, ST_REGROW_NEED_WORDS, STATUS_NAMES
 
 
 def time_function(func):
@@ -55,7 +55,9 @@ def _grow(mode: str, G: Graph, iter_num: int, map: Map, step_length: float, radi
     ids, xy, parent, cost, root_id = G._export()
     n0 = len(ids)
     if mode == "fn":
-        capacity = max(fn_capacity(max_nodes), n0 + 2 + 256)
+        # RRT_star_FN counts only this call's nodes (n_of_nodes starts at 1, src/algorithm.py:209), so removals begin after
+        # max_nodes insertions whatever the Graph already held: live nodes peak at n0 + min(iter_num, max_nodes)
+        capacity = max(fn_capacity(max_nodes), n0 + min(int(iter_num), int(max_nodes)) + 2 + max(256, int(max_nodes) // 4))
     else:
         capacity = n0 + int(iter_num) + 2
     state = random.getstate()
@@ -69,6 +71,7 @@ def _grow(mode: str, G: Graph, iter_num: int, map: Map, step_length: float, radi
     b.reset()
     if n0 > 1 or int(ids[0]) != 0 or G.last_id != 0:
         b.load_tree(0, ids, xy, parent, cost, root_id, G.last_id)
+        b.rebuild_grid()                                 # the caller's vertices may lie outside the box of xy_range
     while True:
         b.run()
         pl = b.planners()[0]
@@ -150,7 +153,7 @@ def _surgery_batch(G: Graph, map: Map, path):
     cap = len(ids) + 2
     b = PlannerBatch("star", starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
                      obstacles=map.obstacles_c, xy_range=G.xy_range, iter_num=1, step_length=1.0, radius=1.0,
-                     node_radius=map.node_radius, capacity=cap, path_cap=max(64, cap), finish_cap=8, grid=False)
+                     node_radius=map.node_radius, capacity=cap, path_cap=max(64, len(path) + 2), finish_cap=8, grid=False)
     b.reset()
     b.load_tree(0, ids, xy, parent, cost, root_id, G.last_id)
     b.set_best_path(0, path)
@@ -202,24 +205,35 @@ def reconnect(G: Graph, path: list, map: Map, step_size: float, id_root: int, id
 
 
 def regrow(G: Graph, map: Map, step_length: float, radius: float, id_root: int, id_separate_root: int, last_node: int,
-           bias: float):
+           bias: float, _n_words: int = 16 * 500 + 256):
     """Grow the root tree (at most 500 extensions, drawing from the global `random` like the planners) until a new node
     can adopt the separated tree; returns None like the reference (src/algorithm.py:482-528). `radius` only feeds the
-    reference's choose_parent call whose result it drops."""
+    reference's choose_parent call whose result it drops. `_n_words` (not in the reference) sizes the chunks in which
+    words of the global generator are handed to the device; the result does not depend on it."""
     import torch
     from .batch import PlannerBatch
     ids, xy, parent, cost, root_id = G._export()
     cap = len(ids) + 502
     state = random.getstate()
-    words = _draw_words(16 * 500 + 256)
+    n_words = max(128, int(_n_words))
+    words = _draw_words(n_words)
     b = PlannerBatch("star", starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
                      obstacles=map.obstacles_c, xy_range=G.xy_range, iter_num=1, step_length=step_length, radius=radius,
                      node_radius=map.node_radius, bias=bias, capacity=cap, path_cap=max(64, cap), finish_cap=8,
                      words=words[None, :])
     b.reset()
     b.load_tree(0, ids, xy, parent, cost, root_id, G.last_id)
+    b.rebuild_grid()
     b.set_best_path(0, [last_node])
-    r, _ = b.regrow([id_separate_root])
+    left = 500                                           # the reference's own cap on extensions (:486)
+    while True:
+        r, its = b.regrow([id_separate_root], max_iter=left)
+        if int(r[0]) != ST_REGROW_NEED_WORDS:
+            break
+        left -= int(its[0])                              # rejected samples ate the buffer: the stream continues
+        words = np.concatenate([words, _draw_words(n_words)])
+        b.words = torch.from_numpy(words[None, :].view(np.int32)).to(b.device)
+        b.prm.words_per_planner = len(words)
     pl = b.planners()[0]
     random.setstate(state)
     if int(pl["cursor"]):

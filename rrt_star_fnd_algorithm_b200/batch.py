@@ -247,13 +247,13 @@ class PlannerBatch:
         assert len(a) == self.P, "one node id per planner"
         return torch.from_numpy(a.copy()).to(self.device)
 
-    def set_obstacles(self, obstacles, grid=True, grid_cell=0.0):
+    def set_obstacles(self, obstacles, grid=True, grid_cell=0.0, _table=None):
         """Replace the obstacle table (a moved / extended map) and rebuild the culling grid.
 
         The grid's box must bound every node: trees grown by the planners stay inside the box of xy_range, starts and
         goals (a steered point lies between a node and a sample), so that box is reused; only after load_tree() are the
         node coordinates themselves read back to bound them."""
-        self.obst_host = obstacle_table(obstacles)
+        self.obst_host = obstacle_table(obstacles) if _table is None else _table     # _table: rows that already carry K
         self.prm.n_obst = len(self.obst_host)
         self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(self.device)
         self.grid, self._grid_t = ObstGrid(), None
@@ -274,6 +274,11 @@ class PlannerBatch:
                 self._grid_t = [torch.from_numpy(a).to(self.device) for a in arrs]
                 g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in self._grid_t]
                 self.grid = g
+
+    def rebuild_grid(self, grid_cell=0.0):
+        """Rebuild the culling grid over a box that bounds the nodes the planners hold NOW (after load_tree() a caller's
+        vertices may lie outside xy_range; the grid's exactness argument needs every segment endpoint inside its box)."""
+        self.set_obstacles(None, grid=True, grid_cell=grid_cell, _table=self.obst_host)
 
     def select_branch(self, current_ids):
         """select_branch for every planner: re-root at node current_ids[p] of its best path. Returns statuses."""

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(32 * kFndWarps) regrow_kernel(const __grid_con
     const long long attempt_cap = attempts + (long long)max_iter * RRTFND_REGROW_ATTEMPTS_PER_ITER;
     while (iter < max_iter && !reconnected) {
         if (attempts >= attempt_cap) { result = RRTFND_ST_ATTEMPT_CAP; break; }   // the reference would spin forever here
-        if (prm.stream_mode == RRTFND_STREAM_WORDS && (long long)rng.cursor + kReserveWordsFnd > prm.words_per_planner) { result = -RRTFND_ST_NEED_WORDS - 100; break; }
+        if (prm.stream_mode == RRTFND_STREAM_WORDS && (long long)rng.cursor + kReserveWordsFnd > prm.words_per_planner) { result = RRTFND_ST_REGROW_NEED_WORDS; break; }
         if (n_slots >= prm.capacity) { result = RRTFND_ST_CAPACITY; break; }
         ++attempts;
         double qx, qy;                                                        // Graph.random_node (src/graph.py:96-98)

@@ -102,13 +102,28 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         pl[p].goal_x = starts_goals_host[4 * p + 2];  pl[p].goal_y = starts_goals_host[4 * p + 3];
         pl[p].seed = seeds_host[2 * p]; pl[p].stream_id = seeds_host[2 * p + 1];
     }
-    // obstacle rows ox, oy, r, K with K = ((-(r*r)) + ox*ox) + oy*oy (first three terms of `c`, src/algorithm.py:619)
-    std::vector<double> ob(4 * M + 4);
+    // obstacle rows ox, oy, r, K. K is the circle-only part of calc_delta's `c`, `-r ** 2 + x0 ** 2 + y0 ** 2`
+    // (src/algorithm.py:619). The reference's `**` on floats is the C library's pow(), which is NOT always fl(x * x), so K
+    // is evaluated with pow() here as well - the same call, on the same host libm, in the same left-to-right order as the
+    // interpreter makes (PlannerBatch evaluates the Python expression itself; tests/test_headline_paths.py requires both
+    // tables to be bit-equal). The exponent is volatile so that the host compiler cannot fold pow(x, 2.0) into x * x.
+    // A caller whose obstacles are not plain floats (Python ints are squared exactly) passes its own K:
+    // RRTFND_FLAG_OBST_HAS_K makes obst_host [M][4] = (ox, oy, r, K).
+    const bool has_k = (prm->flags & RRTFND_FLAG_OBST_HAS_K) != 0;
+    const size_t ostride = has_k ? 4 : 3;
+    std::vector<double> ob(4 * M + 4), ob3(3 * M + 3);
     for (size_t j = 0; j < M; ++j) {
-        const volatile double ox = obst_host[3 * j], oy = obst_host[3 * j + 1], r = obst_host[3 * j + 2];
-        const volatile double r2 = r * r, x2 = ox * ox, y2 = oy * oy;
-        const volatile double t = -r2 + x2;
-        ob[4 * j] = ox; ob[4 * j + 1] = oy; ob[4 * j + 2] = r; ob[4 * j + 3] = t + y2;
+        const double ox = obst_host[ostride * j], oy = obst_host[ostride * j + 1], r = obst_host[ostride * j + 2];
+        double K;
+        if (has_k) K = obst_host[4 * j + 3];
+        else {
+            volatile double two = 2.0;
+            const volatile double r2 = pow(r, two), x2 = pow(ox, two), y2 = pow(oy, two);
+            const volatile double t = -r2 + x2;
+            K = t + y2;
+        }
+        ob[4 * j] = ox; ob[4 * j + 1] = oy; ob[4 * j + 2] = r; ob[4 * j + 3] = K;
+        ob3[3 * j] = ox; ob3[3 * j + 1] = oy; ob3[3 * j + 2] = r;
     }
 
     // culling grid over the box that bounds xy_range and every start / goal
@@ -122,11 +137,11 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
     std::vector<int32_t> g_ss, g_si, g_ps, g_pi;
     if (M > 0 && hi_x > lo_x && hi_y > lo_y) {
         int64_t cnt[2];
-        int grc = rrtfnd_obst_grid_build_host(obst_host, (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, 0, 0, 0, 0, cnt);
+        int grc = rrtfnd_obst_grid_build_host(ob3.data(), (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, 0, 0, 0, 0, cnt);
         if (grc) return grc;
         const size_t ncells = (size_t)grid.nx * grid.ny;
         g_ss.resize(ncells + 1); g_ps.resize(ncells + 1); g_si.resize((size_t)cnt[0] + 1); g_pi.resize((size_t)cnt[1] + 1);
-        grc = rrtfnd_obst_grid_build_host(obst_host, (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, g_ss.data(),
+        grc = rrtfnd_obst_grid_build_host(ob3.data(), (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, g_ss.data(),
                                           g_si.data(), g_ps.data(), g_pi.data(), cnt);
         if (grc) return grc;
     }
@@ -169,7 +184,7 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         bt.finish = (int32_t*)d_fin.p; bt.best_path = (int32_t*)d_bp.p; bt.obst = (const double*)d_ob.p;
         bt.words = (const uint32_t*)d_w.p; bt.trace = nullptr;
         rrtfnd_params_t q = *prm;
-        q.flags &= ~RRTFND_FLAG_TRACE;
+        q.flags &= ~(RRTFND_FLAG_TRACE | RRTFND_FLAG_OBST_HAS_K);
         if ((rc = rrtfnd_init_batch(&q, &bt, st))) break;
         if (timing) { cudaStreamSynchronize(st); t2 = now(); }
         if ((rc = rrtfnd_plan_batch(&q, &bt, st))) break;

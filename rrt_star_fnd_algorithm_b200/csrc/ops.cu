@@ -249,6 +249,7 @@ extern "C" const char* rrtfnd_status_string(int st) {
         case RRTFND_ST_DUPLICATE: return "steered point coincides with an existing vertex";
         case RRTFND_ST_NO_CHILDLESS: return "forced_removal has no removable childless node";
         case RRTFND_ST_STREAM_EXHAUSTED: return "random word buffer exhausted inside forced_removal";
+        case RRTFND_ST_REGROW_NEED_WORDS: return "regrow: random word buffer exhausted, refill and call again";
         case RRTFND_E_BADARG: return "bad argument";
         case RRTFND_E_NOGPU: return "no CUDA device";
         case RRTFND_E_SMEM: return "problem does not fit in shared memory";

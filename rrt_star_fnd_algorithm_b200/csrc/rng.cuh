@@ -41,14 +41,21 @@ static __device__ __noinline__ uint4 philox4x32_10(unsigned long long blk, unsig
 
 // The word source of a planner lives in shared memory (one copy per warp, every lane reads and writes the same
 // values), so drawing a word is an ordinary call instead of a block of code inlined at every draw.
+// Every lane stores the same values; the __syncwarp()s keep the read-modify-write of the shared copy race free even if the
+// warp reaches the call in diverged sub-groups (independent thread scheduling): all lanes read, then all lanes write.
 static __device__ __noinline__ uint32_t next_word(WordSrc& r) {
-    const unsigned long long i = r.cursor++;
+    __syncwarp();
+    const unsigned long long i = r.cursor;
+    const bool have = r.have_blk;
+    const unsigned long long blk_idx = r.blk_idx;
+    __syncwarp();
+    r.cursor = i + 1;
     if (r.mode == RRTFND_STREAM_WORDS) {
         if ((long long)i >= r.n_words) { r.exhausted = true; return 0u; }
         return r.words[i];
     }
     const unsigned long long b = i >> 2;
-    if (!r.have_blk || b != r.blk_idx) {
+    if (!have || b != blk_idx) {
         const uint4 o = philox4x32_10(b, r.stream, r.seed);
         r.b0 = o.x; r.b1 = o.y; r.b2 = o.z; r.b3 = o.w;
         r.blk_idx = b;

@@ -72,7 +72,7 @@ def test_dropin_planners_reproduce_the_reference(dc):
     rets = []
     with contextlib.redirect_stdout(io.StringIO()):
         for name, iters in dc["calls"]:
-            rets.append(call_planner(algorithm, name, G, m, case, iters, dc["node_radius_arg"]))
+            rets.append(call_planner(algorithm, name, G, m, case, iters, dc["node_radius_arg"], dc.get("max_nodes")))
     assert random.random() == float(g["next_random"]), "the global generator was not left where the reference leaves it"
     got = graph_arrays(G)
     for k in ("ids", "parent", "nchild"):

@@ -210,6 +210,61 @@ def test_dropin_fnd_functions_on_graph_objects():
 
 
 @pytest.mark.gpu
+def test_dropin_regrow_refills_the_word_buffer_and_matches_the_oracle():
+    """The drop-in regrow() hands the global generator's words to the device in chunks and refills when rejected samples
+    eat them: a tiny chunk (many refills) and the default give the same Graph, the same following random.random(), and
+    both equal the oracle's regrow fed the Mersenne-Twister words directly."""
+    import copy, random
+    from rrt_star_fnd_algorithm_b200 import algorithm as A, graph, map as map_mod
+    from rrt_star_fnd_algorithm_b200.algorithm import _draw_words
+    from oracle.make_dropin_golden import build_objects, graph_arrays
+    fc = next(f for f in FND_CASES if f["name"] == "star_a")
+    case, g = K.case_by_name(fc["case"]), load_npz("fnd_star_a.npz")
+    t = grown_oracle(case)
+    G, m = build_objects(graph, map_mod, case)
+    e = t.export()
+    G._import(e["ids"], np.column_stack([e["x"], e["y"]]), e["parent"], e["cost"], int(e["ids"].max()), {0: G.start})
+    path = [int(i) for i in g["path0"]]
+    new_path = A.select_branch(G, int(g["current"]), path, m)
+    m.add_obstacles([[G.vertices[new_path[i]], fc["block_r"]] for i in fc["block"]])
+    sep = A.valid_path(G, new_path, m, int(g["current"]))
+    assert sep != int(g["current"])
+    # oracle side of the same surgery, then regrow on the MT words of seed 99
+    assert t.select_branch(int(g["current"])) == 0
+    obst2 = [(float(o[0][0]), float(o[0][1]), float(o[1])) for o in m.obstacles_c]
+    wsep, werr = t.valid_path(obst2, case["node_radius"], int(g["current"]))
+    assert wsep == sep and not werr
+    random.seed(99)
+    words = _draw_words(40000)
+    prm = regrow_params(case)
+    prm.bias = 0.02
+    big = O.OracleTree(case["start"], int(e["ids"].max()) + 600)
+    ex = t.export()
+    big.load(ex["ids"], ex["x"], ex["y"], ex["parent"], ex["cost"], t.root(), int(e["ids"].max()))
+    big.set_best_path([path[0]])
+    r, iters = big.regrow(prm, obst2, case["goal"], sep, words=words, cursor=0)
+    assert r in (0, 1) and iters >= 1
+    results = []
+    for chunk in (128, 16 * 500 + 256):
+        H = copy.deepcopy(G)
+        random.seed(99)
+        A.regrow(H, m, case["step_length"], case["radius"], H.id_vertex[H.start], sep, path[0], 0.02, _n_words=chunk)
+        results.append((graph_arrays(H), random.random()))
+    random.seed(99)
+    random.getrandbits(32 * int(big.planner().cursor))
+    want_next = random.random()
+    for arr, nxt in results:
+        assert nxt == want_next
+        got = dict(arr); want = big.export()
+        nc = np.zeros(len(want["ids"]), np.int32)            # children lists after regrow are inconsistent in the reference (B14)
+        for k in ("ids", "parent"):
+            assert np.array_equal(got[k], want[k]), k
+        for k in ("x", "y", "cost"):
+            assert np.array_equal(np.asarray(got[k]).view(np.uint64), want[k].view(np.uint64)), k
+    assert int(big.planner().cursor) > 128                   # the small chunk really was refilled
+
+
+@pytest.mark.gpu
 def test_gpu_fnd_batch_of_different_planners_matches_the_oracle():
     """48 planners with their own start / goal / stream: re-root each at its own path node, invalidate, reconnect."""
     case = dict(K.case_by_name("float_star"), iter_num=400)
