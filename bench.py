@@ -4,9 +4,12 @@
 A *step* is one complete run of the workload's planners owned by this rank: every tree is re-initialised
 to its root and grown for `iter_num` successful iterations (sample -> occupancy -> nearest visible ->
 steer -> insert -> near set -> collision checks -> choose-parent -> rewire -> goal / best-path bookkeeping).
-Weak scaling: every rank owns `--planners` planners (default 16,384 = config 3 on one GPU; global planner index = rank * planners + i, so a
-planner's problem and tree do not depend on the sharding); after its planners finish, a rank takes part in
-one NCCL all_gather of the per-planner result records and one broadcast of the globally best path.
+Scaling (`--scaling`, default strong): BASELINE.json's config 3 is 16,384 planners SHARDED over the GPUs, so by default the
+workload's planners are split into contiguous blocks (parallel.shard_range: 16,384 / N per rank) and the total work is fixed;
+for N > 1 the line also carries `weak_scaling`, the same measurement with a full 16,384-planner batch on EVERY GPU
+(`--scaling weak` makes that the headline; `--planners` = planners per GPU, weak by definition). A planner's problem is a
+function of its global index only, so its tree does not depend on the sharding. After its planners finish, a rank takes
+part in one NCCL all_gather of the per-planner result records and one broadcast of the globally best path.
 
   value        extensions/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e          the same metric through rrtfnd_plan_host(): HOST buffers in, HOST buffers out, copies timed
@@ -42,7 +45,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
-    ap.add_argument("--planners", type=int, default=0, help="planners per GPU (0 = workload default)")
+    ap.add_argument("--planners", type=int, default=0, help="planners per GPU (weak scaling; 0 = the workload's own count, see --scaling)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the workload's planners sharded over the GPUs (config as written); weak: that many on every GPU")
     ap.add_argument("--iters", type=int, default=0, help="iterations per planner (0 = workload default)")
     ap.add_argument("--launch", type=int, default=0)
     ap.add_argument("--near-cap", type=int, default=64)
@@ -203,13 +208,13 @@ def cpu_baseline(w, budget_s):
                       f"{w['name']} on {cores} host threads, C port of the reference algorithm (oracle/rrt_oracle.c)"}
 
 
-def bench_config(w, P, world, args, capacity):
+def bench_config(w, P, world, args, capacity, scaling="strong"):
     """The `config` object of the JSON line: identical for the B200 arm and the reference arm."""
-    return {"workload": f"{w['name']}: {w['mode']} x {P} planners per GPU ({P * world} total), "
+    return {"workload": f"{w['name']}: {w['mode']} x {P * world} planners in total, {P} per GPU ({scaling} scaling), "
                         f"{len(w['obstacles'])} circular obstacles, {w['iter_num']} iterations each"
                         + (f", then {w['ticks']} replanning ticks with moving obstacles" if "ticks" in w else ""),
-            "planners_per_gpu": P, "iter_num": w["iter_num"],
-            "l2": f"per-step working set {P * capacity * 37 / 1e6:.0f} MB of tree state is re-initialised every step "
+            "planners_per_gpu": P, "planners_total": P * world, "iter_num": w["iter_num"],
+            "l2": f"per-step working set {P * capacity * 37 / 1e6:.0f} MB of tree state per GPU is re-initialised every step "
                   "(larger than L2 for the default size; no explicit flush)",
             "launch": args.launch, "near_cap": args.near_cap}
 
@@ -218,7 +223,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, P = load_workload(args)
+    w, _ = load_workload(args)
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    P, _, scaling = planner_layout(args, world, 0)
     cores = len(os.sched_getaffinity(0))
     # bounded sample per step, sized so that warmup + steps stay within a few minutes
     budget = 150.0 / max(1, args.steps + args.warmup)
@@ -250,42 +257,36 @@ def run_reference_arm(args):
     sample = (f"{count} planners x {iters} of {w['iter_num']} iterations of workload {w['name']} per step on {cores} host "
               f"threads, C port of the reference algorithm (the Python reference cannot travel to the GPU box)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": bench_config(w, P, max(1, int(os.environ.get("WORLD_SIZE", "1"))), args,
-                                   (w["max_nodes"] + 2 + max(256, w["max_nodes"] // 4)) if w["mode"] == "fn" else w["iter_num"] + 2),
+            "config": bench_config(w, P, world, args,
+                                   (w["max_nodes"] + 2 + max(256, w["max_nodes"] // 4)) if w["mode"] == "fn" else w["iter_num"] + 2, scaling),
             "edge_checks_per_sec": edge_total / dt,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    args = parse_args()
-    if os.environ.get("BENCH_DUMP_AFTER"):      # debugging aid: print every thread's Python stack if the run stalls
-        import faulthandler
-        faulthandler.dump_traceback_later(int(os.environ["BENCH_DUMP_AFTER"]), exit=True)
-    if args.impl == "reference":
-        return run_reference_arm(args)
+def planner_layout(args, world, rank):
+    """(planners of this rank, global index of its first planner, "strong" | "weak")."""
+    from rrt_star_fnd_algorithm_b200.parallel import shard_range
+    total = DEFAULT_PLANNERS[args.workload]
+    if args.planners:                                    # an explicit per-GPU batch: weak by definition
+        return args.planners, rank * args.planners, "weak"
+    if args.scaling == "strong" and total >= world and total % world == 0:
+        first, count = shard_range(total, rank, world)
+        return count, first, "strong"
+    return total, rank * total, "weak"                   # replicas (c1 / c4 hold a single planner) or --scaling weak
 
+
+def measure(args, w, P, first, dev, world, rank, steps, warmup, sample_clocks):
+    """Build this rank's batch of P planners (global indices first ..), run `warmup` + `steps` steps, return the device-timed
+    results: every rank returns the same max-over-ranks time and the all-reduced counters."""
     import torch
     import torch.distributed as dist
-    from rrt_star_fnd_algorithm_b200 import _abi, workloads as W
-    from rrt_star_fnd_algorithm_b200 import _structs as S
+    from rrt_star_fnd_algorithm_b200 import workloads as W
     from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
     from rrt_star_fnd_algorithm_b200.parallel import gather_results
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-
-    w, P = load_workload(args)
-    first = rank * P
     starts, goals, seeds, sids = W.planner_problems(w, first, P)
     kw = dict(obstacles=w["obstacles"], xy_range=w["xy_range"], iter_num=w["iter_num"], step_length=w["step_length"],
               radius=w["radius"], node_radius=w["node_radius"], bias=w["bias"], max_nodes=w["max_nodes"],
@@ -332,20 +333,20 @@ def main():
         if timed:
             kern_ms.append((e0, e1))
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(False)
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
+    clocks = ClockSampler(dev.index) if (sample_clocks and rank == 0) else None
+    if clocks:
         clocks.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(True)
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if clocks else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -360,7 +361,38 @@ def main():
                           pl["n_chain_hops"].sum(), pl["solution_found"].sum()], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats)
-    ext, edges, edges_ref, circles, attempts, scan_nodes, hops, solved = [float(v) for v in stats.tolist()]
+    return dict(b=b, kw=kw, pl=pl, ms=ms, clk=clk, stats=[float(v) for v in stats.tolist()],
+                k_ms=float(np.mean([a.elapsed_time(c) for a, c in kern_ms])),
+                replan_ms=float(np.mean([a.elapsed_time(c) for a, c in replan["ms"]])) if replan["ms"] else None,
+                replan_stats=replan["stats"])
+
+
+def main():
+    args = parse_args()
+    if os.environ.get("BENCH_DUMP_AFTER"):      # debugging aid: print every thread's Python stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_DUMP_AFTER"]), exit=True)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+
+    w, _ = load_workload(args)
+    P, first, scaling = planner_layout(args, world, rank)
+    is_c5 = w["name"] == "c5"
+    m = measure(args, w, P, first, dev, world, rank, args.steps, args.warmup, True)
+    b, pl, ms, clk = m["b"], m["pl"], m["ms"], m["clk"]
+    ext, edges, edges_ref, circles, attempts, scan_nodes, hops, solved = m["stats"]
     # the counters are totals of ONE step (state is re-initialised each step); the timed region holds `steps` of them
     rate = args.steps / (ms / 1e3)
 
@@ -368,50 +400,66 @@ def main():
     # part (its own planners, collectives inside), so this must come before the non-zero ranks leave
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e_c5(args, w, P, first, dev, kw) if is_c5 else run_e2e(args, w, P, first, b, dev)
+        e2e = run_e2e_c5(args, w, P, first, dev, m["kw"]) if is_c5 else run_e2e(args, w, P, first, b, dev)
 
+    # ---- rank 0: roofline of the fused planner kernel (its own launches; algorithmic bytes) and the
+    # parity spot check, while the headline batch is still alive
+    roofline = parity = None
+    capacity = b.prm.capacity
+    if rank == 0:
+        k_ms = m["k_ms"]
+        alg_bytes = 16.0 * pl["n_scan_nodes"].sum() + 12.0 * pl["n_chain_hops"].sum() + 32.0 * pl["iter"].sum()
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = alg_bytes / (k_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                # measured for the workload's default single-GPU launch only
+                traffic = json.load(open(tpath)).get(f"{args.workload}") if P == DEFAULT_PLANNERS[args.workload] and not args.iters else None
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "plan_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": peak_src,
+                    "note": "algorithmic bytes (16 B per node visited by a scan + 12 B per parent-chain hop + 32 B per insert) of rank "
+                            "0's launch over its CUDA-event time; the scans are served from L2 through the TMA ring (DRAM traffic is "
+                            "`traffic`), the kernel is bound by per-warp instruction latency, not by HBM (profiles/)"}
+        parity = spot_check(w, first, b)      # against the CPU oracle (not timed): planner 0 of this rank
+
+    # ---- the other scaling mode beside the headline (N > 1): a full workload-sized batch on every GPU
+    weak = None
+    if world > 1 and scaling == "strong":
+        total, n = DEFAULT_PLANNERS[args.workload], max(1, min(args.steps, 3))
+        del b
+        m["b"] = None
+        torch.cuda.empty_cache()
+        mw = measure(args, w, total, rank * total, dev, world, rank, n, 1, False)
+        wrate = n / (mw["ms"] / 1e3)
+        weak = {"value": mw["stats"][0] * wrate, "unit": UNIT, "planners_per_gpu": total, "steps": n, "ms_per_step": mw["ms"] / n,
+                "edge_checks_per_sec": mw["stats"][1] * wrate,
+                "note": "the same kernels with a full workload-sized batch on EVERY GPU (total work grows with N); device-timed, "
+                        "max over ranks"}
+        mw["b"] = None
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the fused planner kernel (rank 0's launches; algorithmic bytes)
-    k_ms = float(np.mean([a.elapsed_time(c) for a, c in kern_ms]))
-    alg_bytes = 16.0 * pl["n_scan_nodes"].sum() + 12.0 * pl["n_chain_hops"].sum() + 32.0 * pl["iter"].sum()
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = alg_bytes / (k_ms / 1e3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            # measured for the workload's default launch size only
-            traffic = json.load(open(tpath)).get(f"{args.workload}") if P == DEFAULT_PLANNERS[args.workload] and not args.iters else None
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "plan_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peak_src,
-                "note": "algorithmic bytes (16 B per node visited by a scan + 12 B per parent-chain hop + 32 B per insert) over "
-                        "the kernel time; the scans are served from L2 through the TMA ring (DRAM traffic is `traffic`), "
-                        "the kernel is bound by per-warp instruction latency, not by HBM (profiles/)"}
-
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline(w, args.cpu_seconds)
 
-    # parity spot check against the CPU oracle (not timed): planner 0 of this rank
-    parity = spot_check(w, first, b)
-
     line = {
         "metric": METRIC, "value": ext * rate,
         "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": bench_config(w, P, world, args, b.prm.capacity),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(w, P, world, args, capacity, scaling),
         "edge_checks_per_sec": edges * rate,
         "edge_checks_ref_equiv_per_sec": edges_ref * rate,
         "circle_tests_per_sec": circles * rate,
@@ -419,9 +467,11 @@ def main():
         "solved_planners": solved, "gpu_launches": 2 * args.steps,
         "roofline": roofline, "clocks": clk, "parity_spot_check": parity,
     }
+    if weak is not None:
+        line["weak_scaling"] = weak
     if is_c5:
-        st, rms = replan["stats"], float(np.mean([a.elapsed_time(c) for a, c in replan["ms"]]))
-        line["replanning"] = dict(st, ticks=w["ticks"], ms_per_step=rms, plan_ms_per_step=k_ms,
+        st, rms = m["replan_stats"], m["replan_ms"]
+        line["replanning"] = dict(st, ticks=w["ticks"], ms_per_step=rms, plan_ms_per_step=m["k_ms"],
                                   moves_per_sec=st["moves"] / (rms / 1e3), note="rank 0; one step = RRT*-FN planning "
                                   "(plan_kernel) + `ticks` replanning ticks (select_branch, valid_path, reconnect, regrow "
                                   "kernels; obstacle tables and per-planner ids cross the host every tick)")

@@ -166,6 +166,13 @@ typedef struct rrtfnd_node_grid {
     int32_t* cand;              /* [P][2*cand_cap] scratch */
 } rrtfnd_node_grid_t;
 
+/* Walk record of one node (rrtfnd_batch_t.walk). gp is only a hint: it is used when the parent's record confirms it. */
+typedef struct rrtfnd_walk {
+    double ecost;               /* = ecost[slot] */
+    int32_t parent;             /* = parent[slot] */
+    int32_t gp;                 /* guess of parent[parent[slot]], -1 = none */
+} rrtfnd_walk_t;
+
 /* Device-resident batch of P independent planners, structure-of-arrays, fixed capacity. */
 typedef struct rrtfnd_batch {
     int32_t n_planners;
@@ -184,6 +191,11 @@ typedef struct rrtfnd_batch {
     rrtfnd_trace_t* trace;      /* [P][trace_cap] or NULL */
     rrtfnd_obst_grid_t grid;    /* optional culling grid over obst */
     rrtfnd_node_grid_t node_grid; /* optional grid over the nodes (RRTFND_FLAG_NODE_GRID) */
+    rrtfnd_walk_t* walk;        /* [P][capacity] scratch of rrtfnd_plan_batch or NULL: a 16-byte copy of (ecost, parent) per node
+                                 * plus a self-healing guess of the grandparent slot, rebuilt from ecost / parent at the start of
+                                 * every call. Graph.get_cost's leaf -> root walk (src/graph.py:41-46) reads ONE record per hop
+                                 * and, while the guesses hold, fetches two hops per memory round trip. Never read by the host;
+                                 * ecost / parent stay the truth. NULL = walk the ecost / parent arrays. */
 } rrtfnd_batch_t;
 
 /* ---- library info ------------------------------------------------------------------------ */

@@ -82,6 +82,7 @@ class Batch(C.Structure):
         ("finish", C.c_void_p), ("best_path", C.c_void_p),
         ("obst", C.c_void_p), ("words", C.c_void_p), ("trace", C.c_void_p),
         ("grid", ObstGrid), ("node_grid", NodeGrid),
+        ("walk", C.c_void_p),
     ]
 
 

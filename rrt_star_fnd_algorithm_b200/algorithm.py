@@ -329,3 +329,261 @@ def through_obstacle_batch(p1, p2, obstacles) -> np.ndarray:
 def through_obstacle(line, obstacles: list) -> bool:
     """through_obstacle for one `Line`-like object with .p1 / .p2 (src/algorithm.py:581-591)."""
     return bool(through_obstacle_batch([line.p1], [line.p2], obstacles)[0])
+
+
+# ---- the reference's per-iteration helpers on Graph objects ------------------------------------------------------------
+# Users who drive the loop themselves (src/algorithm.py:139-149) call these directly. Each keeps the reference's
+# signature, return value and side effects on `G`; the work that dominates the reference's profile - every
+# through_obstacle call (74 % of its time), the visibility search of nearest_node_kdtree, the Graph.get_cost walks of the
+# candidates - runs on the GPU through the C-ABI operators (rrtfnd_edges_vs_circles, rrtfnd_nearest_visible,
+# rrtfnd_chain_cost); what stays on the host is the bookkeeping on the caller's own dictionaries and a handful of scalar
+# operations per call, written with the reference's expressions on the same number types.
+
+def _device_graph(G: Graph, obstacles: list):
+    """G uploaded as a one-planner batch (rows in ascending id): returns (batch, ids, slot_of)."""
+    from .batch import PlannerBatch
+    ids, xy, parent, cost, root_id = G._export()
+    b = PlannerBatch("star", starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
+                     obstacles=obstacles, xy_range=G.xy_range, iter_num=1, step_length=1.0, radius=1.0, node_radius=0.0,
+                     capacity=len(ids) + 2, path_cap=8, finish_cap=8, grid=False)
+    b.reset()
+    b.load_tree(0, ids, xy, parent, cost, root_id, G.last_id)
+    return b, ids, {int(i): k for k, i in enumerate(ids.tolist())}
+
+
+def _chain_costs(G: Graph, node_ids, obstacles=()) -> np.ndarray:
+    """Graph.get_cost for many nodes at once (src/graph.py:34-46): leaf -> root fp64 sums on the GPU, np.float64 each."""
+    import ctypes as C
+    import torch
+    from . import _abi
+    node_ids = [int(i) for i in node_ids]
+    if not node_ids:
+        return np.zeros(0, dtype=np.float64)
+    b, _, slot_of = _device_graph(G, list(obstacles))
+    sl = torch.tensor([slot_of[i] for i in node_ids], dtype=torch.int32, device=b.device)
+    pi = torch.zeros(len(node_ids), dtype=torch.int32, device=b.device)
+    out = torch.zeros(len(node_ids), dtype=torch.float64, device=b.device)
+    bt = b._batch()
+    _abi.check(_abi.lib.rrtfnd_chain_cost(C.byref(bt), b.prm.capacity, pi.data_ptr(), sl.data_ptr(), len(node_ids),
+                                          out.data_ptr(), b._stream()), "rrtfnd_chain_cost")
+    return out.cpu().numpy()
+
+
+def intersection_circle(line, circle: list) -> bool:
+    """Does the segment `line` (a Line-like object with .p1 / .p2) hit the circle `[(x, y), r]`? The reference's predicate
+    with all its quirks - infinite vertical lines, x-only strict between test (src/algorithm.py:555-578)."""
+    return bool(through_obstacle_batch([line.p1], [line.p2], [circle])[0])
+
+
+def steer(to_vertex: tuple, from_vertex: tuple, max_length: float) -> tuple:
+    """Point at most `max_length` from `from_vertex` towards `to_vertex`; `to_vertex` itself, untouched, when it is closer
+    (src/algorithm.py:731-746). Six scalar operations in the reference's order (the planner kernel does the same on the
+    device)."""
+    distance = calc_distance(to_vertex, from_vertex)
+    ux, uy = (to_vertex[0] - from_vertex[0]) / distance, (to_vertex[1] - from_vertex[1]) / distance
+    moved = (from_vertex[0] + ux * max_length, from_vertex[1] + uy * max_length)
+    return moved if distance > max_length else to_vertex
+
+
+def nearest_node_kdtree(G: Graph, vertex: tuple, obstacles: list, separate_tree_nodes: list = (), kdtree=None):
+    """Nearest node of G that sees `vertex`: (position as ndarray, id); a vertex that already exists is returned as is;
+    (np.array(vertex), None) when no node sees it (src/algorithm.py:666-699). The j-th-nearest-until-visible search runs on
+    the GPU over all of G's nodes (the reference builds `kdtree` from exactly those, :41-43; `separate_tree_nodes` is
+    ignored there as well)."""
+    import ctypes as C
+    import torch
+    from . import _abi
+    try:
+        return np.array(vertex), G.id_vertex[vertex]
+    except KeyError:
+        pass
+    b, ids, _ = _device_graph(G, obstacles)
+    q = torch.tensor([[float(vertex[0]), float(vertex[1])]], dtype=torch.float64, device=b.device)
+    slot = torch.zeros(1, dtype=torch.int32, device=b.device)
+    bt = b._batch()
+    _abi.check(_abi.lib.rrtfnd_nearest_visible(C.byref(bt), b.prm.capacity, q.data_ptr(), b.prm.n_obst, slot.data_ptr(), None,
+                                               b._stream()), "rrtfnd_nearest_visible")
+    k = int(slot.item())
+    if k < 0:
+        return np.array(vertex), None
+    node = int(ids[k])
+    return np.array(G.vertices[node], dtype=np.float64), node
+
+
+def nearest_node(G: Graph, vertex: tuple, obstacles: list, separate_tree_nodes: list = ()):
+    """Brute-force twin (src/algorithm.py:702-728): among the nodes outside `separate_tree_nodes` whose
+    Line(node, vertex) is free, the closest by calc_distance, first in dictionary order on ties; (None, None) if there
+    is none. All the segment tests are one GPU call."""
+    try:
+        return vertex, G.id_vertex[vertex]
+    except KeyError:
+        pass
+    cand = [(i, v) for i, v in G.vertices.items() if i not in separate_tree_nodes]
+    if not cand:
+        return None, None
+    blocked = through_obstacle_batch([v for _, v in cand], [vertex] * len(cand), obstacles)
+    best, best_id, best_pos = float("inf"), None, None
+    for (i, v), hit in zip(cand, blocked):
+        if hit:
+            continue
+        d = calc_distance(v, vertex)
+        if d < best:
+            best, best_id, best_pos = d, i, v
+    return best_pos, best_id
+
+
+def new_node(G: Graph, map: Map, obstacles: list, step_length: float, bias: float):
+    """One attempt of the planners (src/algorithm.py:36-51): sample, reject if occupied, nearest visible node, steer,
+    add the vertex. Returns (q_new, id_new, id_near, distance) or four Nones."""
+    q_rand = G.random_node(bias=bias)
+    if map.is_occupied_c(q_rand):
+        return None, None, None, None
+    q_near, id_near = nearest_node_kdtree(G, q_rand, obstacles)
+    if q_near is None or (q_rand == q_near).all():
+        return None, None, None, None
+    q_new = steer(q_rand, q_near, step_length)
+    id_new = G.add_vertex(q_new)
+    return q_new, id_new, id_near, calc_distance(q_new, q_near)
+
+
+def _ball_candidates(G: Graph, q_new, radius, kdtree):
+    """(ids, positions, np.linalg.norm distances) of the caller's ball query, in the caller's k-d tree's own order - the
+    order choose_parent_kdtree's result depends on (src/algorithm.py:837-842)."""
+    i = kdtree.query_ball_point(q_new, r=radius)
+    pos = kdtree.data[i]
+    ids = [G.id_vertex[p[0], p[1]] for p in pos]
+    return ids, pos, np.linalg.norm(pos - q_new, axis=1)
+
+
+def choose_parent_kdtree(G: Graph, q_new: tuple, id_new: int, best_edge: tuple, radius: float, obstacles: list,
+                         separate_tree_nodes: list = (), kdtree=None) -> tuple:
+    """The edge (id_new, parent, cost) the reference returns (src/algorithm.py:822-852), including its side effect: each
+    accepted candidate overwrites G.cost[id_new] while G.parent[id_new] stays, so later comparisons mix the new edge
+    with the old chain. Segment tests and the candidates' get_cost walks run on the GPU."""
+    ids, pos, costs = _ball_candidates(G, q_new, radius, kdtree)
+    if not ids:
+        return best_edge
+    blocked = through_obstacle_batch(pos, [q_new] * len(ids), obstacles)
+    walk_on_host = len(G.children.get(id_new, ())) > 0          # id_new above a candidate: its chain changes as we go
+    chain = None if walk_on_host else _chain_costs(G, ids)
+    for k, (id_ver, cost) in enumerate(zip(ids, costs)):
+        if blocked[k] or id_ver == id_new:               # the ball holds q_new itself: x > x + 0 is never true (:848)
+            continue
+        via = (G.get_cost(id_ver) if walk_on_host else chain[k]) + cost
+        if G.get_cost(id_new) > via:
+            G.cost[id_new] = cost
+            best_edge = (id_new, id_ver, cost)
+    return best_edge
+
+
+def choose_parent(G: Graph, q_new: tuple, id_new: int, best_edge: tuple, radius: float, obstacles: list,
+                  separate_tree_nodes: list = ()) -> tuple:
+    """Brute-force twin (src/algorithm.py:855-879): every vertex in dictionary order, calc_distance rounded to three
+    decimals against the radius."""
+    cand = [(i, v, calc_distance(q_new, v)) for i, v in G.vertices.items() if i != id_new]
+    cand = [c for c in cand if not round(c[2], 3) > radius]
+    if not cand:
+        return best_edge
+    blocked = through_obstacle_batch([v for _, v, _ in cand], [q_new] * len(cand), obstacles)
+    walk_on_host = len(G.children.get(id_new, ())) > 0
+    chain = None if walk_on_host else _chain_costs(G, [i for i, _, _ in cand])
+    for k, (id_ver, _, d) in enumerate(cand):
+        if blocked[k]:
+            continue
+        via = (G.get_cost(id_ver) if walk_on_host else chain[k]) + d
+        if G.get_cost(id_new) > via:
+            G.cost[id_new] = d
+            best_edge = (id_new, id_ver, d)
+    return best_edge
+
+
+def _rewire_apply(G: Graph, id_new: int, cand, blocked):
+    """Re-parent under id_new every free candidate whose cost-to-come improves (src/algorithm.py:905-910, :926-935).
+    Decisions are taken against the tree as it is before the call: a candidate's chain only changes when one of its
+    ancestors is re-parented, and that only ever lowers its cost further below the threshold that was not met."""
+    free = [k for k in range(len(cand)) if not blocked[k]]
+    if not free:
+        return
+    costs = _chain_costs(G, [cand[k][0] for k in free] + [id_new])
+    c_new = costs[-1]
+    for k, c_ver in zip(free, costs[:-1]):
+        id_ver, d = cand[k][0], cand[k][1]
+        if c_ver > c_new + d:
+            parent = G.parent[id_ver]
+            G.children[parent].remove(id_ver)
+            G.parent[id_ver] = id_new
+            G.children[id_new].append(id_ver)
+            G.cost[id_ver] = d
+
+
+def rewire_kdtree(G: Graph, q_new: tuple, id_new: int, radius: float, obstacles: list, kdtree=None):
+    """Rewire step of RRT* over the caller's ball query (src/algorithm.py:882-910)."""
+    ids, pos, costs = _ball_candidates(G, q_new, radius, kdtree)
+    if not ids:
+        return
+    blocked = through_obstacle_batch(pos, [q_new] * len(ids), obstacles)
+    blocked = [bool(h) or i == id_new for h, i in zip(blocked, ids)]       # the new node itself never passes the strict test
+    _rewire_apply(G, id_new, list(zip(ids, costs)), blocked)
+
+
+def rewire(G: Graph, q_new: tuple, id_new: int, radius: float, obstacles: list):
+    """Brute-force twin (src/algorithm.py:913-935): every vertex but the start node and the new one, calc_distance
+    against the radius."""
+    root = G.id_vertex[G.start]
+    cand = [(i, calc_distance(q_new, v), v) for i, v in G.vertices.items() if i != root and i != id_new]
+    cand = [c for c in cand if not c[1] > radius]
+    if not cand:
+        return
+    blocked = through_obstacle_batch([v for _, _, v in cand], [q_new] * len(cand), obstacles)
+    _rewire_apply(G, id_new, cand, blocked)
+
+
+def forced_removal(G: Graph, id_new: int, path: list) -> int:
+    """Delete a random childless node other than id_new and the goal-side end of `path`; returns its id
+    (src/algorithm.py:800-819). Draws from the global `random` exactly like the reference (random.choice per draw)."""
+    keep = path[0] if path else -1
+    childless = [node for node, children in G.children.items() if len(children) == 0]
+    victim = random.choice(childless)
+    while victim == id_new or victim == keep:
+        victim = random.choice(childless)
+    G.remove_vertex(victim)
+    return victim
+
+
+def remove_children(G: Graph, id_node: int, path: list) -> None:
+    """Delete every descendant of id_node that hangs off a child outside `path` (src/algorithm.py:328-341); children on
+    the path, and what hangs below them, stay."""
+    stack = [c for c in G.children[id_node] if c not in path]
+    order = []
+    while stack:                                    # subtree of each off-path child, parents before children
+        n = stack.pop()
+        order.append(n)
+        stack.extend(c for c in G.children[n] if c not in path)
+    for n in reversed(order):                       # leaves first, as the recursion deletes them; an off-path node goes
+        G.remove_vertex(n)                          # even when an on-path child of it stays behind (as in the reference)
+
+
+def check_for_tree_associativity(G: Graph, root_node: int, node_to_check: int) -> bool:
+    """Does node_to_check hang (through any number of parents) from root_node? (src/algorithm.py:407-420)"""
+    node = node_to_check
+    while G.parent[node] is not None:
+        node = G.parent[node]
+    return node == root_node
+
+
+def get_distance_dict(G: Graph, node_to_check: int, indeces_to_check: list = None) -> dict:
+    """{id: distance to node_to_check} for every vertex with the reference's expansion sqrt(|x|^2 - 2 x.y + |y|^2)
+    (src/algorithm.py:938-951; cancellation can make an entry NaN, as there). The third parameter is unused in the
+    reference as well; it gets a default here because get_near_nodes calls the function without it (:431)."""
+    pts = np.array([v for v in G.vertices.values()])
+    q = np.array(G.vertices[node_to_check]).reshape(-1, 2)
+    x2 = np.sum(pts ** 2, axis=1).reshape(-1, 1)
+    y2 = np.sum(q ** 2, axis=1).reshape(-1, 1)
+    d = np.sqrt(x2 - 2 * np.matmul(pts, q.T) + y2.T)
+    return {i: row[0] for i, row in zip(G.vertices, d)}
+
+
+def get_near_nodes(G: Graph, node_to_check: int, radius: float, root_node: int) -> list:
+    """Ids within `radius` of node_to_check that belong to the tree rooted at root_node (src/algorithm.py:423-434)."""
+    return [i for i, d in get_distance_dict(G, node_to_check).items()
+            if d <= radius and check_for_tree_associativity(G, root_node, i)]

@@ -114,6 +114,7 @@ class PlannerBatch:
         self.nchild = torch.empty((P, Cn), dtype=torch.int32, device=dev)
         self.id = torch.empty((P, Cn), dtype=torch.int32, device=dev)
         self.nflags = torch.zeros((P, Cn), dtype=torch.uint8, device=dev)
+        self.walk = torch.empty((P, Cn, 2), dtype=torch.float64, device=dev)     # rrtfnd_walk_t scratch of the planner kernel
         self.finish = torch.empty((P, prm.finish_cap), dtype=torch.int32, device=dev)
         self.best_path_t = torch.empty((P, prm.path_cap), dtype=torch.int32, device=dev)
         self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(dev)
@@ -168,6 +169,7 @@ class PlannerBatch:
         b.obst = self.obst.data_ptr()
         b.words = self.words.data_ptr() if self.words is not None else None
         b.trace = self.trace_t.data_ptr() if self.trace_t is not None else None
+        b.walk = self.walk.data_ptr() if self.walk is not None else None
         return b
 
     def _stream(self):
@@ -223,6 +225,7 @@ class PlannerBatch:
             new = torch.zeros((self.P, capacity) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
             new[:, :old] = t
             setattr(self, name, new)
+        self.walk = torch.empty((self.P, capacity, 2), dtype=torch.float64, device=self.device)
         self.prm.capacity = capacity
 
     def restore_problems(self):
@@ -238,6 +241,7 @@ class PlannerBatch:
         for name in ("xy", "ecost", "parent", "nchild", "id", "nflags"):
             t = getattr(self, name)
             setattr(self, name, torch.zeros((self.P, int(capacity)) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device))
+        self.walk = torch.empty((self.P, int(capacity), 2), dtype=torch.float64, device=self.device)
         self.prm.capacity = int(capacity)
         self._initialised = False
 

@@ -19,6 +19,7 @@
 // and its culling grid (grid.cuh) are shared by all planners and stay L1 resident.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/rrtfnd.h"
 #include "arith.cuh"
@@ -55,6 +56,15 @@
 #ifndef RRTFND_LANE_MIN_HINT
 #define RRTFND_LANE_MIN_HINT 0
 #endif
+// Candidate chunks of the near set: 1 = each lane's segment test and parent-chain walk run in ONE loop over the walk records
+// (seg_walk_lane), and choose-parent's re-summed chain is prepared by all lanes at once; 0 = round 1's separate loops.
+#ifndef RRTFND_FUSED_WALK
+#define RRTFND_FUSED_WALK 1
+#endif
+// resident warps per SM the lean instances' register allocation admits: 16 -> 128 registers, 20 -> 96, 24 -> 80
+#ifndef RRTFND_LEAN_MINW
+#define RRTFND_LEAN_MINW 16
+#endif
 
 // Diagnostic build (-DRRTFND_PHASE_CLOCKS): lane 0 of every warp accumulates clock64() deltas per phase of the iteration,
 // summed over the grid into g_phase_clocks and read back by rrtfnd_debug_phase_clocks(). Not compiled into the product.
@@ -87,12 +97,21 @@ struct SampleBatch {
     int last_goal;             // the last valid entry is a goal-bias hit (2 words instead of 6)
 };
 
-// shared memory of one warp: xy ring (n_stages tiles) | mbarriers | word source | attempt batch | chain[kChainCap] | stage[kStage] |
-// rwlist[near_cap] (re-parented slots of one iteration; overflow goes to nflags) | live bitmap + prefix counts (compaction)
+// shared memory of one warp: xy ring (n_stages tiles) | attempt batch | chain[kChainCap] | stage[kStage] | rwlist[near_cap]
+// (re-parented slots of one iteration; overflow goes to nflags) | mbarriers | word source | [live bitmap + prefix counts].
+// The compaction's live bitmap and prefix counts are only alive inside compact_tree(), at an attempt boundary, when the
+// ring, the attempt batch and the per-iteration scratch hold nothing: they ALIAS that region (scratch_bytes) when they fit
+// and get their own space behind the word source otherwise. Every kilobyte not allocated here is L1 for the tree gathers.
+__host__ __device__ inline size_t scratch_bytes(const rrtfnd_params_t& prm, int n_stages) {
+    return (size_t)n_stages * kTileBytes + align_up(sizeof(SampleBatch), 16) + kChainCap * 8 + kStage * 4 +
+           align_up((size_t)prm.near_cap * 4, 16);
+}
+__host__ __device__ inline size_t compact_bytes(const rrtfnd_params_t& prm) {
+    return can_compact(prm) ? 2 * align_up((size_t)bitmap_words(prm) * 4, 16) : 0;
+}
 __host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
-    size_t o = (size_t)n_stages * kTileBytes + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) +
-               align_up(sizeof(SampleBatch), 16) + kChainCap * 8 + kStage * 4 + align_up((size_t)prm.near_cap * 4, 16);
-    if (can_compact(prm)) o += 2 * align_up((size_t)bitmap_words(prm) * 4, 16);
+    size_t o = scratch_bytes(prm, n_stages) + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16);
+    if (compact_bytes(prm) > scratch_bytes(prm, n_stages)) o += compact_bytes(prm);
     return align_up(o, 128);
 }
 
@@ -213,6 +232,124 @@ __device__ __forceinline__ double path_cost(const int32_t* parent, const double*
     int n = from;
     while (n != root && n >= 0) { cost = dadd(cost, ecost[n]); n = parent[n]; ++hops; }
     return cost;
+}
+
+// ---- walk records (rrtfnd_batch_t.walk): one 16-byte record per node = (ecost, parent, grandparent guess) --------------
+// Graph.get_cost (src/graph.py:41-46) is a pointer chase: ~40 dependent hops per candidate, each a round trip to L2 or
+// HBM. The record packs what one hop needs into ONE 16-byte load, and its third field lets a walk request the parent's
+// and the grandparent's records together: when the parent's record confirms the guess, two hops cost one round trip.
+// The guess is only a hint - re-parenting a node leaves its children's guesses stale; a walk that finds one wrong takes
+// the slow step and repairs it - so results never depend on it. ecost[] / parent[] stay the truth (ABI, FND operators).
+struct WRec { double ecost; int parent; int gp; };
+__device__ __forceinline__ WRec wrec_load(const rrtfnd_walk_t* W, int s) {
+    const double2 v = *reinterpret_cast<const double2*>(W + s);
+    WRec r; r.ecost = v.x;
+    const long long b = __double_as_longlong(v.y);
+    r.parent = (int)(unsigned)(b & 0xffffffffll); r.gp = (int)(b >> 32);
+    return r;
+}
+__device__ __forceinline__ void wrec_store(rrtfnd_walk_t* W, int s, double ecost, int parent, int gp) {
+    const long long b = ((long long)gp << 32) | (unsigned)parent;
+    *reinterpret_cast<double2*>(W + s) = make_double2(ecost, __longlong_as_double(b));
+}
+// records of slots [0, n_slots) from the truth arrays (start of a call, after a compaction)
+static __device__ __noinline__ void wrec_rebuild(rrtfnd_walk_t* W, const int32_t* PARENT, const double* ECOST, int n_slots, int lane) {
+    for (int s = lane; s < n_slots; s += 32) {
+        const int p = PARENT[s];
+        wrec_store(W, s, ECOST[s], p, p >= 0 ? PARENT[p] : -1);
+    }
+    __syncwarp();
+}
+
+// One lane's share of a candidate chunk: through_obstacle(Line(p1, p2)) over the culled circles of ITS segment (as
+// seg_blocked with first = 0, stride = 1) fused with ITS parent-chain walk (Graph.get_cost). One loop step = at most one
+// circle test and one walk round; the round's two record loads are issued before the circle's arithmetic and consumed after
+// it, so the pointer chase's memory latency hides behind the divisions and square roots of the segment test (and the other
+// way round). A hit abandons the walk (its sum is never used). `acc` starts as the caller's running sum; `rec_chain`
+// (one lane per chunk at most) receives the addends in order. Returns (circle tests << 1) | hit; depth = hops walked.
+__device__ __forceinline__ int seg_walk_lane(const double2* __restrict__ tab, const rrtfnd_obst_grid_t* __restrict__ g, int M,
+                                             int full_cells, bool has_seg, double p1x, double p1y, double p2x, double p2y,
+                                             rrtfnd_walk_t* W, int w_from, double* rec_chain, double& acc, int& depth) {
+    // ---- segment set-up (identical to seg_blocked)
+    Seg sg = make_seg(p1x, p1y, p2x, p2y);
+    int cy = 0, cy1 = -1, nx = 0;
+    double x0 = 0, y0 = 0, inv = 0, cell = 0, slack = 0, dxdy = 0;
+    const double ylo = p1y < p2y ? p1y : p2y, yhi = p1y < p2y ? p2y : p1y;
+    bool cull = false, flat = true, multi = false;
+    if (has_seg) {
+        cy1 = 0;                                             // one pseudo-row holding the whole table
+        if (full_cells > 0 && !sg.vertical && fabs(sg.m) <= g->slope_max) {
+            x0 = g->x0; y0 = g->y0; inv = g->inv_cell;
+            nx = g->nx;
+            cy = grid_cell(ylo, y0, inv, g->ny);
+            cy1 = grid_cell(yhi, y0, inv, g->ny);
+            multi = cy1 > cy;
+            cell = 1.0 / inv;
+            slack = g->coord_max * 1e-9;
+            dxdy = (p2x - p1x) / (p2y - p1y);
+            flat = !(fabs(dxdy) < 1e300);
+            cull = true;
+        }
+    }
+    const int32_t* __restrict__ start = g->seg_start;
+    const int32_t* __restrict__ items = g->seg_items;
+    int j = 0, e = 0, tests = 0;
+    bool seg_live = has_seg, hit = false;
+    // ---- walk set-up: v = node whose edge is added next, rv = its record
+    depth = 0;
+    int v = w_from;
+    WRec rv; rv.ecost = 0.0; rv.parent = -1; rv.gp = -1;
+    if (v >= 0) rv = wrec_load(W, v);
+    bool walking = rv.parent >= 0;
+    while (seg_live || walking) {
+        WRec rp, rg;
+        rp.ecost = 0.0; rp.parent = -1; rp.gp = -1; rg = rp;
+        if (walking) {                                       // issued now, consumed after the circle test
+            rp = wrec_load(W, rv.parent);
+            if (rv.gp >= 0) rg = wrec_load(W, rv.gp);
+        }
+        if (seg_live) {
+            if (j >= e) {                                    // next row of cells (or the end of the segment)
+                if (cy > cy1) seg_live = false;
+                else {
+                    j = 0; e = M;
+                    if (cull) {
+                        double xa = sg.lo, xb = sg.hi;
+                        if (multi && !flat) {
+                            const double ra = fmax(y0 + cy * cell - slack, ylo), rb = fmin(y0 + (cy + 1) * cell + slack, yhi);
+                            const double xs = p1x + (ra - p1y) * dxdy, xe = p1x + (rb - p1y) * dxdy;
+                            xa = fmax(sg.lo, fmin(xs, xe) - slack);
+                            xb = fmin(sg.hi, fmax(xs, xe) + slack);
+                        }
+                        const int cx0 = grid_cell(xa, x0, inv, nx), cx1 = grid_cell(xb, x0, inv, nx);
+                        j = RRTFND_TAB_LD(start + cy * nx + cx0);
+                        e = RRTFND_TAB_LD(start + cy * nx + cx1 + 1);
+                    }
+                    ++cy;
+                }
+            } else {
+                double ox, oy, r, K;
+                load_obst(tab, cull ? RRTFND_TAB_LD(items + j) : j, ox, oy, r, K);
+                ++j; ++tests;
+                if (seg_hits_circle(sg, ox, oy, r, K)) { hit = true; seg_live = false; walking = false; }
+            }
+        }
+        if (walking) {
+            if (rec_chain && depth < kChainCap) rec_chain[depth] = rv.ecost;
+            acc = dadd(acc, rv.ecost); ++depth;
+            if (rp.parent >= 0 && rv.gp == rp.parent) {      // the guess holds: the parent's edge as well, on to the grandparent
+                if (rec_chain && depth < kChainCap) rec_chain[depth] = rp.ecost;
+                acc = dadd(acc, rp.ecost); ++depth;
+                v = rv.gp; rv = rg;
+            } else {
+                if (rp.parent >= 0) wrec_store(W, v, rv.ecost, rv.parent, rp.parent);   // repair the hint (a benign same-value race)
+                v = rv.parent; rv = rp;
+            }
+            walking = rv.parent >= 0;
+        }
+    }
+    if (hit) depth = 0;
+    return (tests << 1) | (hit ? 1 : 0);
 }
 
 // ---- rare paths, kept out of line so that the per-iteration code stays small ---------------------------------
@@ -419,6 +556,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     int32_t* FINISH = bt.finish + (size_t)p * prm.finish_cap;
     int32_t* BPATH = bt.best_path + (size_t)p * prm.path_cap;
     rrtfnd_planner_t* PL = bt.planners + p;
+    rrtfnd_walk_t* WREC = bt.walk + (size_t)p * C;
     constexpr bool kLean = MODE >= 0;
     // Prepared attempt batches pay where rejected attempts are frequent and nothing else draws from the stream between
     // attempts; RRT*-FN draws in forced_removal after every extension once the cap is reached, which discards the batch
@@ -431,18 +569,20 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     const int n_stages = prm.reserved;                 // resolved by the host wrapper (2 or 4)
     unsigned char* ws = warp_base + (size_t)wib * warp_smem_bytes(prm, n_stages);
     unsigned char* wp = ws + (size_t)n_stages * kTileBytes;
-    XYStream xs;
-    stream_init(xs, ws, wp, n_stages, lane);
-    wp += align_up((size_t)n_stages * 8, 16);
-    WordSrc& rng = *reinterpret_cast<WordSrc*>(wp);    // identical values written by every lane
-    wp += align_up(sizeof(WordSrc), 16);
     SampleBatch& sb = *reinterpret_cast<SampleBatch*>(wp);   // prepared attempts; identical scalars written by every lane
     wp += align_up(sizeof(SampleBatch), 16);
     double* chain = reinterpret_cast<double*>(wp);     // edge costs along the new node's parent chain, leaf side first
     wp += kChainCap * 8;
     int* stage = reinterpret_cast<int*>(wp);
     int* rwlist = stage + kStage;
-    uint32_t* bm = reinterpret_cast<uint32_t*>(rwlist + align_up((size_t)prm.near_cap * 4, 16) / 4);
+    wp = reinterpret_cast<unsigned char*>(rwlist + align_up((size_t)prm.near_cap * 4, 16) / 4);
+    XYStream xs;
+    stream_init(xs, ws, wp, n_stages, lane);
+    wp += align_up((size_t)n_stages * 8, 16);
+    WordSrc& rng = *reinterpret_cast<WordSrc*>(wp);    // identical values written by every lane
+    wp += align_up(sizeof(WordSrc), 16);
+    // compaction scratch: over the (then idle) ring / batch / scratch region when it fits, else its own space
+    uint32_t* bm = reinterpret_cast<uint32_t*>(compact_bytes(prm) > scratch_bytes(prm, n_stages) ? wp : ws);
     uint32_t* pre = bm + align_up((size_t)bitmap_words(prm) * 4, 16) / 4;
 
     const Obst ob = make_obst(obst_tab, prm.n_obst, obst_grid);
@@ -478,6 +618,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0;
     sb.pos = 0; sb.len = 0;
     __syncwarp();
+#if RRTFND_FUSED_WALK
+    wrec_rebuild(WREC, PARENT, ECOST, PL->n_slots, lane);
+#endif
 
     // slot of the cached best path's leaf (ids ascend with slots: binary search around tombstones)
     int best_leaf_slot = -1;
@@ -530,6 +673,11 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             compact_tree(XY, ECOST, PARENT, NCHILD, ID, NFLAG, FINISH, n_finish, n_slots, bm, pre, &root_slot, &best_leaf_slot, lane);
             n_slots = n_live;
             ++n_compactions;
+            sb.pos = 0; sb.len = 0;       // the bitmap may have lain over the prepared attempts: prepare them again
+            __syncwarp();
+#if RRTFND_FUSED_WALK
+            wrec_rebuild(WREC, PARENT, ECOST, n_slots, lane);
+#endif
         }
         // ================================================================ A/B. Graph.random_node (src/graph.py:96-98) and
         // Map.is_occupied_c (src/map.py:38-47; rejection at src/algorithm.py:39-40)
@@ -750,6 +898,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             XY[new_slot] = make_double2(px, py);
             ID[new_slot] = id_new; PARENT[new_slot] = near_slot; ECOST[new_slot] = e0;   // :141-142
             NCHILD[new_slot] = 0; NFLAG[new_slot] = 0;
+#if RRTFND_FUSED_WALK
+            wrec_store(WREC, new_slot, e0, near_slot, PARENT[near_slot]);
+#endif
             if (NG) {                                                             // push onto its cell's list
                 const int c = grid_cell(py, ng.y0, ng.inv_cell, ng.ny) * ng.nx + grid_cell(px, ng.x0, ng.inv_cell, ng.nx);
                 NEXT[new_slot] = HEAD[c]; HEAD[c] = new_slot;
@@ -844,6 +995,29 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     const int n = min(count - head, first ? 31 : 32);
                     __syncwarp();
                     // ---- one chunk: lane i < n owns candidate i; in the first chunk lane 31 walks the new node's chain
+#if RRTFND_FUSED_WALK
+                    int s = -1; double dpl = 0.0, cc = 0.0, c_x = 0.0, c_y = 0.0;
+                    const bool mine = lane < n;
+                    if (mine) {
+                        s = stage[head + lane];
+                        const double2 c = XY[s];
+                        c_x = c.x; c_y = c.y;
+                        dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
+                        if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
+                    }
+                    // Line(node, q_new): p1 = node (:846 / :903) and Graph.get_cost(id) (:848 / :905) in one loop; lane 31 of the
+                    // first chunk walks the new node's chain from its parent, starts from its edge cost and records the addends
+                    const bool rec = first && lane == 31;
+                    int w_from = s, depth = 0;
+                    if (rec) { w_from = walk_from; cc = walk_acc; }
+                    const int r = seg_walk_lane(ob.tab, ob.g, ob.M, ob.full_cells, mine, c_x, c_y, px, py, WREC, w_from,
+                                                rec ? chain : nullptr, cc, depth);
+                    my_tests += r >> 1;
+                    my_hops += depth;
+                    const bool hit = !mine || (r & 1);
+                    __syncwarp();
+                    PH_MARK(6);                                                   // per-candidate segment tests + parent-chain walks
+#else
                     int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
                     int w_from = -1;
                     if (lane < n) {
@@ -895,10 +1069,34 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     }
                     __syncwarp();
                     PH_MARK(7);                                                   // parent-chain walks
+#endif
                     if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; chain_depth = __shfl_sync(kFull, depth, 31); }
                     if (do_cp) {
                         // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
                         unsigned open = __ballot_sync(kFull, lane < n && !hit);
+#if RRTFND_FUSED_WALK
+                        // An accepted candidate sets G.cost[id_new] = its distance with the parent untouched, so get_cost(id_new)
+                        // becomes that distance summed along id_near's chain (:849) - a value that depends on the candidate
+                        // alone, not on the acceptances before it: every lane prepares its own, then the sequential pass over
+                        // the candidates is a compare and a select per candidate.
+                        double resum = dpl;
+                        if (open && chain_depth <= kChainCap)
+                            for (int h = 0; h < chain_depth; ++h) resum = dadd(resum, chain[h]);
+                        const double via = dadd(cc, dpl);
+                        while (open) {
+                            const int i = __ffs(open) - 1;
+                            open &= open - 1;
+                            if (cp_cn > __shfl_sync(kFull, via, i)) {
+                                cp_slot = __shfl_sync(kFull, s, i); cp_cost = __shfl_sync(kFull, dpl, i);
+                                if (chain_depth <= kChainCap) cp_cn = __shfl_sync(kFull, resum, i);
+                                else {
+                                    long long h = 0;
+                                    cp_cn = chain_walk(PARENT, ECOST, near_slot, cp_cost, h);   // every lane walks the same chain
+                                    if (lane == 0) my_hops += h;
+                                }
+                            }
+                        }
+#else
                         while (open) {
                             const int i = __ffs(open) - 1;
                             open &= open - 1;
@@ -916,6 +1114,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                                 }
                             }
                         }
+#endif
                     }
                     if (do_rw) {
                         const bool rw = lane < n && !hit && cc > dadd(cost_new, dpl);   // :905, strict
@@ -942,7 +1141,12 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             }
 
             if (pass == 0 && commit_cp && k_total > 0) {   // EXTENSION (not the shipped behaviour): adopt the returned edge
-                if (lane == 0) { PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost; }
+                if (lane == 0) {
+                    PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost;
+#if RRTFND_FUSED_WALK
+                    wrec_store(WREC, new_slot, cp_cost, cp_slot, PARENT[cp_slot]);
+#endif
+                }
                 __syncwarp();
             }
         }
@@ -959,12 +1163,17 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         {
             int d_childless = 0, flagged = 0;
             if (lane == 0) {
+                const int new_parent = PARENT[new_slot];
                 auto reparent = [&](int s) {
                     const int oldp = PARENT[s];
                     if (--NCHILD[oldp] == 0) ++d_childless;
                     const double2 v = XY[s];
                     PARENT[s] = new_slot;
-                    ECOST[s] = dist_plain(v.x, v.y, px, py);
+                    const double ec = dist_plain(v.x, v.y, px, py);
+                    ECOST[s] = ec;
+#if RRTFND_FUSED_WALK
+                    wrec_store(WREC, s, ec, new_slot, new_parent);            // its children keep a stale hint until a walk repairs it
+#endif
                     flagged |= NFLAG[s] & 1;
                 };
                 const int n_list = n_rw < prm.near_cap ? n_rw : prm.near_cap;
@@ -1181,6 +1390,10 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
+    if (const char* cv = getenv("RRTFND_CARVEOUT")) {   // experiment: shared-memory carve-out in percent (the rest of the 256 KB is L1)
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+        if (e != cudaSuccess) return (int)e;
+    }
 #if RRTFND_SMEM_TABLES
     {
         int dev = 0, sms = 148, per_sm = 1;
@@ -1237,6 +1450,9 @@ static int check_params(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
     if ((prm->flags & RRTFND_FLAG_TRACE) && (!bt->trace || prm->trace_cap < 1)) return RRTFND_E_BADARG;
     if (!bt->planners || !bt->xy || !bt->ecost || !bt->parent || !bt->nchild || !bt->id || !bt->nflags || !bt->finish ||
         !bt->best_path || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
+#if RRTFND_FUSED_WALK
+    if (!bt->walk) return RRTFND_E_BADARG;
+#endif
     if (bt->grid.nx > 0 && (!bt->grid.seg_start || !bt->grid.seg_items || !bt->grid.pt_start || !bt->grid.pt_items ||
                             bt->grid.ny <= 0)) return RRTFND_E_BADARG;
     return 0;
@@ -1291,10 +1507,10 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<8, 16, false, RRTFND_MODE_FN, true>(&q, &b, st)
                                                       : launch_plan<8, 16, false, RRTFND_MODE_FN, false>(&q, &b, st);
 #endif
-    if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<1, 16, false, RRTFND_MODE_STAR, true>(&q, &b, st)
-                                                        : launch_plan<1, 16, false, RRTFND_MODE_STAR, false>(&q, &b, st);
-    if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<1, 16, false, RRTFND_MODE_FN, true>(&q, &b, st)
-                                                      : launch_plan<1, 16, false, RRTFND_MODE_FN, false>(&q, &b, st);
+    if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, true>(&q, &b, st)
+                                                        : launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, false>(&q, &b, st);
+    if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_FN, true>(&q, &b, st)
+                                                      : launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_FN, false>(&q, &b, st);
     switch (cfg.wpb) {
         case 1: return launch_wpb<1>(&q, &b, cfg.minw, st);
         case 2: return launch_wpb<2>(&q, &b, cfg.minw, st);
