@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c2r", "c3", "c4", "c5"])
     ap.add_argument("--planners", type=int, default=0, help="planners per GPU (weak scaling; 0 = the workload's own count, see --scaling)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the workload's planners sharded over the GPUs (config as written); weak: that many on every GPU")
@@ -60,7 +60,7 @@ def parse_args():
 # default planners per GPU. c3 at N=1 is BASELINE.json's config 3 as written (16,384 planners on one B200, 3 GB of tree
 # state); with weak scaling every further GPU gets a batch of the same size. 16,384 planners are ~7 waves of resident
 # warps per SM, which also evens out the planner-to-planner variance that leaves SMs idle at the end of a 1-wave launch.
-DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c3": 16384, "c4": 1, "c5": 4096}
+DEFAULT_PLANNERS = {"c1": 1, "c2": 4096, "c2r": 4096, "c3": 16384, "c4": 1, "c5": 4096}
 
 
 class ClockSampler:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RRTFND_ABI_VERSION 2
+#define RRTFND_ABI_VERSION 3
 
 /* planner kinds: src/algorithm.py:55 (RRT), :98 (RRT_star), :190 (RRT_star_FN) */
 #define RRTFND_MODE_RRT 0
@@ -216,6 +216,22 @@ int rrtfnd_obst_grid_build_host(const double* obst_host, int32_t n_obst, double 
                                 double hi_x, double lo_y, double hi_y, double cell, rrtfnd_obst_grid_t* grid_out,
                                 int32_t* seg_start_host, int32_t* seg_items_host, int32_t* pt_start_host,
                                 int32_t* pt_items_host, int64_t* n_items_out);
+/* The same for rows of the device table's own form [M][4] (ox, oy, r, K), which may hold rectangle rows (below). */
+int rrtfnd_obst_grid_build_host4(const double* obst4_host, int32_t n_obst, double node_radius, double lo_x,
+                                 double hi_x, double lo_y, double hi_y, double cell, rrtfnd_obst_grid_t* grid_out,
+                                 int32_t* seg_start_host, int32_t* seg_items_host, int32_t* pt_start_host,
+                                 int32_t* pt_items_host, int64_t* n_items_out);
+
+/* ---- EXTENSION: rectangular obstacles -----------------------------------------------------------------------------
+ * The reference declares Map.obstacles_r (src/map.py:18, :54) but never fills or tests it, so this is a builder-defined
+ * extension: PARITY UNPINNED BY THE REFERENCE (pinned on oracle/rrt_oracle.c's restatement of the same expressions).
+ * Wherever an obstacle table [M][4] is taken, a row whose third column is NEGATIVE is an axis-aligned rectangle
+ * (cx, cy, -hx, hy): centre, negated half width (hx > 0), half height. Semantics, by analogy with the circles (segments
+ * against the raw shape, points against the shape inflated by node_radius; csrc/arith.cuh):
+ *   segment: the closed segment p1-p2 intersects the closed rectangle (separating axes on the segment's midpoint and half
+ *            vector; no division, one fp64 rounding per written operation);
+ *   point:   its distance to the rectangle is < node_radius (strict), or it lies inside the closed rectangle.
+ * Circles and rectangles may be mixed in one table; the culling grid lists both. */
 
 /* ---- stateless batched operators (device pointers) ------------------------------------------ */
 
@@ -308,6 +324,54 @@ int rrtfnd_fnd_reconnect(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch
  * find_path(path[0], root). */
 int rrtfnd_fnd_regrow(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root_id,
                       int32_t max_iter, int32_t* out_reconnected, int32_t* out_iters, void* stream);
+
+/* EXTENSION (DetectCollision on path EDGES; the reference's valid_path tests the path nodes only, src/algorithm.py:356): after
+ * rrtfnd_fnd_valid_path, cut every still-linked pair (child = path[i], parent = path[i + 1]) of the stored path whose segment
+ * through_obstacle(Line(parent, child)) (:581-591) is blocked - the child becomes a separate root, nothing is deleted.
+ * separate_root_id[p] = valid_path's result (negative = skip the planner); out_separate_root_id[p] = the root of the tree
+ * holding the goal-side leaf if anything was cut, else the input (may alias it); out_n_cut[p] (may be NULL) = edges cut.
+ * Parity unpinned by the reference; pinned on the oracle's composition of the reference's own through_obstacle. */
+int rrtfnd_fnd_cut_blocked_edges(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const int32_t* separate_root_id,
+                                 int32_t* out_separate_root_id, int32_t* out_n_cut, void* stream);
+
+/* ---- the replanning tick (BASELINE.json config 5) as ONE call without device -> host traffic --------------------------------
+ * The reference stops at the init_movement() stub (src/algorithm.py:283-291); its usage example test_select_branch (:437-479)
+ * implies the loop: step to the next path node (select_branch), validate the path against the moved obstacles (valid_path),
+ * mend what was split off (reconnect, else regrow). rrtfnd_fnd_tick runs that for every planner: per-planner state and the
+ * tick's outcome live in device arrays (all int32 [P] unless noted), the bookkeeping between the operators is a handful of
+ * one-thread-per-planner kernels, so a tick is a sequence of launches on `stream` and nothing is copied to the host. The
+ * caller moves the obstacles first (batch->obst / batch->grid, e.g. rrtfnd_obst_grid_build_device). */
+typedef struct rrtfnd_fnd_loop {
+    int32_t max_rounds;     /* separate trees mended per tick (one per occupied stretch of the path), goal side first */
+    int32_t reserved;
+    int32_t* phase;         /* in/out: 0 MOVING, 1 ARRIVED (one path node left), 2 LOST */
+    int32_t* current;       /* out: node the robot stepped to (path[-2]), -1 = did not move */
+    int32_t* status;        /* out: select_branch status */
+    int32_t* prev_root;     /* scratch: valid_path argument */
+    int32_t* separate;      /* out: valid_path result (after the edge cut, if enabled) */
+    int32_t* index_error;   /* out: valid_path's IndexError flag */
+    int32_t* edge_cuts;     /* out: edges cut by the edge invalidation (may be NULL) */
+    int32_t* todo;          /* scratch: separate root to mend in the current round */
+    int32_t* regrow_arg;    /* scratch */
+    int32_t* link_tmp;      /* scratch */
+    int32_t* regrow_tmp;    /* scratch */
+    int32_t* iters_tmp;     /* scratch */
+    int32_t* linked;        /* out [P][max_rounds]: id each separate root was linked to by reconnect, -1 */
+    int32_t* regrow;        /* out [P][max_rounds]: regrow result (1 reconnected, 0 not, 3 attempt cap, < 0 status), 0 = not run */
+    int32_t* regrow_iters;  /* out [P][max_rounds]: extensions regrow made */
+    int64_t* stats;         /* in/out [16], accumulated: moves, splits, reconnected, regrown, regrow extensions, then (last tick
+                             * only meaningful if zeroed before it) lost, arrived; ticks; ... */
+} rrtfnd_fnd_loop_t;
+int rrtfnd_fnd_tick(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, const rrtfnd_fnd_loop_t* loop,
+                    double reconnect_radius, int32_t regrow_iters, int32_t edge_invalidation, void* stream);
+
+/* The culling grid of rrtfnd_obst_grid_build_host4, built by a kernel from the DEVICE table obst [M][4] into the caller's
+ * device arrays (grid->seg_start / pt_start hold cells_cap entries, seg_items / pt_items seg_cap / pt_cap). The grid
+ * geometry depends on the box, M and `cell` only; coord_max must bound every |coordinate| and radius the table will hold
+ * (it sets the exactness margin; larger is still exact). *overflow (device int) = 1 if a list did not fit. */
+int rrtfnd_obst_grid_build_device(const double* obst, int32_t n_obst, double node_radius, double lo_x, double hi_x,
+                                  double lo_y, double hi_y, double cell, double coord_max, rrtfnd_obst_grid_t* grid,
+                                  int32_t seg_cap, int32_t pt_cap, int32_t cells_cap, int32_t* overflow, void* stream);
 
 /* ---- host-buffer entry point (what the Python drop-in and bench `e2e` call) -------------------- */
 

@@ -65,6 +65,7 @@ def lib():
     L.orc_fnd_select_branch.argtypes = [vp, C.c_int]
     L.orc_fnd_valid_path.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int, ip]
     L.orc_fnd_reconnect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.orc_fnd_cut_blocked_edges.argtypes = [vp, vp, C.c_int, C.c_int, ip]
     L.orc_fnd_regrow.argtypes = [vp, C.POINTER(Params), vp, C.c_double, C.c_double, C.c_int, vp, C.c_int64, C.c_uint64, C.c_uint64,
                                  C.c_int, ip]
     L.orc_set_cursor.argtypes = [vp, C.c_uint64]
@@ -177,6 +178,13 @@ class OracleTree:
         err = C.c_int(0)
         sep = self.L.orc_fnd_valid_path(self.h, _ptr(ob), len(ob), float(node_radius), int(previous_root), C.byref(err))
         return sep, bool(err.value)
+
+    def cut_blocked_edges(self, obstacles, separate_root):
+        """Edge invalidation (extension, see rrt_oracle.c): returns (separate root after the cuts, edges cut)."""
+        ob = obst_table3(obstacles)
+        n = C.c_int(0)
+        sep = self.L.orc_fnd_cut_blocked_edges(self.h, _ptr(ob), len(ob), int(separate_root), C.byref(n))
+        return sep, n.value
 
     def reconnect(self, obstacles, separate_root, radius, last_node):
         ob = obst_table3(obstacles)

@@ -13,7 +13,8 @@ MAX_ROUNDS = 4
 class OracleReplanner:
     """One planner (an oracle.OracleTree that already ran its planner) stepped through replanning ticks."""
 
-    def __init__(self, tree, prm, goal, seed, stream_id, node_radius, reconnect_radius, regrow_iters=500):
+    def __init__(self, tree, prm, goal, seed, stream_id, node_radius, reconnect_radius, regrow_iters=500, edge_invalidation=False):
+        self.edge_invalidation = bool(edge_invalidation)
         self.t, self.prm, self.goal, self.seed, self.stream_id = tree, prm, goal, int(seed), int(stream_id)
         self.node_radius, self.reconnect_radius, self.regrow_iters = float(node_radius), float(reconnect_radius), int(regrow_iters)
         n = len(tree.best_path())
@@ -23,7 +24,7 @@ class OracleReplanner:
         """Returns dict(current, status, separate_root, index_error, phase, linked[R], regrow[R], regrow_iters[R])."""
         t = self.t
         out = dict(current=-1, status=-1, separate_root=-1, index_error=0, linked=[-1] * MAX_ROUNDS, regrow=[0] * MAX_ROUNDS,
-                   regrow_iters=[0] * MAX_ROUNDS)
+                   regrow_iters=[0] * MAX_ROUNDS, edge_cuts=0)
         path = t.best_path()
         if self.phase == MOVING and len(path) >= 2:
             cur = int(path[-2])                                   # the robot steps to the next node of its path
@@ -33,6 +34,8 @@ class OracleReplanner:
             bad, sep = st != 0, cur
             if not bad:
                 sep, err = t.valid_path(obstacles, self.node_radius, cur)
+                if self.edge_invalidation and not err:            # extension: also cut path edges that now cross an obstacle
+                    sep, out["edge_cuts"] = t.cut_blocked_edges(obstacles, sep)
                 out["separate_root"], out["index_error"] = (-1 if err else sep), int(err)
                 bad = err or not self._alive(t.root())
             if bad:

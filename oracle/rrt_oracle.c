@@ -201,11 +201,35 @@ static int seg_hits_circle_impl(double p1x, double p1y, double p2x, double p2y, 
     return (x1 > lo && x1 < hi) || (x2 > lo && x2 < hi); /* :576 */
 }
 
+/* EXTENSION — rectangular obstacles. The reference declares Map.obstacles_r (src/map.py:18, :54) and never implements it:
+ * PARITY UNPINNED BY THE REFERENCE. This restates the semantics documented in include/rrtfnd.h (a table row with a negative
+ * third column is the rectangle (cx, cy, -hx, hy)), operation for operation as csrc/arith.cuh evaluates them, so that the
+ * CUDA path has a checker. Segment: closed segment vs closed rectangle by separating axes. */
+static int seg_hits_rect(double p1x, double p1y, double p2x, double p2y, double cx, double cy, double hx, double hy) {
+    double ex = (p2x - p1x) * 0.5, ey = (p2y - p1y) * 0.5;
+    double mx = (p1x + ex) - cx, my = (p1y + ey) - cy;
+    double ax = fabs(ex), ay = fabs(ey);
+    if (fabs(mx) > hx + ax) return 0;
+    if (fabs(my) > hy + ay) return 0;
+    double cross = mx * ey - my * ex, reach = hx * ay + hy * ax;
+    return !(fabs(cross) > reach);
+}
+/* point: inside the closed rectangle, or closer to it than node_radius (strict, like src/map.py:45) */
+static int point_in_inflated_rect(double px, double py, double cx, double cy, double hx, double hy, double node_radius) {
+    double dx = fmax(fabs(px - cx) - hx, 0.0), dy = fmax(fabs(py - cy) - hy, 0.0);
+    if (dx == 0.0 && dy == 0.0) return 1;
+    return sqrt(dx * dx + dy * dy) < node_radius;
+}
+
 /* through_obstacle (src/algorithm.py:581-591); obst is [M][4] ox, oy, r, K */
 static int through_obstacle(double p1x, double p1y, double p2x, double p2y, const double* obst, int M,
                             int64_t* n_tests) {
     for (int j = 0; j < M; ++j) {
         if (n_tests) ++*n_tests;
+        if (obst[4 * j + 2] < 0.0) {          /* rectangle row (extension) */
+            if (seg_hits_rect(p1x, p1y, p2x, p2y, obst[4 * j], obst[4 * j + 1], -obst[4 * j + 2], obst[4 * j + 3])) return 1;
+            continue;
+        }
         if (seg_hits_circle(p1x, p1y, p2x, p2y, obst[4 * j], obst[4 * j + 1], obst[4 * j + 2], obst[4 * j + 3])) return 1;
     }
     return 0;
@@ -214,6 +238,10 @@ static int through_obstacle(double p1x, double p1y, double p2x, double p2y, cons
 /* Map.is_occupied_c (src/map.py:38-47) */
 static int is_occupied(double px, double py, const double* obst, int M, double node_radius) {
     for (int j = 0; j < M; ++j) {
+        if (obst[4 * j + 2] < 0.0) {          /* rectangle row (extension) */
+            if (point_in_inflated_rect(px, py, obst[4 * j], obst[4 * j + 1], -obst[4 * j + 2], obst[4 * j + 3], node_radius)) return 1;
+            continue;
+        }
         double dx = px - obst[4 * j], dy = py - obst[4 * j + 1];
         double d = sqrt(pow2_ref(dx) + pow2_ref(dy));
 #ifdef ORC_POW_AUDIT
@@ -475,6 +503,29 @@ int orc_fnd_valid_path(orc_tree_t* t, const double* obst, int M, double node_rad
         sep = child;                              /* :361 */
     }
     return sep;
+}
+
+/* EXTENSION — invalidation of path EDGES (DetectCollision of the RRT*FND paper; the reference's valid_path tests the path nodes
+ * only, src/algorithm.py:356, and its own loop is a stub, :283-291): PARITY UNPINNED BY THE REFERENCE. Composed from the
+ * reference's through_obstacle (:581-591): after valid_path, every still-linked pair (child = path[i], parent = path[i + 1]) of
+ * the stored path whose Line(parent, child) is blocked is cut - the child becomes a separate root, nothing is deleted. Returns
+ * the root of the tree that holds the goal-side leaf if anything was cut (and it is not the planner's root), else sep_in. */
+int orc_fnd_cut_blocked_edges(orc_tree_t* t, const double* obst, int M, int sep_in, int* n_cut) {
+    int cuts = 0;
+    for (int i = t->best_len - 2; i >= 0; --i) {
+        int c = t->best_path[i], q = t->best_path[i + 1];
+        if (c < 0 || q < 0 || !t->alive[c] || !t->alive[q] || t->parent[c] != q) continue;
+        ++t->n_edge_checks; ++t->n_edge_checks_ref;
+        if (!through_obstacle(t->x[q], t->y[q], t->x[c], t->y[c], obst, M, &t->n_circle_tests)) continue;
+        t->parent[c] = -1;
+        t->nchild[q]--;
+        ++cuts;
+    }
+    if (n_cut) *n_cut = cuts;
+    if (cuts == 0 || t->best_len == 0 || !t->alive[t->best_path[0]]) return sep_in;
+    int n = t->best_path[0];
+    while (t->parent[n] >= 0) n = t->parent[n];
+    return n != t->root ? n : sep_in;
 }
 
 /* reconnect (src/algorithm.py:370-404) + get_near_nodes (:423-434) + get_distance_dict (:938-951, called with the

@@ -3,7 +3,7 @@ or cannot be loaded, importing this module raises."""
 import ctypes as C
 import os
 
-from ._structs import ABI_VERSION, Batch, ObstGrid, Params, Planner
+from ._structs import ABI_VERSION, Batch, FndLoop, ObstGrid, Params, Planner
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RRTFND_LIB") or os.path.join(_HERE, "librrtfnd.so")   # RRTFND_LIB: an A/B build of the same sources
@@ -14,7 +14,8 @@ EXPORTS = [
     "rrtfnd_edges_vs_circles", "rrtfnd_points_occupied", "rrtfnd_edges_vs_circles_grid", "rrtfnd_points_occupied_grid", "rrtfnd_nearest_visible", "rrtfnd_near_set",
     "rrtfnd_chain_cost", "rrtfnd_pow_libm", "rrtfnd_plan_batch", "rrtfnd_init_batch",
     "rrtfnd_fnd_select_branch", "rrtfnd_fnd_valid_path", "rrtfnd_fnd_reconnect", "rrtfnd_fnd_regrow",
-    "rrtfnd_plan_host",
+    "rrtfnd_plan_host", "rrtfnd_obst_grid_build_host4", "rrtfnd_obst_grid_build_device", "rrtfnd_fnd_cut_blocked_edges",
+    "rrtfnd_fnd_tick",
 ]
 
 
@@ -51,6 +52,10 @@ def _load():
     lib.rrtfnd_fnd_regrow.argtypes = [PP, PB, vp, i32, vp, vp, vp]
     lib.rrtfnd_plan_host.argtypes = [PP, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     lib.rrtfnd_obst_grid_build_host.argtypes = [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, C.POINTER(ObstGrid), vp, vp, vp, vp, vp]
+    lib.rrtfnd_obst_grid_build_host4.argtypes = [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, C.POINTER(ObstGrid), vp, vp, vp, vp, vp]
+    lib.rrtfnd_obst_grid_build_device.argtypes = [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, dbl, C.POINTER(ObstGrid), i32, i32, i32, vp, vp]
+    lib.rrtfnd_fnd_cut_blocked_edges.argtypes = [PP, PB, vp, vp, vp, vp]
+    lib.rrtfnd_fnd_tick.argtypes = [PP, PB, C.POINTER(FndLoop), dbl, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here = the library does not match the header
         if name not in ("rrtfnd_status_string", "rrtfnd_plan_smem_bytes", "rrtfnd_abi_version"):

@@ -1,7 +1,7 @@
 """ctypes mirrors of the structs in include/rrtfnd.h (kept field-for-field in the same order)."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MODE_RRT, MODE_STAR, MODE_FN = 0, 1, 2
 STREAM_WORDS, STREAM_PHILOX = 0, 1
@@ -83,6 +83,16 @@ class Batch(C.Structure):
         ("obst", C.c_void_p), ("words", C.c_void_p), ("trace", C.c_void_p),
         ("grid", ObstGrid), ("node_grid", NodeGrid),
         ("walk", C.c_void_p),
+    ]
+
+
+class FndLoop(C.Structure):
+    _fields_ = [
+        ("max_rounds", C.c_int32), ("reserved", C.c_int32),
+        ("phase", C.c_void_p), ("current", C.c_void_p), ("status", C.c_void_p), ("prev_root", C.c_void_p),
+        ("separate", C.c_void_p), ("index_error", C.c_void_p), ("edge_cuts", C.c_void_p), ("todo", C.c_void_p),
+        ("regrow_arg", C.c_void_p), ("link_tmp", C.c_void_p), ("regrow_tmp", C.c_void_p), ("iters_tmp", C.c_void_p),
+        ("linked", C.c_void_p), ("regrow", C.c_void_p), ("regrow_iters", C.c_void_p), ("stats", C.c_void_p),
     ]
 
 

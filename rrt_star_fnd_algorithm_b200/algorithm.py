@@ -64,7 +64,7 @@ def _grow(mode: str, G: Graph, iter_num: int, map: Map, step_length: float, radi
     n_words = 256 + 16 * int(iter_num)
     words = _draw_words(n_words)
     b = PlannerBatch(mode, starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
-                     obstacles=map.obstacles_c, xy_range=G.xy_range, iter_num=iter_num, step_length=step_length,
+                     obstacles=map.obstacles_c, rectangles=getattr(map, "obstacles_r", ()), xy_range=G.xy_range, iter_num=iter_num, step_length=step_length,
                      radius=radius, node_radius=map.node_radius, goal_node_radius=node_radius, bias=bias,
                      max_nodes=max_nodes, words=words[None, :], capacity=capacity, eval_choose_parent=False,
                      path_cap=max(1024, capacity), finish_cap=max(1024, capacity))
@@ -152,7 +152,7 @@ def _surgery_batch(G: Graph, map: Map, path):
     ids, xy, parent, cost, root_id = G._export()
     cap = len(ids) + 2
     b = PlannerBatch("star", starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
-                     obstacles=map.obstacles_c, xy_range=G.xy_range, iter_num=1, step_length=1.0, radius=1.0,
+                     obstacles=map.obstacles_c, rectangles=getattr(map, "obstacles_r", ()), xy_range=G.xy_range, iter_num=1, step_length=1.0, radius=1.0,
                      node_radius=map.node_radius, capacity=cap, path_cap=max(64, len(path) + 2), finish_cap=8, grid=False)
     b.reset()
     b.load_tree(0, ids, xy, parent, cost, root_id, G.last_id)
@@ -218,7 +218,7 @@ def regrow(G: Graph, map: Map, step_length: float, radius: float, id_root: int, 
     n_words = max(128, int(_n_words))
     words = _draw_words(n_words)
     b = PlannerBatch("star", starts=[(float(G.start[0]), float(G.start[1]))], goals=[(float(G.goal[0]), float(G.goal[1]))],
-                     obstacles=map.obstacles_c, xy_range=G.xy_range, iter_num=1, step_length=step_length, radius=radius,
+                     obstacles=map.obstacles_c, rectangles=getattr(map, "obstacles_r", ()), xy_range=G.xy_range, iter_num=1, step_length=step_length, radius=radius,
                      node_radius=map.node_radius, bias=bias, capacity=cap, path_cap=max(64, cap), finish_cap=8,
                      words=words[None, :])
     b.reset()

@@ -16,40 +16,55 @@ from ._structs import (
 _MODES = {"rrt": MODE_RRT, "star": MODE_STAR, "fn": MODE_FN, MODE_RRT: MODE_RRT, MODE_STAR: MODE_STAR, MODE_FN: MODE_FN}
 
 
-def obstacle_table(obstacles) -> np.ndarray:
-    """Rows (ox, oy, r, K) from the reference's obstacle list `[(pos, r), ...]` or from (ox, oy, r) triples.
+def obstacle_table(obstacles, rectangles=()) -> np.ndarray:
+    """Rows of the device obstacle table from the reference's circle list `[(pos, r), ...]` (or (ox, oy, r) triples) and,
+    as an EXTENSION the reference only declares (Map.obstacles_r, src/map.py:18), axis-aligned rectangles
+    `[(cx, cy), (hx, hy)]` (centre, half extents; or (cx, cy, hx, hy)).
 
-    K is the circle-only part of calc_delta's `c` (src/algorithm.py:619), evaluated with the reference's own
-    expression on the caller's own number types: `-r ** 2 + x0 ** 2 + y0 ** 2`.
+    Circle rows are (ox, oy, r, K): K is the circle-only part of calc_delta's `c` (src/algorithm.py:619), evaluated with
+    the reference's own expression on the caller's own number types: `-r ** 2 + x0 ** 2 + y0 ** 2`. Rectangle rows are
+    (cx, cy, -hx, hy): the negative third column marks them (include/rrtfnd.h).
     """
     rows = []
     for ob in obstacles:
+        if len(ob) == 4:                      # a row that already carries K (or a rectangle row)
+            rows.append(tuple(float(v) for v in ob))
+            continue
         if len(ob) == 2:
             (x0, y0), r = (ob[0][0], ob[0][1]), ob[1]
         else:
             x0, y0, r = ob
         K = -r ** 2 + x0 ** 2 + y0 ** 2
         rows.append((float(x0), float(y0), float(r), float(K)))
+    for rc in rectangles:
+        (cx, cy), (hx, hy) = ((rc[0][0], rc[0][1]), (rc[1][0], rc[1][1])) if len(rc) == 2 else ((rc[0], rc[1]), (rc[2], rc[3]))
+        if not (hx > 0 and hy >= 0):
+            raise ValueError("a rectangle needs half extents hx > 0, hy >= 0")
+        rows.append((float(cx), float(cy), -float(hx), float(hy)))
     return np.asarray(rows, dtype=np.float64).reshape(-1, 4)
 
 
-def build_obstacle_grid(obstacles3: np.ndarray, node_radius: float, bounds, cell: float = 0.0):
-    """Host-side culling grid (rrtfnd_obst_grid_build_host): returns (ObstGrid without pointers, 4 int32 arrays).
+def build_obstacle_grid(table4: np.ndarray, node_radius: float, bounds, cell: float = 0.0):
+    """Host-side culling grid (rrtfnd_obst_grid_build_host4) over the rows of the device table [M][4]: returns (ObstGrid
+    without pointers, 4 int32 arrays).
 
     `bounds` = (lo_x, hi_x, lo_y, hi_y) must contain every coordinate the planners can produce."""
-    ob = np.ascontiguousarray(obstacles3, dtype=np.float64).reshape(-1, 3)
+    ob = np.asarray(table4, dtype=np.float64)
+    if ob.ndim == 2 and ob.shape[1] == 3:                     # plain (ox, oy, r) circles
+        ob = np.column_stack([ob, np.zeros(len(ob))])
+    ob = np.ascontiguousarray(ob).reshape(-1, 4)
     g = ObstGrid()
     cnt = (C.c_int64 * 2)()
     args = (ob.ctypes.data, len(ob), float(node_radius), float(bounds[0]), float(bounds[1]), float(bounds[2]),
             float(bounds[3]), float(cell), C.byref(g))
-    _abi.check(_abi.lib.rrtfnd_obst_grid_build_host(*args, None, None, None, None, cnt), "rrtfnd_obst_grid_build_host")
+    _abi.check(_abi.lib.rrtfnd_obst_grid_build_host4(*args, None, None, None, None, cnt), "rrtfnd_obst_grid_build_host4")
     if g.nx == 0:
         return g, None
     nc = g.nx * g.ny
     arrs = [np.zeros(nc + 1, np.int32), np.zeros(max(int(cnt[0]), 1), np.int32),
             np.zeros(nc + 1, np.int32), np.zeros(max(int(cnt[1]), 1), np.int32)]
-    _abi.check(_abi.lib.rrtfnd_obst_grid_build_host(*args, *[a.ctypes.data for a in arrs], cnt),
-               "rrtfnd_obst_grid_build_host")
+    _abi.check(_abi.lib.rrtfnd_obst_grid_build_host4(*args, *[a.ctypes.data for a in arrs], cnt),
+               "rrtfnd_obst_grid_build_host4")
     return g, arrs
 
 
@@ -59,7 +74,7 @@ def fn_capacity(max_nodes: int) -> int:
 
 
 class PlannerBatch:
-    def __init__(self, mode, *, starts, goals, obstacles, xy_range, iter_num, step_length, radius=0.0,
+    def __init__(self, mode, *, starts, goals, obstacles, xy_range, iter_num, step_length, radius=0.0, rectangles=(),
                  node_radius=1.0, goal_node_radius=None, bias=0.0, max_nodes=200, seeds=None, stream_ids=None, words=None,
                  capacity=None, near_cap=64, finish_cap=1024, path_cap=1024, trace=False,
                  eval_choose_parent=True, commit_choose_parent=False, max_attempts=0, device=None, launch=0,
@@ -78,7 +93,7 @@ class PlannerBatch:
             capacity = fn_capacity(max_nodes) if m == MODE_FN else int(iter_num) + 2
         prm = Params()
         prm.mode, prm.iter_num, prm.max_nodes, prm.capacity = m, int(iter_num), int(max_nodes), int(capacity)
-        self.obst_host = obstacle_table(obstacles)
+        self.obst_host = obstacle_table(obstacles, rectangles)
         prm.n_obst = len(self.obst_host)
         prm.near_cap, prm.finish_cap, prm.path_cap = int(near_cap), int(finish_cap), int(path_cap)
         prm.flags = (FLAG_EVAL_CHOOSE_PARENT if eval_choose_parent else 0) | (2 if commit_choose_parent else 0) | \
@@ -125,7 +140,7 @@ class PlannerBatch:
             pts = np.concatenate([starts, goals, np.asarray(xy_range, dtype=np.float64).T])
             bounds = (pts[:, 0].min(), pts[:, 0].max(), pts[:, 1].min(), pts[:, 1].max())
             self._bounds = bounds
-            g, arrs = build_obstacle_grid(self.obst_host[:, :3], prm.node_radius, bounds, grid_cell)
+            g, arrs = build_obstacle_grid(self.obst_host, prm.node_radius, bounds, grid_cell)
             if arrs is not None:
                 self._grid_t = [torch.from_numpy(a).to(dev) for a in arrs]
                 g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in self._grid_t]
@@ -251,13 +266,13 @@ class PlannerBatch:
         assert len(a) == self.P, "one node id per planner"
         return torch.from_numpy(a.copy()).to(self.device)
 
-    def set_obstacles(self, obstacles, grid=True, grid_cell=0.0, _table=None):
+    def set_obstacles(self, obstacles, grid=True, grid_cell=0.0, _table=None, rectangles=()):
         """Replace the obstacle table (a moved / extended map) and rebuild the culling grid.
 
         The grid's box must bound every node: trees grown by the planners stay inside the box of xy_range, starts and
         goals (a steered point lies between a node and a sample), so that box is reused; only after load_tree() are the
         node coordinates themselves read back to bound them."""
-        self.obst_host = obstacle_table(obstacles) if _table is None else _table     # _table: rows that already carry K
+        self.obst_host = obstacle_table(obstacles, rectangles) if _table is None else _table     # _table: rows that already carry K
         self.prm.n_obst = len(self.obst_host)
         self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(self.device)
         self.grid, self._grid_t = ObstGrid(), None
@@ -273,11 +288,49 @@ class PlannerBatch:
                 allxy = np.concatenate(live + [pts])
                 allxy = allxy[~np.isnan(allxy).any(axis=1)]
                 bounds = (allxy[:, 0].min(), allxy[:, 0].max(), allxy[:, 1].min(), allxy[:, 1].max())
-            g, arrs = build_obstacle_grid(self.obst_host[:, :3], self.prm.node_radius, bounds, grid_cell)
+            g, arrs = build_obstacle_grid(self.obst_host, self.prm.node_radius, bounds, grid_cell)
             if arrs is not None:
                 self._grid_t = [torch.from_numpy(a).to(self.device) for a in arrs]
                 g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in self._grid_t]
                 self.grid = g
+
+    def set_obstacle_table_async(self, table4_host: np.ndarray, grid_cell=0.0):
+        """set_obstacles for the replanning loop: the rows (ox, oy, r, K) go up with one asynchronous copy and the culling grid
+        is rebuilt by a kernel; the host neither builds lists nor waits."""
+        t = np.ascontiguousarray(table4_host, dtype=np.float64).reshape(-1, 4)
+        b = self._bounds
+        coord_max = float(max(np.abs(t[:, :3]).max(), np.abs(t[t[:, 2] < 0, 3]).max() if (t[:, 2] < 0).any() else 0.0,
+                              abs(b[0]), abs(b[1]), abs(b[2]), abs(b[3])))
+        self.set_obstacles_device(torch.from_numpy(t).to(self.device, non_blocking=True), coord_max, grid_cell)
+        self.obst_host = t
+
+    def set_obstacles_device(self, table4_dev, coord_max, grid_cell=0.0):
+        """Replace the obstacle table by `table4_dev` (a float64 CUDA tensor [M][4] holding ox, oy, r, K rows, same M as
+        now) and rebuild the culling grid with a kernel (rrtfnd_obst_grid_build_device): nothing crosses the host, which
+        is what the replanning loop wants when the obstacles move every tick. `coord_max` bounds every |coordinate| and
+        radius the table can hold (it sets the grid's exactness margin). Only for trees grown by the planners (the box of
+        xy_range, starts and goals bounds them)."""
+        assert table4_dev.is_cuda and table4_dev.dtype == torch.float64 and tuple(table4_dev.shape) == (self.prm.n_obst, 4)
+        assert not self._loaded, "after load_tree() use set_obstacles(), which bounds the loaded nodes"
+        self.obst = table4_dev.contiguous()
+        self.obst_host = None                                   # stale from now on
+        M = self.prm.n_obst
+        if getattr(self, "_dev_grid", None) is None:
+            b = self._bounds
+            cells_cap, items_cap = 512 * 512 + 1, max(4096, 64 * M)
+            self._dev_grid = [torch.zeros(cells_cap, dtype=torch.int32, device=self.device), torch.zeros(items_cap, dtype=torch.int32, device=self.device),
+                              torch.zeros(cells_cap, dtype=torch.int32, device=self.device), torch.zeros(items_cap, dtype=torch.int32, device=self.device)]
+            self._grid_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        g = ObstGrid()
+        g.seg_start, g.seg_items, g.pt_start, g.pt_items = [t.data_ptr() for t in self._dev_grid]
+        b = self._bounds
+        with torch.cuda.device(self.device):
+            _abi.check(_abi.lib.rrtfnd_obst_grid_build_device(self.obst.data_ptr(), M, float(self.prm.node_radius), float(b[0]), float(b[1]),
+                                                              float(b[2]), float(b[3]), float(grid_cell), float(coord_max), C.byref(g),
+                                                              self._dev_grid[1].numel(), self._dev_grid[3].numel(), self._dev_grid[0].numel(),
+                                                              self._grid_overflow.data_ptr(), self._stream()),
+                       "rrtfnd_obst_grid_build_device")
+        self.grid, self._grid_t = g, self._dev_grid
 
     def rebuild_grid(self, grid_cell=0.0):
         """Rebuild the culling grid over a box that bounds the nodes the planners hold NOW (after load_tree() a caller's
@@ -305,6 +358,19 @@ class PlannerBatch:
                                                       C.c_void_p(sep.data_ptr()), C.c_void_p(err.data_ptr()), self._stream()),
                        "rrtfnd_fnd_valid_path")
         return sep.cpu().numpy(), err.cpu().numpy()
+
+    def cut_blocked_edges(self, separate_root_ids):
+        """EXTENSION (edge invalidation, include/rrtfnd.h): after valid_path, cut the path edges that cross an obstacle.
+        Returns (separate root ids after the cuts, edges cut)."""
+        sep = self._ids_tensor(separate_root_ids)
+        out = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        cuts = torch.zeros(self.P, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            b = self._batch()
+            _abi.check(_abi.lib.rrtfnd_fnd_cut_blocked_edges(C.byref(self.prm), C.byref(b), C.c_void_p(sep.data_ptr()),
+                                                             C.c_void_p(out.data_ptr()), C.c_void_p(cuts.data_ptr()), self._stream()),
+                       "rrtfnd_fnd_cut_blocked_edges")
+        return out.cpu().numpy(), cuts.cpu().numpy()
 
     def reconnect(self, separate_root_ids, radius):
         """reconnect for every planner. Returns the id each separate root was linked to (-1 = none)."""

@@ -30,7 +30,7 @@ def is_stale():
     t = os.path.getmtime(LIB)
     # every file under csrc/ (sources, .cuh, .h) plus the public header and this script
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    return any(os.path.isfile(d) and os.path.getmtime(d) > t for d in deps)
 
 
 def build_library(force=False, verbose=False):

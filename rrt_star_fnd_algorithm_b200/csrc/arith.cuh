@@ -61,6 +61,7 @@ __device__ __forceinline__ double pow_half_ref(double x) { return dsqrt(x); }
 // (src/algorithm.py:607-621) that do not depend on the circle.
 struct Seg {
     double p1x;      // x_pos of a vertical line
+    double p1y, ylo, yhi;   // only read by the rectangle extension (values the callers hold anyway)
     double m, k;     // Line.dir, Line.const_term
     double mk, kk;   // m*k, k*k (k**2)
     double a2, a4;   // 2*a, 4*a with a = 1 + m*m   (exact scalings)
@@ -81,12 +82,44 @@ __device__ __forceinline__ Seg make_seg(double p1x, double p1y, double p2x, doub
     s.a4 = dmul(4.0, a);
     s.lo = p1x < p2x ? p1x : p2x;
     s.hi = p1x < p2x ? p2x : p1x;
+    s.p1y = p1y;
+    s.ylo = p1y < p2y ? p1y : p2y;
+    s.yhi = p1y < p2y ? p2y : p1y;
     return s;
+}
+
+// ---- EXTENSION: axis-aligned rectangles -------------------------------------------------------------------------------
+// The reference declares Map.obstacles_r (src/map.py:18, :54) and never implements it, so there is nothing to be faithful
+// to: PARITY UNPINNED BY THE REFERENCE, pinned on the oracle's restatement of the same expressions (oracle/rrt_oracle.c).
+// A rectangle shares the obstacle table with the circles as the row (cx, cy, -hx, hy): centre, NEGATED half width (a
+// negative third column marks a rectangle, hx > 0), half height. Semantics, chosen like the circles' (segments against
+// the raw shape, points against the shape inflated by node_radius):
+//   segment: closed segment p1-p2 intersects the closed rectangle, by separating axes on the segment's midpoint m and
+//            half vector e - no division, one rounding per written operation:
+//            |m.x - cx| <= hx + |e.x|  and  |m.y - cy| <= hy + |e.y|  and  |m' x e| <= hx |e.y| + hy |e.x|
+//   point:   distance from the point to the rectangle < node_radius (strict, like src/map.py:45), or the point lies in
+//            the closed rectangle.
+static __device__ __noinline__ bool seg_hits_rect(double p1x, double p1y, double p2x, double p2y, double cx, double cy, double hx,
+                                                  double hy) {
+    const double ex = dmul(dsub(p2x, p1x), 0.5), ey = dmul(dsub(p2y, p1y), 0.5);
+    const double mx = dsub(dadd(p1x, ex), cx), my = dsub(dadd(p1y, ey), cy);
+    const double ax = fabs(ex), ay = fabs(ey);
+    if (fabs(mx) > dadd(hx, ax)) return false;
+    if (fabs(my) > dadd(hy, ay)) return false;
+    return !(fabs(dsub(dmul(mx, ey), dmul(my, ex))) > dadd(dmul(hx, ay), dmul(hy, ax)));
+}
+static __device__ __noinline__ bool point_in_inflated_rect(double px, double py, double cx, double cy, double hx, double hy,
+                                                           double node_radius) {
+    const double dx = fmax(dsub(fabs(dsub(px, cx)), hx), 0.0), dy = fmax(dsub(fabs(dsub(py, cy)), hy), 0.0);
+    if (dx == 0.0 && dy == 0.0) return true;
+    return dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))) < node_radius;
 }
 
 // intersection_circle (src/algorithm.py:555-578) for one circle (ox, oy, r) with
 // K = ((-(r*r)) + ox*ox) + oy*oy precomputed (first three terms of `c`, :619).
 __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double oy, double r, double K) {
+    if (r < 0.0)                                                                // a rectangle row (cx, cy, -hx, hy): extension above
+        return seg_hits_rect(s.p1x, s.p1y, s.p1x == s.lo ? s.hi : s.lo, s.p1y == s.ylo ? s.yhi : s.ylo, ox, oy, -r, K);
     if (s.vertical) return fabs(dsub(ox, s.p1x)) <= r;                          // :563-567
     const double b = dmul(2.0, dsub(dadd(-ox, s.mk), dmul(s.m, oy)));           // :618
     const double c = dadd(dsub(K, dmul(dadd(oy, oy), s.k)), s.kk);              // :619
@@ -99,7 +132,8 @@ __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double 
 
 // Map.is_occupied_c for one circle (src/map.py:44-45)
 __device__ __forceinline__ bool point_in_inflated(double px, double py, double ox, double oy, double r,
-                                                  double node_radius) {
+                                                  double node_radius, double K = 0.0) {
+    if (r < 0.0) return point_in_inflated_rect(px, py, ox, oy, -r, K, node_radius);   // rectangle row (extension)
     const double dx = dsub(px, ox), dy = dsub(py, oy);
     return dsqrt(dadd(pow2_ref(dx), pow2_ref(dy))) < dadd(node_radius, r);      // np.sqrt((..) ** 2 + (..) ** 2)
 }

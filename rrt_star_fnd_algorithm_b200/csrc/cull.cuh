@@ -15,17 +15,6 @@
 #include "arith.cuh"
 #include "grid.cuh"
 
-// Experiment knob (-DRRTFND_SMEM_TABLES=1, default off, unmeasured): the planner kernel keeps the obstacle table and the
-// culling lists in shared memory (persistent CTAs, planner.cu), so these reads must be generic loads instead of __ldg.
-#ifndef RRTFND_SMEM_TABLES
-#define RRTFND_SMEM_TABLES 0
-#endif
-#if RRTFND_SMEM_TABLES
-#define RRTFND_TAB_LD(p) (*(p))
-#else
-#define RRTFND_TAB_LD(p) __ldg(p)
-#endif
-
 namespace rrtfnd {
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -47,7 +36,7 @@ __device__ __forceinline__ Obst make_obst(const double* obst, int n_obst, const 
     ob.full_cells = 0;
     if (grid->nx > 0 && grid->seg_start != nullptr && n_obst > 0) {
         const int ncells = grid->nx * grid->ny;
-        const int n_items = RRTFND_TAB_LD(grid->seg_start + ncells);
+        const int n_items = __ldg(grid->seg_start + ncells);
         ob.full_cells = (int)(((long long)n_obst * ncells) / (n_items > 0 ? n_items : 1));
         if (ob.full_cells < 1) ob.full_cells = 1;
     }
@@ -56,7 +45,7 @@ __device__ __forceinline__ Obst make_obst(const double* obst, int n_obst, const 
 
 __device__ __forceinline__ void load_obst(const double2* __restrict__ tab, int j, double& ox, double& oy, double& r,
                                           double& K) {
-    const double2 a = RRTFND_TAB_LD(tab + 2 * j), b = RRTFND_TAB_LD(tab + 2 * j + 1);
+    const double2 a = __ldg(tab + 2 * j), b = __ldg(tab + 2 * j + 1);
     ox = a.x; oy = a.y; r = b.x; K = b.y;
 }
 
@@ -100,12 +89,12 @@ static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, 
                 xb = fmin(sg.hi, fmax(xs, xe) + slack);
             }
             const int cx0 = grid_cell(xa, x0, inv, nx), cx1 = grid_cell(xb, x0, inv, nx);
-            j = RRTFND_TAB_LD(start + cy * nx + cx0);
-            e = RRTFND_TAB_LD(start + cy * nx + cx1 + 1);
+            j = __ldg(start + cy * nx + cx0);
+            e = __ldg(start + cy * nx + cx1 + 1);
         }
         for (j += first; j < e; j += stride) {
             double ox, oy, r, K;
-            load_obst(tab, cull ? RRTFND_TAB_LD(items + j) : j, ox, oy, r, K);
+            load_obst(tab, cull ? __ldg(items + j) : j, ox, oy, r, K);
             ++tests;
             if (seg_hits_circle(sg, ox, oy, r, K)) return (tests << 1) | 1;
         }
@@ -121,15 +110,15 @@ __device__ __forceinline__ bool point_occupied_warp(const Obst& ob, double px, d
     if (cull) {
         const rrtfnd_obst_grid_t* g = ob.g;
         const int c = grid_cell(py, g->y0, g->inv_cell, g->ny) * g->nx + grid_cell(px, g->x0, g->inv_cell, g->nx);
-        j = RRTFND_TAB_LD(g->pt_start + c);
-        e = RRTFND_TAB_LD(g->pt_start + c + 1);
+        j = __ldg(g->pt_start + c);
+        e = __ldg(g->pt_start + c + 1);
     }
     bool occ = false;
     for (j += lane; j < e; j += 32) {
         double ox, oy, r, K;
-        load_obst(ob.tab, cull ? RRTFND_TAB_LD(ob.g->pt_items + j) : j, ox, oy, r, K);
+        load_obst(ob.tab, cull ? __ldg(ob.g->pt_items + j) : j, ox, oy, r, K);
         ++tests;
-        occ |= point_in_inflated(px, py, ox, oy, r, node_radius);
+        occ |= point_in_inflated(px, py, ox, oy, r, node_radius, K);
     }
     return __any_sync(kFull, occ);
 }

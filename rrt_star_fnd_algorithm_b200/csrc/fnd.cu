@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(32 * kFndWarps) valid_path_kernel(const rrtfnd
         for (int j = 0; j < M && !occ; ++j) {
             double ox, oy, r, K;
             load_obst(tab, j, ox, oy, r, K);
-            occ = point_in_inflated(c.x, c.y, ox, oy, r, prm.node_radius);
+            occ = point_in_inflated(c.x, c.y, ox, oy, r, prm.node_radius, K);
         }
         if (occ) v.NFLAG[s] |= kOccupied;
     }
@@ -419,6 +419,189 @@ __global__ void __launch_bounds__(32 * kFndWarps) regrow_kernel(const __grid_con
     }
 }
 
+
+// ---- EXTENSION: invalidation of path EDGES (DetectCollision of the RRT*FND paper; the reference's valid_path only tests the
+// path NODES, src/algorithm.py:356, and its loop stops at the init_movement() stub, :283-291). Run after valid_path on the
+// stored path (ids, goal side first): every consecutive pair (child = path[i], parent = path[i+1]) that is still linked
+// and whose segment through_obstacle(Line(parent, child)) (:581-591; p1 = the node nearer the robot) reports blocked is
+// cut - the child becomes the root of a separate tree, nothing is deleted - and the goal-side-most separate root (the
+// root of the leaf's tree) is returned, which is what reconnect / regrow then mend. PARITY UNPINNED BY THE REFERENCE;
+// pinned on oracle/rrt_oracle.c orc_fnd_cut_blocked_edges, composed from the reference's own through_obstacle.
+__global__ void __launch_bounds__(32 * kFndWarps) cut_edges_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt,
+                                                                   const int32_t* __restrict__ sep_in, int32_t* __restrict__ sep_out,
+                                                                   int32_t* __restrict__ n_cut_out) {
+    extern __shared__ int32_t fnd_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, p = blockIdx.x * kFndWarps + wib;
+    if (p >= bt.n_planners) return;
+    if (sep_in[p] < 0) {                                                     // negative id = leave this planner alone
+        if (lane == 0) { sep_out[p] = sep_in[p]; if (n_cut_out) n_cut_out[p] = 0; }
+        return;
+    }
+    int32_t* pslot = fnd_smem + (size_t)wib * prm.path_cap;                  // slot of path node i, -1 if it is gone
+    const PlannerView v = view_of(prm, bt, p);
+    const int n_slots = v.PL->n_slots, L = min(v.PL->best_len, prm.path_cap);
+    const double2* tab = reinterpret_cast<const double2*>(bt.obst);
+    for (int i = lane; i < L; i += 32) pslot[i] = -1;
+    __syncwarp();
+    for (int s = lane; s < n_slots; s += 32) {
+        const int id = v.ID[s];
+        if (id >= 0)
+            for (int i = 0; i < L; ++i) if (v.BPATH[i] == id) { pslot[i] = s; break; }
+    }
+    __syncwarp();
+    int n_cut = 0;
+    for (int base = 0; base + 1 < L; base += 32) {                            // one lane per path edge
+        const int i = base + lane;
+        bool cut = false;
+        if (i + 1 < L) {
+            const int c = pslot[i], q = pslot[i + 1];
+            if (c >= 0 && q >= 0 && v.PARENT[c] == q) {
+                const double2 a = v.XY[q], b = v.XY[c];
+                cut = seg_blocked(tab, &bt.grid, prm.n_obst, 0, a.x, a.y, b.x, b.y, 0, 1) & 1;   // every circle (the map has just changed)
+            }
+        }
+        __syncwarp();
+        if (cut) { v.NCHILD[pslot[i + 1]] -= 1; v.PARENT[pslot[i]] = -1; }   // distinct parents and children: no two lanes meet
+        n_cut += __popc(__ballot_sync(kFull, cut));
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int out = sep_in[p];
+        if (n_cut > 0 && L > 0 && pslot[0] >= 0) {                            // root of the tree that holds the goal-side leaf
+            int n = pslot[0];
+            while (v.PARENT[n] >= 0) n = v.PARENT[n];
+            if (n != v.PL->root_slot) out = v.ID[n];
+        }
+        sep_out[p] = out;
+        if (n_cut_out) n_cut_out[p] = n_cut;
+    }
+}
+
+// ---- the replanning tick's bookkeeping, on the device (rrtfnd_fnd_tick): what fnd_loop.FNDReplanner.tick() computes on the
+// host from downloaded planner records, one thread per planner, so that a tick is a sequence of launches without a single
+// device -> host copy. Phases: 0 MOVING, 1 ARRIVED, 2 LOST.
+enum { kMoving = 0, kArrived = 1, kLost = 2 };
+enum { kStMoves = 0, kStSplits, kStReconnected, kStRegrown, kStRegrowExt, kStLost, kStArrived, kStTicks, kStEdgeCuts };
+
+__device__ __forceinline__ void stat_add(const rrtfnd_fnd_loop_t& lp, int k, long long v) {
+    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(lp.stats) + k, (unsigned long long)v);
+}
+
+// the robot steps to the next node of its path: current = path[-2] (fnd_loop.py step 1)
+__global__ void tick_begin_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt, const rrtfnd_fnd_loop_t lp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= bt.n_planners) return;
+    const rrtfnd_planner_t* PL = bt.planners + p;
+    const int L = PL->best_len;
+    const int cur = (lp.phase[p] == kMoving && L >= 2) ? bt.best_path[(size_t)p * prm.path_cap + (L - 2)] : -1;
+    lp.current[p] = cur;
+    for (int r = 0; r < lp.max_rounds; ++r) {
+        lp.linked[(size_t)p * lp.max_rounds + r] = -1; lp.regrow[(size_t)p * lp.max_rounds + r] = 0;
+        lp.regrow_iters[(size_t)p * lp.max_rounds + r] = 0;
+    }
+    lp.todo[p] = -1;
+    stat_add(lp, kStMoves, cur >= 0);
+}
+// valid_path only for planners whose select_branch succeeded
+__global__ void tick_after_select_kernel(const rrtfnd_batch_t bt, const rrtfnd_fnd_loop_t lp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= bt.n_planners) return;
+    lp.prev_root[p] = (lp.current[p] >= 0 && lp.status[p] == 0) ? lp.current[p] : -1;
+}
+// who is lost, who has a split-off tree to mend
+__global__ void tick_after_valid_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt, const rrtfnd_fnd_loop_t lp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= bt.n_planners) return;
+    const rrtfnd_planner_t* PL = bt.planners + p;
+    const int cur = lp.current[p];
+    const bool moving = cur >= 0;
+    const int root_id = bt.id[(size_t)p * prm.capacity + PL->root_slot];     // is the robot's own node still there?
+    const bool bad = moving && (lp.status[p] != 0 || lp.index_error[p] != 0 || root_id < 0);
+    if (bad) lp.phase[p] = kLost;
+    const int sep = lp.separate[p];
+    lp.todo[p] = (moving && !bad && sep != cur) ? sep : -1;
+    if (lp.edge_cuts) stat_add(lp, kStEdgeCuts, lp.edge_cuts[p]);
+}
+// regrow only where reconnect found no link
+__global__ void tick_after_reconnect_kernel(const rrtfnd_batch_t bt, const rrtfnd_fnd_loop_t lp, int rnd) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= bt.n_planners) return;
+    const int todo = lp.todo[p];
+    const int linked = lp.link_tmp[p];
+    lp.linked[(size_t)p * lp.max_rounds + rnd] = todo >= 0 ? linked : -1;
+    lp.regrow_arg[p] = (todo >= 0 && linked < 0) ? todo : -1;
+}
+// outcome of the round; the path now ends at the root of the next separate tree, if there is one
+__global__ void tick_after_regrow_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt, const rrtfnd_fnd_loop_t lp, int rnd) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= bt.n_planners) return;
+    const rrtfnd_planner_t* PL = bt.planners + p;
+    const bool split = lp.todo[p] >= 0, need = lp.regrow_arg[p] >= 0;
+    const int res = need ? lp.regrow_tmp[p] : 0, its = need ? lp.iters_tmp[p] : 0;
+    lp.regrow[(size_t)p * lp.max_rounds + rnd] = res;
+    lp.regrow_iters[(size_t)p * lp.max_rounds + rnd] = its;
+    const bool failed = need && res != 1;
+    if (failed) lp.phase[p] = kLost;
+    stat_add(lp, kStSplits, split); stat_add(lp, kStReconnected, split && !need);
+    stat_add(lp, kStRegrown, need && !failed); stat_add(lp, kStRegrowExt, its);
+    const int L = PL->best_len;
+    const int tail = L >= 1 ? bt.best_path[(size_t)p * prm.path_cap + (L - 1)] : -1;
+    const int root_id = bt.id[(size_t)p * prm.capacity + PL->root_slot];
+    lp.todo[p] = (split && !failed && tail != root_id) ? tail : -1;
+}
+__global__ void tick_end_kernel(const rrtfnd_batch_t bt, const rrtfnd_fnd_loop_t lp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= bt.n_planners) return;
+    if (lp.todo[p] >= 0) lp.phase[p] = kLost;                                // still broken after max_rounds
+    if (lp.phase[p] == kMoving && lp.current[p] >= 0 && bt.planners[p].best_len <= 1) lp.phase[p] = kArrived;
+    stat_add(lp, kStLost, lp.phase[p] == kLost); stat_add(lp, kStArrived, lp.phase[p] == kArrived);
+    if (p == 0) stat_add(lp, kStTicks, 1);
+}
+
+// ---- culling grid built on the device (rrtfnd_obst_grid_build_device): the same boxes and the same cell function as the
+// host builder (host_api.cu), for obstacle tables that change every tick. One CTA; lists in ascending obstacle index.
+__global__ void __launch_bounds__(256) grid_build_kernel(const double* __restrict__ obst, int M, double node_radius, rrtfnd_obst_grid_t g,
+                                                         int32_t* seg_start, int32_t* seg_items, int32_t* pt_start, int32_t* pt_items,
+                                                         int seg_cap, int pt_cap, int32_t* overflow) {
+    const int ncells = g.nx * g.ny, tid = threadIdx.x;
+    __shared__ int s_tot[2];
+    auto box = [&](int j, double infl, int& x0, int& x1, int& y0, int& y1) {
+        const double ox = obst[4 * j], oy = obst[4 * j + 1], r = obst[4 * j + 2];
+        const double ex = fabs(r), ey = r < 0.0 ? fabs(obst[4 * j + 3]) : fabs(r);
+        const double bx = __dmul_rn(__dadd_rn(ex, infl), 1.000000001), by = __dmul_rn(__dadd_rn(ey, infl), 1.000000001);
+        x0 = grid_cell(__dsub_rn(ox, bx), g.x0, g.inv_cell, g.nx); x1 = grid_cell(__dadd_rn(ox, bx), g.x0, g.inv_cell, g.nx);
+        y0 = grid_cell(__dsub_rn(oy, by), g.y0, g.inv_cell, g.ny); y1 = grid_cell(__dadd_rn(oy, by), g.y0, g.inv_cell, g.ny);
+    };
+    // per cell: count, then (after the scan) fill, scanning the obstacles in ascending index
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = tid; c < ncells; c += blockDim.x) {
+            const int cx = c % g.nx, cy = c / g.nx;
+            int ns = 0, np = 0;
+            const int bs = pass ? seg_start[c] : 0, bp = pass ? pt_start[c] : 0;
+            for (int j = 0; j < M; ++j) {
+                int x0, x1, y0, y1;
+                box(j, g.margin, x0, x1, y0, y1);
+                if (cx >= x0 && cx <= x1 && cy >= y0 && cy <= y1) { if (pass && bs + ns < seg_cap) seg_items[bs + ns] = j; ++ns; }
+                box(j, fabs(node_radius), x0, x1, y0, y1);
+                if (cx >= x0 && cx <= x1 && cy >= y0 && cy <= y1) { if (pass && bp + np < pt_cap) pt_items[bp + np] = j; ++np; }
+            }
+            if (!pass) { seg_start[c + 1] = ns; pt_start[c + 1] = np; }
+        }
+        __syncthreads();
+        if (!pass) {
+            if (tid < 2) {                                   // exclusive scans (thread 0: seg, thread 1: pt)
+                int32_t* a = tid ? pt_start : seg_start;
+                int run = 0;
+                a[0] = 0;
+                for (int c = 1; c <= ncells; ++c) { run += a[c]; a[c] = run; }
+                s_tot[tid] = run;
+            }
+            __syncthreads();
+            if (tid == 0) *overflow = (s_tot[0] > seg_cap || s_tot[1] > pt_cap) ? 1 : 0;
+        }
+    }
+}
+
 }  // namespace rrtfnd
 
 using namespace rrtfnd;
@@ -465,5 +648,67 @@ extern "C" int rrtfnd_fnd_regrow(const rrtfnd_params_t* prm, const rrtfnd_batch_
     if (prm->stream_mode == RRTFND_STREAM_WORDS && !bt->words) return RRTFND_E_BADARG;
     const int blocks = (bt->n_planners + kFndWarps - 1) / kFndWarps;
     regrow_kernel<<<blocks, 32 * kFndWarps, 0, (cudaStream_t)stream>>>(*prm, *bt, separate_root_id, max_iter, out_reconnected, out_iters);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rrtfnd_fnd_cut_blocked_edges(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, const int32_t* separate_root_id,
+                                            int32_t* out_separate_root_id, int32_t* out_n_cut, void* stream) {
+    if (fnd_check(prm, bt) || !separate_root_id || !out_separate_root_id || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
+    const size_t smem = (size_t)kFndWarps * prm->path_cap * sizeof(int32_t);
+    if (smem > 227 * 1024) return RRTFND_E_SMEM;
+    cudaError_t e = cudaFuncSetAttribute(cut_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int blocks = (bt->n_planners + kFndWarps - 1) / kFndWarps;
+    cut_edges_kernel<<<blocks, 32 * kFndWarps, smem, (cudaStream_t)stream>>>(*prm, *bt, separate_root_id, out_separate_root_id, out_n_cut);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rrtfnd_fnd_tick(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, const rrtfnd_fnd_loop_t* lp,
+                               double reconnect_radius, int32_t regrow_iters, int32_t edge_invalidation, void* stream) {
+    if (fnd_check(prm, bt) || !lp || lp->max_rounds < 1 || regrow_iters < 0) return RRTFND_E_BADARG;
+    if (!lp->phase || !lp->current || !lp->status || !lp->prev_root || !lp->separate || !lp->index_error || !lp->todo ||
+        !lp->regrow_arg || !lp->link_tmp || !lp->regrow_tmp || !lp->iters_tmp || !lp->linked || !lp->regrow || !lp->regrow_iters ||
+        !lp->stats) return RRTFND_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = bt->n_planners, nt = 128, nb = (P + nt - 1) / nt;
+    int rc;
+    tick_begin_kernel<<<nb, nt, 0, st>>>(*prm, *bt, *lp);
+    if ((rc = rrtfnd_fnd_select_branch(prm, bt, lp->current, lp->status, stream))) return rc;
+    tick_after_select_kernel<<<nb, nt, 0, st>>>(*bt, *lp);
+    if ((rc = rrtfnd_fnd_valid_path(prm, bt, lp->prev_root, lp->separate, lp->index_error, stream))) return rc;
+    if (edge_invalidation) {
+        if (!lp->edge_cuts) return RRTFND_E_BADARG;
+        if ((rc = rrtfnd_fnd_cut_blocked_edges(prm, bt, lp->separate, lp->separate, lp->edge_cuts, stream))) return rc;
+    }
+    tick_after_valid_kernel<<<nb, nt, 0, st>>>(*prm, *bt, *lp);
+    for (int rnd = 0; rnd < lp->max_rounds; ++rnd) {      // one separate tree per round, goal side first
+        if ((rc = rrtfnd_fnd_reconnect(prm, bt, lp->todo, reconnect_radius, lp->link_tmp, stream))) return rc;
+        tick_after_reconnect_kernel<<<nb, nt, 0, st>>>(*bt, *lp, rnd);
+        if ((rc = rrtfnd_fnd_regrow(prm, bt, lp->regrow_arg, regrow_iters, lp->regrow_tmp, lp->iters_tmp, stream))) return rc;
+        tick_after_regrow_kernel<<<nb, nt, 0, st>>>(*prm, *bt, *lp, rnd);
+    }
+    tick_end_kernel<<<nb, nt, 0, st>>>(*bt, *lp);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rrtfnd_obst_grid_build_device(const double* obst, int32_t n_obst, double node_radius, double lo_x, double hi_x,
+                                             double lo_y, double hi_y, double cell, double coord_max, rrtfnd_obst_grid_t* grid,
+                                             int32_t seg_cap, int32_t pt_cap, int32_t cells_cap, int32_t* overflow, void* stream) {
+    if (!grid || n_obst < 0 || (n_obst > 0 && !obst) || !(hi_x > lo_x) || !(hi_y > lo_y) || !overflow || !(coord_max > 0.0) ||
+        !(coord_max < 1e100)) return RRTFND_E_BADARG;
+    if (!grid->seg_start || !grid->seg_items || !grid->pt_start || !grid->pt_items) return RRTFND_E_BADARG;
+    int32_t* ss = const_cast<int32_t*>(grid->seg_start); int32_t* si = const_cast<int32_t*>(grid->seg_items);
+    int32_t* ps = const_cast<int32_t*>(grid->pt_start); int32_t* pi = const_cast<int32_t*>(grid->pt_items);
+    const double slope_max = 256.0;
+    const double w = hi_x - lo_x, h = hi_y - lo_y;
+    if (n_obst == 0) { grid->nx = grid->ny = 0; return 0; }
+    if (!(cell > 0.0)) cell = sqrt(w * h / (double)n_obst);
+    cell = fmax(cell, fmax(w, h) / 512.0);
+    const int nx = (int)fmin(512.0, fmax(1.0, ceil(w / cell))), ny = (int)fmin(512.0, fmax(1.0, ceil(h / cell)));
+    if ((long long)nx * ny + 1 > cells_cap) return RRTFND_E_BADARG;
+    grid->x0 = lo_x; grid->y0 = lo_y; grid->inv_cell = 1.0 / cell;
+    grid->slope_max = slope_max; grid->coord_max = coord_max; grid->margin = rrtfnd::grid_seg_margin(coord_max, slope_max);
+    grid->nx = nx; grid->ny = ny;
+    grid_build_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(obst, n_obst, node_radius, *grid, ss, si, ps, pi, seg_cap, pt_cap, overflow);
     return (int)cudaGetLastError();
 }

@@ -29,17 +29,19 @@ struct DevBuf {
 }  // namespace
 
 // ---- obstacle grid builder (pure host code) --------------------------------------------------------------
-extern "C" int rrtfnd_obst_grid_build_host(const double* obst_host, int32_t M, double node_radius, double lo_x,
-                                           double hi_x, double lo_y, double hi_y, double cell,
-                                           rrtfnd_obst_grid_t* g, int32_t* seg_start_host, int32_t* seg_items_host,
-                                           int32_t* pt_start_host, int32_t* pt_items_host, int64_t* n_items_out) {
+static int grid_build(const double* obst_host, int stride, int32_t M, double node_radius, double lo_x,
+                      double hi_x, double lo_y, double hi_y, double cell,
+                      rrtfnd_obst_grid_t* g, int32_t* seg_start_host, int32_t* seg_items_host,
+                      int32_t* pt_start_host, int32_t* pt_items_host, int64_t* n_items_out) {
     if (!g || M < 0 || (M > 0 && !obst_host) || !(hi_x > lo_x) || !(hi_y > lo_y) || !n_items_out) return RRTFND_E_BADARG;
     memset(g, 0, sizeof *g);
     n_items_out[0] = n_items_out[1] = 0;
     if (M == 0) return 0;                                       // nx == 0: culling disabled
     double S = fmax(fmax(fabs(lo_x), fabs(hi_x)), fmax(fabs(lo_y), fabs(hi_y)));
-    for (int j = 0; j < M; ++j)
-        for (int c = 0; c < 3; ++c) S = fmax(S, fabs(obst_host[3 * j + c]));
+    for (int j = 0; j < M; ++j) {
+        for (int c = 0; c < 3; ++c) S = fmax(S, fabs(obst_host[stride * j + c]));
+        if (stride == 4 && obst_host[4 * j + 2] < 0.0) S = fmax(S, fabs(obst_host[4 * j + 3]));   // a rectangle's half height
+    }
     if (!(S < 1e100)) return RRTFND_E_BADARG;
     const double slope_max = 256.0;
     const double margin = rrtfnd::grid_seg_margin(S, slope_max);
@@ -54,13 +56,17 @@ extern "C" int rrtfnd_obst_grid_build_host(const double* obst_host, int32_t M, d
     struct Box { int x0, x1, y0, y1; };
     std::vector<Box> bs((size_t)M), bp((size_t)M);
     for (int j = 0; j < M; ++j) {
-        const double ox = obst_host[3 * j], oy = obst_host[3 * j + 1], r = obst_host[3 * j + 2];
-        // segments: inflate by r + margin; points: by r + node_radius (Map.is_occupied_c); both with relative slack
-        const double Rs = (fabs(r) + margin) * 1.000000001, Rp = (fabs(r) + fabs(node_radius)) * 1.000000001;
-        bs[j] = Box{rrtfnd::grid_cell(ox - Rs, g->x0, g->inv_cell, nx), rrtfnd::grid_cell(ox + Rs, g->x0, g->inv_cell, nx),
-                    rrtfnd::grid_cell(oy - Rs, g->y0, g->inv_cell, ny), rrtfnd::grid_cell(oy + Rs, g->y0, g->inv_cell, ny)};
-        bp[j] = Box{rrtfnd::grid_cell(ox - Rp, g->x0, g->inv_cell, nx), rrtfnd::grid_cell(ox + Rp, g->x0, g->inv_cell, nx),
-                    rrtfnd::grid_cell(oy - Rp, g->y0, g->inv_cell, ny), rrtfnd::grid_cell(oy + Rp, g->y0, g->inv_cell, ny)};
+        const double ox = obst_host[stride * j], oy = obst_host[stride * j + 1], r = obst_host[stride * j + 2];
+        // half extents of the obstacle's own box: (r, r) for a circle, (hx, hy) for a rectangle row (cx, cy, -hx, hy)
+        const bool rect = stride == 4 && r < 0.0;
+        const double ex = fabs(r), ey = rect ? fabs(obst_host[4 * j + 3]) : fabs(r);
+        // segments: inflate by the margin; points: by node_radius (Map.is_occupied_c); both with relative slack
+        const double Sx = (ex + margin) * 1.000000001, Sy = (ey + margin) * 1.000000001;
+        const double Px = (ex + fabs(node_radius)) * 1.000000001, Py = (ey + fabs(node_radius)) * 1.000000001;
+        bs[j] = Box{rrtfnd::grid_cell(ox - Sx, g->x0, g->inv_cell, nx), rrtfnd::grid_cell(ox + Sx, g->x0, g->inv_cell, nx),
+                    rrtfnd::grid_cell(oy - Sy, g->y0, g->inv_cell, ny), rrtfnd::grid_cell(oy + Sy, g->y0, g->inv_cell, ny)};
+        bp[j] = Box{rrtfnd::grid_cell(ox - Px, g->x0, g->inv_cell, nx), rrtfnd::grid_cell(ox + Px, g->x0, g->inv_cell, nx),
+                    rrtfnd::grid_cell(oy - Py, g->y0, g->inv_cell, ny), rrtfnd::grid_cell(oy + Py, g->y0, g->inv_cell, ny)};
         for (int cy = bs[j].y0; cy <= bs[j].y1; ++cy) for (int cx = bs[j].x0; cx <= bs[j].x1; ++cx) ++cnt_s[(size_t)cy * nx + cx + 1];
         for (int cy = bp[j].y0; cy <= bp[j].y1; ++cy) for (int cx = bp[j].x0; cx <= bp[j].x1; ++cx) ++cnt_p[(size_t)cy * nx + cx + 1];
     }
@@ -76,6 +82,22 @@ extern "C" int rrtfnd_obst_grid_build_host(const double* obst_host, int32_t M, d
         for (int cy = bp[j].y0; cy <= bp[j].y1; ++cy) for (int cx = bp[j].x0; cx <= bp[j].x1; ++cx) pt_items_host[fp[(size_t)cy * nx + cx]++] = j;
     }
     return 0;
+}
+
+extern "C" int rrtfnd_obst_grid_build_host(const double* obst_host, int32_t M, double node_radius, double lo_x, double hi_x,
+                                           double lo_y, double hi_y, double cell, rrtfnd_obst_grid_t* g, int32_t* seg_start_host,
+                                           int32_t* seg_items_host, int32_t* pt_start_host, int32_t* pt_items_host,
+                                           int64_t* n_items_out) {
+    return grid_build(obst_host, 3, M, node_radius, lo_x, hi_x, lo_y, hi_y, cell, g, seg_start_host, seg_items_host, pt_start_host,
+                      pt_items_host, n_items_out);
+}
+
+extern "C" int rrtfnd_obst_grid_build_host4(const double* obst4_host, int32_t M, double node_radius, double lo_x, double hi_x,
+                                            double lo_y, double hi_y, double cell, rrtfnd_obst_grid_t* g, int32_t* seg_start_host,
+                                            int32_t* seg_items_host, int32_t* pt_start_host, int32_t* pt_items_host,
+                                            int64_t* n_items_out) {
+    return grid_build(obst4_host, 4, M, node_radius, lo_x, hi_x, lo_y, hi_y, cell, g, seg_start_host, seg_items_host, pt_start_host,
+                      pt_items_host, n_items_out);
 }
 
 extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const double* starts_goals_host,
@@ -111,7 +133,7 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
     // RRTFND_FLAG_OBST_HAS_K makes obst_host [M][4] = (ox, oy, r, K).
     const bool has_k = (prm->flags & RRTFND_FLAG_OBST_HAS_K) != 0;
     const size_t ostride = has_k ? 4 : 3;
-    std::vector<double> ob(4 * M + 4), ob3(3 * M + 3);
+    std::vector<double> ob(4 * M + 4);
     for (size_t j = 0; j < M; ++j) {
         const double ox = obst_host[ostride * j], oy = obst_host[ostride * j + 1], r = obst_host[ostride * j + 2];
         double K;
@@ -123,7 +145,6 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
             K = t + y2;
         }
         ob[4 * j] = ox; ob[4 * j + 1] = oy; ob[4 * j + 2] = r; ob[4 * j + 3] = K;
-        ob3[3 * j] = ox; ob3[3 * j + 1] = oy; ob3[3 * j + 2] = r;
     }
 
     // culling grid over the box that bounds xy_range and every start / goal
@@ -137,11 +158,11 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
     std::vector<int32_t> g_ss, g_si, g_ps, g_pi;
     if (M > 0 && hi_x > lo_x && hi_y > lo_y) {
         int64_t cnt[2];
-        int grc = rrtfnd_obst_grid_build_host(ob3.data(), (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, 0, 0, 0, 0, cnt);
+        int grc = rrtfnd_obst_grid_build_host4(ob.data(), (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, 0, 0, 0, 0, cnt);
         if (grc) return grc;
         const size_t ncells = (size_t)grid.nx * grid.ny;
         g_ss.resize(ncells + 1); g_ps.resize(ncells + 1); g_si.resize((size_t)cnt[0] + 1); g_pi.resize((size_t)cnt[1] + 1);
-        grc = rrtfnd_obst_grid_build_host(ob3.data(), (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, g_ss.data(),
+        grc = rrtfnd_obst_grid_build_host4(ob.data(), (int32_t)M, prm->node_radius, lo_x, hi_x, lo_y, hi_y, 0.0, &grid, g_ss.data(),
                                           g_si.data(), g_ps.data(), g_pi.data(), cnt);
         if (grc) return grc;
     }

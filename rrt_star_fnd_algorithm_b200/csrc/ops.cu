@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) points_occupied_kernel(const double* __re
             }
             if (live && !occ) {
                 bool h = false;
-                for (int j = lane; j < n; j += 32) h |= point_in_inflated(x, y, ox[j], oy[j], orr[j], node_radius);
+                for (int j = lane; j < n; j += 32) h |= point_in_inflated(x, y, ox[j], oy[j], orr[j], node_radius, oK[j]);
                 occ = __any_sync(kFullMask, h);
             }
         }

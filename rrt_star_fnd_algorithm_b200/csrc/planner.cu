@@ -38,28 +38,19 @@
 #define RRTFND_ANN_GROW 2
 #endif
 
-// Experiment knob (-DRRTFND_RANK_IN_NEAR=1, default off, unmeasured): after an annulus search the reference-equivalent
-// edge-check count needs the winner's rank among all nodes, today a separate pass over the tree (key_rank); the near-set
-// scan of the same iteration touches every node anyway and can count it on the side.
-#ifndef RRTFND_RANK_IN_NEAR
-#define RRTFND_RANK_IN_NEAR 0
+// Measured on B200 in round 2 and removed (profiles/r02_variants.md): the winner's rank counted inside the near-set scan instead
+// of a separate pass (-9 %: six more instructions in the hottest loop cost more than the pass they save), candidates split over
+// idle lanes (+-0), a first annulus bounded by the lanes' own minima (-4 %), persistent CTAs with the obstacle tables in shared
+// memory (hung), the segment test and the chain walk fused into one loop (-26 %).
+// Graph.get_cost walks of the candidate chunks: 0 = over the parent[] / ecost[] arrays (two loads per hop, one hop per memory
+// round trip); 1 = over the 16-byte walk records with the self-healing grandparent hint (walk_records: one load per hop, two
+// hops per round trip while the hints hold). Measured on B200 (profiles/r02_*): see DESIGN.md.
+#ifndef RRTFND_WALK_RECORDS
+#define RRTFND_WALK_RECORDS 0
 #endif
-// Experiment knob (-DRRTFND_SPLIT_CANDIDATES=1, default off, unmeasured): lane i owns candidate i, so a chunk of 12 ball nodes
-// leaves 20 lanes idle while 12 lanes walk ~10 circles each; with <= 16 (<= 8) candidates two (four) lanes share one
-// candidate's circle list (seg_blocked's first / stride pair) and the hit bits are folded back to the owner lane.
-#ifndef RRTFND_SPLIT_CANDIDATES
-#define RRTFND_SPLIT_CANDIDATES 0
-#endif
-// Experiment knob (-DRRTFND_LANE_MIN_HINT=1, default off, unmeasured): when the nearest node is blocked, every lane still holds
-// the nearest node of its own stride from the argmin scan; the lanes whose candidate lies within 8x the nearest distance test
-// theirs in parallel, and the nearest VISIBLE one bounds the search: one pass over (nearest, bound] replaces the doubling annuli.
-#ifndef RRTFND_LANE_MIN_HINT
-#define RRTFND_LANE_MIN_HINT 0
-#endif
-// Candidate chunks of the near set: 1 = each lane's segment test and parent-chain walk run in ONE loop over the walk records
-// (seg_walk_lane), and choose-parent's re-summed chain is prepared by all lanes at once; 0 = round 1's separate loops.
-#ifndef RRTFND_FUSED_WALK
-#define RRTFND_FUSED_WALK 1
+// choose-parent's re-summed chain (src/algorithm.py:849) prepared by all lanes at once (1) or re-summed at each acceptance (0)
+#ifndef RRTFND_CP_PARALLEL
+#define RRTFND_CP_PARALLEL 0
 #endif
 // resident warps per SM the lean instances' register allocation admits: 16 -> 128 registers, 20 -> 96, 24 -> 80
 #ifndef RRTFND_LEAN_MINW
@@ -143,15 +134,15 @@ static __device__ __noinline__ int point_occupied_lane(const double2* tab, const
     int j = 0, e = M;
     if (cull) {
         const int c = grid_cell(py, g->y0, g->inv_cell, g->ny) * g->nx + grid_cell(px, g->x0, g->inv_cell, g->nx);
-        j = RRTFND_TAB_LD(g->pt_start + c);
-        e = RRTFND_TAB_LD(g->pt_start + c + 1);
+        j = __ldg(g->pt_start + c);
+        e = __ldg(g->pt_start + c + 1);
     }
     int tests = 0;
     for (; j < e; ++j) {
         double ox, oy, r, K;
-        load_obst(tab, cull ? RRTFND_TAB_LD(g->pt_items + j) : j, ox, oy, r, K);
+        load_obst(tab, cull ? __ldg(g->pt_items + j) : j, ox, oy, r, K);
         ++tests;
-        if (point_in_inflated(px, py, ox, oy, r, node_radius)) return 2 * tests + 1;
+        if (point_in_inflated(px, py, ox, oy, r, node_radius, K)) return 2 * tests + 1;
     }
     return 2 * tests;
 }
@@ -261,95 +252,28 @@ static __device__ __noinline__ void wrec_rebuild(rrtfnd_walk_t* W, const int32_t
     __syncwarp();
 }
 
-// One lane's share of a candidate chunk: through_obstacle(Line(p1, p2)) over the culled circles of ITS segment (as
-// seg_blocked with first = 0, stride = 1) fused with ITS parent-chain walk (Graph.get_cost). One loop step = at most one
-// circle test and one walk round; the round's two record loads are issued before the circle's arithmetic and consumed after
-// it, so the pointer chase's memory latency hides behind the divisions and square roots of the segment test (and the other
-// way round). A hit abandons the walk (its sum is never used). `acc` starts as the caller's running sum; `rec_chain`
-// (one lane per chunk at most) receives the addends in order. Returns (circle tests << 1) | hit; depth = hops walked.
-__device__ __forceinline__ int seg_walk_lane(const double2* __restrict__ tab, const rrtfnd_obst_grid_t* __restrict__ g, int M,
-                                             int full_cells, bool has_seg, double p1x, double p1y, double p2x, double p2y,
-                                             rrtfnd_walk_t* W, int w_from, double* rec_chain, double& acc, int& depth) {
-    // ---- segment set-up (identical to seg_blocked)
-    Seg sg = make_seg(p1x, p1y, p2x, p2y);
-    int cy = 0, cy1 = -1, nx = 0;
-    double x0 = 0, y0 = 0, inv = 0, cell = 0, slack = 0, dxdy = 0;
-    const double ylo = p1y < p2y ? p1y : p2y, yhi = p1y < p2y ? p2y : p1y;
-    bool cull = false, flat = true, multi = false;
-    if (has_seg) {
-        cy1 = 0;                                             // one pseudo-row holding the whole table
-        if (full_cells > 0 && !sg.vertical && fabs(sg.m) <= g->slope_max) {
-            x0 = g->x0; y0 = g->y0; inv = g->inv_cell;
-            nx = g->nx;
-            cy = grid_cell(ylo, y0, inv, g->ny);
-            cy1 = grid_cell(yhi, y0, inv, g->ny);
-            multi = cy1 > cy;
-            cell = 1.0 / inv;
-            slack = g->coord_max * 1e-9;
-            dxdy = (p2x - p1x) / (p2y - p1y);
-            flat = !(fabs(dxdy) < 1e300);
-            cull = true;
+// Graph.get_cost over the walk records: leaf -> root, `acc` the running sum to start from; `rec_chain` (one lane per chunk at
+// most) receives the addends in order. Returns the hops walked. One round = the parent's and the guessed grandparent's
+// records requested together; a confirmed guess advances two hops for one memory round trip.
+__device__ __forceinline__ int walk_records(rrtfnd_walk_t* W, int from, double* rec_chain, double& acc) {
+    int depth = 0, v = from;
+    WRec rv = wrec_load(W, v);
+    while (rv.parent >= 0) {
+        const WRec rp = wrec_load(W, rv.parent);
+        WRec rg = rp;
+        if (rv.gp >= 0) rg = wrec_load(W, rv.gp);
+        if (rec_chain && depth < kChainCap) rec_chain[depth] = rv.ecost;
+        acc = dadd(acc, rv.ecost); ++depth;
+        if (rp.parent >= 0 && rv.gp == rp.parent) {          // the guess holds: the parent's edge as well, on to the grandparent
+            if (rec_chain && depth < kChainCap) rec_chain[depth] = rp.ecost;
+            acc = dadd(acc, rp.ecost); ++depth;
+            v = rv.gp; rv = rg;
+        } else {
+            if (rp.parent >= 0) wrec_store(W, v, rv.ecost, rv.parent, rp.parent);   // repair the hint (a benign same-value race)
+            v = rv.parent; rv = rp;
         }
     }
-    const int32_t* __restrict__ start = g->seg_start;
-    const int32_t* __restrict__ items = g->seg_items;
-    int j = 0, e = 0, tests = 0;
-    bool seg_live = has_seg, hit = false;
-    // ---- walk set-up: v = node whose edge is added next, rv = its record
-    depth = 0;
-    int v = w_from;
-    WRec rv; rv.ecost = 0.0; rv.parent = -1; rv.gp = -1;
-    if (v >= 0) rv = wrec_load(W, v);
-    bool walking = rv.parent >= 0;
-    while (seg_live || walking) {
-        WRec rp, rg;
-        rp.ecost = 0.0; rp.parent = -1; rp.gp = -1; rg = rp;
-        if (walking) {                                       // issued now, consumed after the circle test
-            rp = wrec_load(W, rv.parent);
-            if (rv.gp >= 0) rg = wrec_load(W, rv.gp);
-        }
-        if (seg_live) {
-            if (j >= e) {                                    // next row of cells (or the end of the segment)
-                if (cy > cy1) seg_live = false;
-                else {
-                    j = 0; e = M;
-                    if (cull) {
-                        double xa = sg.lo, xb = sg.hi;
-                        if (multi && !flat) {
-                            const double ra = fmax(y0 + cy * cell - slack, ylo), rb = fmin(y0 + (cy + 1) * cell + slack, yhi);
-                            const double xs = p1x + (ra - p1y) * dxdy, xe = p1x + (rb - p1y) * dxdy;
-                            xa = fmax(sg.lo, fmin(xs, xe) - slack);
-                            xb = fmin(sg.hi, fmax(xs, xe) + slack);
-                        }
-                        const int cx0 = grid_cell(xa, x0, inv, nx), cx1 = grid_cell(xb, x0, inv, nx);
-                        j = RRTFND_TAB_LD(start + cy * nx + cx0);
-                        e = RRTFND_TAB_LD(start + cy * nx + cx1 + 1);
-                    }
-                    ++cy;
-                }
-            } else {
-                double ox, oy, r, K;
-                load_obst(tab, cull ? RRTFND_TAB_LD(items + j) : j, ox, oy, r, K);
-                ++j; ++tests;
-                if (seg_hits_circle(sg, ox, oy, r, K)) { hit = true; seg_live = false; walking = false; }
-            }
-        }
-        if (walking) {
-            if (rec_chain && depth < kChainCap) rec_chain[depth] = rv.ecost;
-            acc = dadd(acc, rv.ecost); ++depth;
-            if (rp.parent >= 0 && rv.gp == rp.parent) {      // the guess holds: the parent's edge as well, on to the grandparent
-                if (rec_chain && depth < kChainCap) rec_chain[depth] = rp.ecost;
-                acc = dadd(acc, rp.ecost); ++depth;
-                v = rv.gp; rv = rg;
-            } else {
-                if (rp.parent >= 0) wrec_store(W, v, rv.ecost, rv.parent, rp.parent);   // repair the hint (a benign same-value race)
-                v = rv.parent; rv = rp;
-            }
-            walking = rv.parent >= 0;
-        }
-    }
-    if (hit) depth = 0;
-    return (tests << 1) | (hit ? 1 : 0);
+    return depth;
 }
 
 // ---- rare paths, kept out of line so that the per-iteration code stays small ---------------------------------
@@ -482,36 +406,6 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
     }
 }
 
-#if RRTFND_SMEM_TABLES
-__device__ unsigned g_plan_queue[1];      // next planner index of the running launch (reset by the host wrapper; one launch at a time)
-
-// bytes of the shared-memory copy of the tables: obstacle rows, then seg_start / seg_items / pt_start / pt_items
-__host__ __device__ inline size_t table_smem_bytes(int n_obst, int n_cells, int n_seg, int n_pt) {
-    return align_up((size_t)n_obst * 32, 16) + 2 * align_up((size_t)(n_cells + 1) * 4, 16) + align_up((size_t)n_seg * 4, 16) +
-           align_up((size_t)n_pt * 4, 16);
-}
-// Whole CTA: copy the tables behind `base`, publish a grid descriptor whose pointers address the copies; returns the bytes used.
-__device__ size_t stage_tables(const rrtfnd_batch_t& bt, int n_obst, unsigned char* base, rrtfnd_obst_grid_t* sg) {
-    const rrtfnd_obst_grid_t& g = bt.grid;
-    const int nc = g.nx * g.ny;
-    const int n_seg = nc > 0 ? __ldg(g.seg_start + nc) : 0, n_pt = nc > 0 ? __ldg(g.pt_start + nc) : 0;
-    double* tab = reinterpret_cast<double*>(base);
-    int32_t* ss = reinterpret_cast<int32_t*>(base + align_up((size_t)n_obst * 32, 16));
-    int32_t* ps = ss + align_up((size_t)(nc + 1) * 4, 16) / 4;
-    int32_t* si = ps + align_up((size_t)(nc + 1) * 4, 16) / 4;
-    int32_t* pi = si + align_up((size_t)n_seg * 4, 16) / 4;
-    for (int i = threadIdx.x; i < n_obst * 4; i += blockDim.x) tab[i] = bt.obst[i];
-    for (int i = threadIdx.x; i <= nc && nc > 0; i += blockDim.x) { ss[i] = g.seg_start[i]; ps[i] = g.pt_start[i]; }
-    for (int i = threadIdx.x; i < n_seg; i += blockDim.x) si[i] = g.seg_items[i];
-    for (int i = threadIdx.x; i < n_pt; i += blockDim.x) pi[i] = g.pt_items[i];
-    if (threadIdx.x == 0) {
-        *sg = g;
-        if (nc > 0) { sg->seg_start = ss; sg->seg_items = si; sg->pt_start = ps; sg->pt_items = pi; }
-    }
-    __syncthreads();
-    return table_smem_bytes(n_obst, nc, n_seg, n_pt);
-}
-#endif
 
 // WPB warps (= planners) per CTA; MINW = resident warps per SM the register allocation must allow (16 -> 128
 // registers, 24 -> 80, 32 -> 64): small batches get registers, large ones get occupancy.
@@ -522,27 +416,12 @@ template <int WPB, int MINW, bool NG, int MODE, bool RING>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-#if RRTFND_SMEM_TABLES
-    // Persistent CTA: the obstacle table and both culling lists are copied into shared memory once, then every warp pulls
-    // planners from a queue until it is empty (a finished planner's warp slot is reused at once, as with one planner per CTA).
-    __shared__ rrtfnd_obst_grid_t sgrid;
-    unsigned char* const warp_base = smem + stage_tables(bt, prm.n_obst, smem, &sgrid);
-    const double* const obst_tab = reinterpret_cast<const double*>(smem);
-    const rrtfnd_obst_grid_t* const obst_grid = &sgrid;
-    for (;;) {
-    __syncwarp();
-    int p = 0;
-    if (lane == 0) p = (int)atomicAdd(&g_plan_queue[0], 1u);
-    p = __shfl_sync(0xffffffffu, p, 0);
-    if (p >= bt.n_planners) break;
-#else
     unsigned char* const warp_base = smem;
     const double* const obst_tab = bt.obst;
     const rrtfnd_obst_grid_t* const obst_grid = &bt.grid;
     const int p = blockIdx.x * WPB + wib;
     if (p >= bt.n_planners) return;                       // whole warp leaves; warps never synchronise with each other
     {
-#endif
     const int C = prm.capacity;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -618,7 +497,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0;
     sb.pos = 0; sb.len = 0;
     __syncwarp();
-#if RRTFND_FUSED_WALK
+#if RRTFND_WALK_RECORDS
     wrec_rebuild(WREC, PARENT, ECOST, PL->n_slots, lane);
 #endif
 
@@ -675,7 +554,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             ++n_compactions;
             sb.pos = 0; sb.len = 0;       // the bitmap may have lain over the prepared attempts: prepare them again
             __syncwarp();
-#if RRTFND_FUSED_WALK
+#if RRTFND_WALK_RECORDS
             wrec_rebuild(WREC, PARENT, ECOST, n_slots, lane);
 #endif
         }
@@ -717,14 +596,8 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         // the visible ones is the node the reference would have stopped at, because everything in earlier annuli was
         // blocked. A boxed-in sample therefore costs O(log N) scans instead of O(N).
         int near_slot = -1;
-#if RRTFND_RANK_IN_NEAR
-        bool rank_pending = false; double rank_d = 0.0; int rank_s = 0; int my_rank = 0;
-#endif
         {
             double bd = CUDART_INF; int bs = kIntMax;
-#if RRTFND_LANE_MIN_HINT
-            double lane_d = CUDART_INF; int lane_s = kIntMax;
-#endif
             // what the scans below run over: the whole tree (TMA ring), or - node grid - the nodes of a window of cells
             const int32_t* list = nullptr;
             int n_items = n_slots, rho = 1;
@@ -750,9 +623,6 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         if (d < bd || (NG && d == bd && sl[u] < bs)) { bd = d; bs = sl[u]; }
                     }
                 }
-#if RRTFND_LANE_MIN_HINT
-                lane_d = bd; lane_s = bs;                                         // this lane's own nearest, before the reduction
-#endif
                 warp_argmin(bd, bs);
                 PH_MARK(1);                                                       // nearest scan
                 n_scan_nodes += list ? n_items : n_live;
@@ -781,28 +651,8 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 const double t_floor = dmul(dmul(prm.step_length, prm.step_length), 0.0625);
                 rounds = n_live;                                                  // if nothing is visible every node was tried
                 bool first_annulus = true;
-#if RRTFND_LANE_MIN_HINT
-                double hint_T = 0.0;                                              // squared distance of the nearest visible lane candidate
-                {
-                    bool vis = false;
-                    if (lane_s != kIntMax && lane_s != bs && lane_d <= dmul(bd, 64.0)) {
-                        const double2 c = XY[lane_s];
-                        const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, c.x, c.y, 0, 1);
-                        my_tests += r >> 1;
-                        vis = !(r & 1);
-                    }
-                    double hd = vis ? lane_d : CUDART_INF; int hs = vis ? lane_s : kIntMax;
-                    __syncwarp();
-                    warp_argmin(hd, hs);
-                    if (hs != kIntMax) hint_T = hd;
-                }
-#endif
                 for (;;) {
                     // any schedule of thresholds is exact; it trades full scans (one per annulus) against segment tests
-#if RRTFND_LANE_MIN_HINT
-                    if (first_annulus && hint_T > 0.0) T = hint_T;                 // the bound itself is staged and visible: one pass
-                    else
-#endif
                     T = dmul(T, first_annulus ? (double)RRTFND_ANN_FIRST : (double)RRTFND_ANN_GROW);
                     first_annulus = false;
                     if (T < t_floor) T = t_floor;
@@ -863,10 +713,6 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     warp_argmin(vd, vs);
                     if (vs != kIntMax) {
                         near_slot = vs;
-#if RRTFND_RANK_IN_NEAR
-                        if (!NG && mode != RRTFND_MODE_RRT) { rank_pending = true; rank_d = vd; rank_s = vs; rounds = 0; }
-                        else
-#endif
                         rounds = (NG && list) ? ng_key_rank(XY, list, n_items, qx, qy, vd, vs, lane)
                                               : key_rank(XY, n_slots, qx, qy, vd, vs, lane);
                         break;
@@ -898,7 +744,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             XY[new_slot] = make_double2(px, py);
             ID[new_slot] = id_new; PARENT[new_slot] = near_slot; ECOST[new_slot] = e0;   // :141-142
             NCHILD[new_slot] = 0; NFLAG[new_slot] = 0;
-#if RRTFND_FUSED_WALK
+#if RRTFND_WALK_RECORDS
             wrec_store(WREC, new_slot, e0, near_slot, PARENT[near_slot]);
 #endif
             if (NG) {                                                             // push onto its cell's list
@@ -977,12 +823,6 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int s = sl[u];
-#if RRTFND_RANK_IN_NEAR
-                    if (rank_pending && pass == 0) {                              // nodes with key <= the annulus winner's (NaN: false)
-                        const double dq = dist2(v[u].x, v[u].y, qx, qy);
-                        my_rank += ((dq < rank_d || (dq == rank_d && s <= rank_s)) && s != new_slot) ? 1 : 0;
-                    }
-#endif
                     const bool in = dist2(v[u].x, v[u].y, px, py) <= r2 && s != new_slot;
                     const unsigned m = __ballot_sync(kFull, in);
                     if (in) stage[count + __popc(m & lt_mask)] = s;
@@ -995,29 +835,6 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     const int n = min(count - head, first ? 31 : 32);
                     __syncwarp();
                     // ---- one chunk: lane i < n owns candidate i; in the first chunk lane 31 walks the new node's chain
-#if RRTFND_FUSED_WALK
-                    int s = -1; double dpl = 0.0, cc = 0.0, c_x = 0.0, c_y = 0.0;
-                    const bool mine = lane < n;
-                    if (mine) {
-                        s = stage[head + lane];
-                        const double2 c = XY[s];
-                        c_x = c.x; c_y = c.y;
-                        dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
-                        if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
-                    }
-                    // Line(node, q_new): p1 = node (:846 / :903) and Graph.get_cost(id) (:848 / :905) in one loop; lane 31 of the
-                    // first chunk walks the new node's chain from its parent, starts from its edge cost and records the addends
-                    const bool rec = first && lane == 31;
-                    int w_from = s, depth = 0;
-                    if (rec) { w_from = walk_from; cc = walk_acc; }
-                    const int r = seg_walk_lane(ob.tab, ob.g, ob.M, ob.full_cells, mine, c_x, c_y, px, py, WREC, w_from,
-                                                rec ? chain : nullptr, cc, depth);
-                    my_tests += r >> 1;
-                    my_hops += depth;
-                    const bool hit = !mine || (r & 1);
-                    __syncwarp();
-                    PH_MARK(6);                                                   // per-candidate segment tests + parent-chain walks
-#else
                     int s = -1; double dpl = 0.0, cc = 0.0; bool hit = true;
                     int w_from = -1;
                     if (lane < n) {
@@ -1026,30 +843,11 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
                         if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
                         // Line(node, q_new): p1 = node (:846 / :903)
-#if !RRTFND_SPLIT_CANDIDATES
                         const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
                         my_tests += r >> 1;
                         hit = r & 1;
                         if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
-#endif
                     }
-#if RRTFND_SPLIT_CANDIDATES
-                    {
-                        const int gl = n <= 8 ? 4 : n <= 16 ? 2 : 1;              // lanes per candidate (warp-uniform)
-                        const int ci = lane / gl, sub = lane % gl;
-                        int r = 0;
-                        if (ci < n) {
-                            const double2 c2 = XY[stage[head + ci]];
-                            r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c2.x, c2.y, px, py, sub, gl);
-                        }
-                        my_tests += r >> 1;
-                        const unsigned hits = __ballot_sync(kFull, r & 1);
-                        if (lane < n) {
-                            hit = ((hits >> (lane * gl)) & ((1u << gl) - 1u)) != 0;
-                            if (!hit) w_from = s;                                 // Graph.get_cost(id) (:848 / :905)
-                        }
-                    }
-#endif
                     // parent-chain walks, one loop for all lanes (Graph.get_cost, src/graph.py:41-46): lane 31 of the first
                     // chunk walks the new node's chain, starts from its edge cost and records the addends
                     const bool rec = first && lane == 31;
@@ -1057,6 +855,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     PH_MARK(6);                                                   // per-candidate segment tests
                     if (rec) { w_from = walk_from; cc = walk_acc; }
                     if (w_from >= 0) {
+#if RRTFND_WALK_RECORDS
+                        depth = walk_records(WREC, w_from, rec ? chain : nullptr, cc);
+#else
                         int wn = w_from, q = PARENT[wn];
                         while (q >= 0) {
                             const double e = ECOST[wn];
@@ -1065,16 +866,16 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                             wn = q; q = PARENT[wn];
                             ++depth;
                         }
+#endif
                         my_hops += depth;
                     }
                     __syncwarp();
                     PH_MARK(7);                                                   // parent-chain walks
-#endif
                     if (first) { cost_new = __shfl_sync(kFull, cc, 31); cp_cn = cost_new; chain_depth = __shfl_sync(kFull, depth, 31); }
                     if (do_cp) {
                         // choose_parent_kdtree's RETURNED edge (:845-852), candidates in ascending id
                         unsigned open = __ballot_sync(kFull, lane < n && !hit);
-#if RRTFND_FUSED_WALK
+#if RRTFND_CP_PARALLEL
                         // An accepted candidate sets G.cost[id_new] = its distance with the parent untouched, so get_cost(id_new)
                         // becomes that distance summed along id_near's chain (:849) - a value that depends on the candidate
                         // alone, not on the acceptances before it: every lane prepares its own, then the sequential pass over
@@ -1143,7 +944,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             if (pass == 0 && commit_cp && k_total > 0) {   // EXTENSION (not the shipped behaviour): adopt the returned edge
                 if (lane == 0) {
                     PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost;
-#if RRTFND_FUSED_WALK
+#if RRTFND_WALK_RECORDS
                     wrec_store(WREC, new_slot, cp_cost, cp_slot, PARENT[cp_slot]);
 #endif
                 }
@@ -1151,9 +952,6 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             }
         }
         if (__any_sync(kFull, dup)) { status = RRTFND_ST_DUPLICATE; break; }
-#if RRTFND_RANK_IN_NEAR
-        if (rank_pending) { const int rk = (int)warp_sum((long long)my_rank); n_edge_checks += rk; n_edge_checks_ref += rk; }
-#endif
         n_scan_nodes += nlist ? n_near_items : n_live;
         n_edge_checks += k_total;
         n_edge_checks_ref += 2 * (long long)k_total + 2;   // each candidate twice + Line(q_new, q_new) twice
@@ -1171,7 +969,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     PARENT[s] = new_slot;
                     const double ec = dist_plain(v.x, v.y, px, py);
                     ECOST[s] = ec;
-#if RRTFND_FUSED_WALK
+#if RRTFND_WALK_RECORDS
                     wrec_store(WREC, s, ec, new_slot, new_parent);            // its children keep a stale hint until a walk repairs it
 #endif
                     flagged |= NFLAG[s] & 1;
@@ -1337,7 +1135,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         PL->n_rewired = n_rewired; PL->n_removed = n_removed; PL->solution_found = solution_found;
         PL->n_compactions = n_compactions; PL->fn_count = fn_count;
     }
-    }   // one planner (RRTFND_SMEM_TABLES: next planner of the queue)
+    }
 }
 
 // Graph.__init__ (src/graph.py:25-32): a tree holding only the start node, id 0.
@@ -1369,24 +1167,6 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
     size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
     auto kern = plan_kernel<WPB, MINW, NG, MODE, RING>;
     int blocks = (bt->n_planners + WPB - 1) / WPB;
-#if RRTFND_SMEM_TABLES
-    {   // table sizes (two words back from the device: an experiment build can afford the synchronisation), queue reset,
-        // persistent grid of as many CTAs as fit
-        const int nc = bt->grid.nx * bt->grid.ny;
-        int n_seg = 0, n_pt = 0;
-        cudaError_t e0 = cudaSuccess;
-        if (nc > 0) {
-            e0 = cudaMemcpyAsync(&n_seg, bt->grid.seg_start + nc, 4, cudaMemcpyDeviceToHost, st);
-            if (e0 == cudaSuccess) e0 = cudaMemcpyAsync(&n_pt, bt->grid.pt_start + nc, 4, cudaMemcpyDeviceToHost, st);
-            if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(st);
-        }
-        if (e0 != cudaSuccess) return (int)e0;
-        bytes += table_smem_bytes(prm->n_obst, nc, n_seg, n_pt);
-        const unsigned zero = 0;
-        e0 = cudaMemcpyToSymbolAsync(g_plan_queue, &zero, 4, 0, cudaMemcpyHostToDevice, st);
-        if (e0 != cudaSuccess) return (int)e0;
-    }
-#endif
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
@@ -1394,17 +1174,6 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
         if (e != cudaSuccess) return (int)e;
     }
-#if RRTFND_SMEM_TABLES
-    {
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WPB, bytes);
-        if (e != cudaSuccess) return (int)e;
-        if (per_sm < 1) return RRTFND_E_SMEM;
-        if (blocks > sms * per_sm) blocks = sms * per_sm;
-    }
-#endif
     kern<<<blocks, 32 * WPB, bytes, st>>>(*prm, *bt);
     return (int)cudaGetLastError();
 }
@@ -1450,7 +1219,7 @@ static int check_params(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
     if ((prm->flags & RRTFND_FLAG_TRACE) && (!bt->trace || prm->trace_cap < 1)) return RRTFND_E_BADARG;
     if (!bt->planners || !bt->xy || !bt->ecost || !bt->parent || !bt->nchild || !bt->id || !bt->nflags || !bt->finish ||
         !bt->best_path || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
-#if RRTFND_FUSED_WALK
+#if RRTFND_WALK_RECORDS
     if (!bt->walk) return RRTFND_E_BADARG;
 #endif
     if (bt->grid.nx > 0 && (!bt->grid.seg_start || !bt->grid.seg_items || !bt->grid.pt_start || !bt->grid.pt_items ||
@@ -1500,13 +1269,6 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     // of the launch word overrides: 1 = plain loads, 2 / 4 = ring.
     const int stages_req = (prm->reserved >> 4) & 15;
     const bool ring = stages_req == 1 ? false : (stages_req == 2 || stages_req == 4) ? true : prm->capacity > 2048;
-#if RRTFND_SMEM_TABLES
-    // the tables are shared by the 8 warps of a persistent CTA, two CTAs per SM
-    if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<8, 16, false, RRTFND_MODE_STAR, true>(&q, &b, st)
-                                                        : launch_plan<8, 16, false, RRTFND_MODE_STAR, false>(&q, &b, st);
-    if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<8, 16, false, RRTFND_MODE_FN, true>(&q, &b, st)
-                                                      : launch_plan<8, 16, false, RRTFND_MODE_FN, false>(&q, &b, st);
-#endif
     if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, true>(&q, &b, st)
                                                         : launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, false>(&q, &b, st);
     if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_FN, true>(&q, &b, st)

@@ -34,8 +34,9 @@ MAX_ROUNDS = 4   # separate trees mended per tick (one per occupied stretch of t
 class FNDReplanner:
     """Drives the replanning ticks of a PlannerBatch whose planners hold a solution (run() it first)."""
 
-    def __init__(self, batch, reconnect_radius, regrow_iters=500):
+    def __init__(self, batch, reconnect_radius, regrow_iters=500, edge_invalidation=False):
         self.b = batch
+        self.edge_invalidation = bool(edge_invalidation)    # extension: also cut path EDGES that cross an obstacle
         self.reconnect_radius = float(reconnect_radius)
         self.regrow_iters = int(regrow_iters)
         pl = batch.planners()
@@ -68,6 +69,9 @@ class FNDReplanner:
         st = b.select_branch(cur)
         b.set_obstacles(obstacles)
         sep, err = b.valid_path(np.where(moving & (st == 0), cur, -1).astype(np.int32))
+        if self.edge_invalidation:
+            sep, cuts = b.cut_blocked_edges(np.where(err != 0, -1, sep).astype(np.int32))
+            self.stats["edge_cuts"] = self.stats.get("edge_cuts", 0) + int(cuts.sum())
         # is the robot's own node still there? (valid_path deletes an occupied root like any other path node)
         _, _, root_id = self._path_ends()
         bad = moving & ((st != 0) | (err != 0) | (root_id < 0))
@@ -102,3 +106,66 @@ class FNDReplanner:
         s["lost"], s["arrived"] = int((self.phase == LOST).sum()), int((self.phase == ARRIVED).sum())
         return dict(current=cur, status=st, separate_root=sep, index_error=err, linked=linked, regrow=grown,
                     regrow_iters=grown_its, phase=self.phase.copy())
+
+
+class DeviceFNDReplanner:
+    """The same loop with the bookkeeping on the device (rrtfnd_fnd_tick): per-planner phases and the tick's outcome live in
+    device arrays, a tick is one C-ABI call that only launches kernels, the moved obstacle table goes up with one asynchronous
+    copy and its culling grid is rebuilt by a kernel. Nothing is copied back unless the caller asks (`fetch=True`, what the
+    parity tests do; `stats` downloads 16 counters and the phases). Results are identical to FNDReplanner's."""
+
+    FIELDS = ("phase", "current", "status", "prev_root", "separate", "index_error", "edge_cuts", "todo", "regrow_arg",
+              "link_tmp", "regrow_tmp", "iters_tmp")
+
+    def __init__(self, batch, reconnect_radius, regrow_iters=500, edge_invalidation=False):
+        import ctypes as C
+        from ._structs import FndLoop
+        self.b = batch
+        self.reconnect_radius, self.regrow_iters = float(reconnect_radius), int(regrow_iters)
+        self.edge_invalidation = bool(edge_invalidation)
+        P, dev = batch.P, batch.device
+        pl = batch.planners()                               # the one download: the phases at the start
+        phase = np.where(pl["best_len"] >= 1, MOVING, LOST).astype(np.int32)
+        phase[(phase == MOVING) & (pl["best_len"] == 1)] = ARRIVED
+        self.t = {k: torch.zeros(P, dtype=torch.int32, device=dev) for k in self.FIELDS}
+        self.t["phase"] = torch.from_numpy(phase).to(dev)
+        for k in ("linked", "regrow", "regrow_iters"):
+            self.t[k] = torch.zeros((P, MAX_ROUNDS), dtype=torch.int32, device=dev)
+        self.stats_t = torch.zeros(16, dtype=torch.int64, device=dev)
+        lp = FndLoop()
+        lp.max_rounds = MAX_ROUNDS
+        for k in self.FIELDS + ("linked", "regrow", "regrow_iters"):
+            setattr(lp, k, self.t[k].data_ptr())
+        lp.stats = self.stats_t.data_ptr()
+        self._lp, self._C = lp, C
+        self.ticks = 0
+
+    def tick(self, obstacles, fetch=True):
+        """One replanning tick against `obstacles` [(ox, oy, r), ...] (or table rows (ox, oy, r, K)). With fetch=True returns the
+        same per-planner arrays as FNDReplanner.tick (one download); with fetch=False nothing leaves the device."""
+        from . import _abi
+        from .batch import obstacle_table
+        b, C = self.b, self._C
+        b.set_obstacle_table_async(obstacle_table(obstacles))
+        with torch.cuda.device(b.device):
+            bt = b._batch()
+            _abi.check(_abi.lib.rrtfnd_fnd_tick(C.byref(b.prm), C.byref(bt), C.byref(self._lp), self.reconnect_radius,
+                                                self.regrow_iters, int(self.edge_invalidation), b._stream()), "rrtfnd_fnd_tick")
+        self.ticks += 1
+        if not fetch:
+            return None
+        g = {k: self.t[k].cpu().numpy() for k in ("current", "status", "separate", "index_error", "linked", "regrow", "regrow_iters",
+                                                  "phase", "edge_cuts")}
+        return dict(current=g["current"], status=g["status"], separate_root=g["separate"], index_error=g["index_error"],
+                    linked=g["linked"], regrow=g["regrow"], regrow_iters=g["regrow_iters"], phase=g["phase"], edge_cuts=g["edge_cuts"])
+
+    @property
+    def phase(self):
+        return self.t["phase"].cpu().numpy()
+
+    @property
+    def stats(self):
+        s = self.stats_t.cpu().numpy()
+        ph = self.phase
+        return dict(moves=int(s[0]), splits=int(s[1]), reconnected=int(s[2]), regrown=int(s[3]), regrow_extensions=int(s[4]),
+                    lost=int((ph == LOST).sum()), arrived=int((ph == ARRIVED).sum()), edge_cuts=int(s[8]))

@@ -13,7 +13,9 @@ import numpy as np
 class Map:
     def __init__(self, size: tuple, start: tuple, goal: tuple, node_radius: int):
         self.obstacles_c = []   # circles: [(x, y), r]
-        self.obstacles_r = []   # rectangles: declared by the reference, never implemented there (src/map.py:18, :54)
+        # rectangles [(cx, cy), (hx, hy)] (centre, half extents): the list is declared by the reference and never filled or
+        # tested there (src/map.py:18, :54); here it is an EXTENSION with builder-defined semantics (include/rrtfnd.h)
+        self.obstacles_r = []
         self.width = size[0]
         self.height = size[1]
         self.start = start
@@ -23,6 +25,12 @@ class Map:
     def add_obstacles(self, obstacles):
         for obstacle in obstacles:
             self.obstacles_c.append(obstacle)
+
+    def add_rectangles(self, rectangles):
+        """Extension: axis-aligned rectangles `[(cx, cy), (hx, hy)]`, tested like the circles (segments against the raw
+        shape, points against the shape inflated by node_radius)."""
+        for rect in rectangles:
+            self.obstacles_r.append(rect)
 
     def obstacle_table(self) -> np.ndarray:
         """[M][3] float64 (x, y, r) view of obstacles_c."""
@@ -35,15 +43,15 @@ class Map:
         from . import _abi
         from .batch import obstacle_table
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
-        if len(pts) == 0 or not self.obstacles_c:
+        if len(pts) == 0 or not (self.obstacles_c or self.obstacles_r):
             return np.zeros(len(pts), dtype=bool)
         dev = torch.device("cuda", torch.cuda.current_device())
-        tab = torch.from_numpy(obstacle_table(self.obstacles_c)).to(dev)
+        tab = torch.from_numpy(obstacle_table(self.obstacles_c, self.obstacles_r)).to(dev)
         px, py = torch.from_numpy(pts[:, 0].copy()).to(dev), torch.from_numpy(pts[:, 1].copy()).to(dev)
         out = torch.zeros(len(pts), dtype=torch.uint8, device=dev)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _abi.check(_abi.lib.rrtfnd_points_occupied(C.c_void_p(px.data_ptr()), C.c_void_p(py.data_ptr()), len(pts),
-                                                   C.c_void_p(tab.data_ptr()), len(self.obstacles_c),
+                                                   C.c_void_p(tab.data_ptr()), len(tab),
                                                    float(self.node_radius), C.c_void_p(out.data_ptr()), st),
                    "rrtfnd_points_occupied")
         return out.cpu().numpy().astype(bool)

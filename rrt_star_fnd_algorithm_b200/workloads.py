@@ -41,6 +41,24 @@ def c2():
                 seed_base=1000, planners=4096)
 
 
+def c2r():
+    """Config 2 as BASELINE.json words it ("200 rectangular obstacles"): the same centres as c2, axis-aligned rectangles with
+    half extents U(0.5, 2.0)^2 instead of circles. Rectangles are an EXTENSION - the reference declares Map.obstacles_r and
+    never implements it (src/map.py:18, :54) - so this variant is parity-unpinned by the reference (pinned on the oracle)."""
+    w = c2()
+    rng = np.random.default_rng(22)
+    rects = []
+    for (cx, cy, _) in w["obstacles"]:
+        while True:
+            hx, hy = rng.uniform(0.5, 2.0, 2)
+            clear = all(max(abs(p[0] - cx) - hx, 0.0) ** 2 + max(abs(p[1] - cy) - hy, 0.0) ** 2 >= (w["node_radius"] + 1e-9) ** 2
+                        for p in (w["start"], w["goal"]))
+            if clear:
+                break
+        rects.append((float(cx), float(cy), -float(hx), float(hy)))       # table rows (cx, cy, -hx, hy)
+    return dict(w, name="c2r", obstacles=rects, seed_base=2000)
+
+
 def c3():
     """Config 3: RRT*, 200x200 map, 500 circles, 16,384 planners with random start/goal, 5,000 iterations."""
     obst = _circles(3, 500, 0, 200, 1.0, 4.0)
@@ -91,7 +109,7 @@ def c5():
                 seed_base=5000, planners=4096, ticks=ticks, reconnect_radius=15.0, regrow_iters=100)
 
 
-WORKLOADS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
+WORKLOADS = {"c1": c1, "c2": c2, "c2r": c2r, "c3": c3, "c4": c4, "c5": c5}
 
 
 def planner_problems(w, first, count):

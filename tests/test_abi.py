@@ -17,12 +17,13 @@ def header_functions():
 
 def test_library_exports_every_declared_symbol():
     from rrt_star_fnd_algorithm_b200 import _abi
+    from rrt_star_fnd_algorithm_b200._structs import ABI_VERSION as S_ABI
     names = header_functions()
     assert len(names) >= 15
     for n in names:
         assert hasattr(_abi.lib, n), f"{n} is declared in include/rrtfnd.h but missing from librrtfnd.so"
     assert sorted(_abi.EXPORTS) == names, "the ctypes binding list and the header disagree"
-    assert _abi.lib.rrtfnd_abi_version() == 2
+    assert _abi.lib.rrtfnd_abi_version() == S_ABI
 
 
 def test_struct_mirrors_match_the_header_layout():
@@ -36,6 +37,8 @@ def test_struct_mirrors_match_the_header_layout():
     int main(void) {
         printf("%zu %zu %zu %zu %zu\n", sizeof(rrtfnd_params_t), sizeof(rrtfnd_planner_t), sizeof(rrtfnd_trace_t),
                sizeof(rrtfnd_batch_t), sizeof(rrtfnd_obst_grid_t));
+        printf("%zu %zu %zu %zu\n", sizeof(rrtfnd_fnd_loop_t), offsetof(rrtfnd_fnd_loop_t, stats), offsetof(rrtfnd_batch_t, walk),
+               sizeof(rrtfnd_walk_t));
         printf("%zu %zu %zu %zu\n", offsetof(rrtfnd_params_t, step_length), offsetof(rrtfnd_planner_t, n_slots),
                offsetof(rrtfnd_batch_t, grid), offsetof(rrtfnd_obst_grid_t, seg_start));
         return 0;
@@ -45,6 +48,8 @@ def test_struct_mirrors_match_the_header_layout():
         subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")], text=True).split()
     sizes = [int(v) for v in out]
+    assert sizes[5:9] == [C.sizeof(S.FndLoop), S.FndLoop.stats.offset, S.Batch.walk.offset, 16]
+    sizes = sizes[:5] + sizes[9:]
     assert sizes[:5] == [C.sizeof(S.Params), C.sizeof(S.Planner), C.sizeof(S.Trace), C.sizeof(S.Batch), C.sizeof(S.ObstGrid)]
     assert sizes[5:] == [S.Params.step_length.offset, S.Planner.n_slots.offset, S.Batch.grid.offset, S.ObstGrid.seg_start.offset]
 

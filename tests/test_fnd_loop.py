@@ -22,14 +22,15 @@ def small_c5(iter_num=1500, max_nodes=400):
     return w
 
 
-def oracle_planners(w, P, ticks):
+def oracle_planners(w, P, ticks, edges=False):
     s, g, seeds, sids = W.planner_problems(w, 0, P)
     prm = K.params_for(w, stream_mode=S.STREAM_PHILOX, flags=0)
     out = []
     for p in range(P):
         t = O.OracleTree(s[p], w["iter_num"] + 2 + ticks * w["regrow_iters"])
         assert t.run(prm, w["obstacles"], g[p], seed=int(seeds[p]), stream_id=int(sids[p]))[0] == S.ST_DONE
-        out.append(OracleReplanner(t, prm, g[p], seeds[p], sids[p], w["node_radius"], w["reconnect_radius"], w["regrow_iters"]))
+        out.append(OracleReplanner(t, prm, g[p], seeds[p], sids[p], w["node_radius"], w["reconnect_radius"], w["regrow_iters"],
+                                   edge_invalidation=edges))
     return out
 
 
@@ -132,6 +133,14 @@ class OracleBackedBatch:
         self._refresh()
         return sep, err
 
+    def cut_blocked_edges(self, sep):
+        out, cuts = np.array(sep, np.int32).copy(), np.zeros(self.P, np.int32)
+        for p, (r, s_) in enumerate(zip(self.reps, sep)):
+            if s_ >= 0:
+                out[p], cuts[p] = r.t.cut_blocked_edges(self.obstacles, int(s_))
+        self._refresh()
+        return out, cuts
+
     def reconnect(self, ids, radius):
         out = np.array([r.t.reconnect(self.obstacles, int(i), radius, int(r.t.best_path()[0])) if i >= 0 else -1
                         for r, i in zip(self.reps, ids)], np.int32)
@@ -147,13 +156,14 @@ class OracleBackedBatch:
         return res, its
 
 
-def test_product_loop_host_logic_equals_the_oracle_loop_on_oracle_trees():
+@pytest.mark.parametrize("edges", [False, True], ids=["nodes", "nodes+edges"])
+def test_product_loop_host_logic_equals_the_oracle_loop_on_oracle_trees(edges):
     from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner
     w = small_c5()
     P, T = 10, w["ticks"]
     fake = OracleBackedBatch(w, P, T)
-    loop = FNDReplanner(fake, w["reconnect_radius"], w["regrow_iters"])
-    reps = oracle_planners(w, P, T)
+    loop = FNDReplanner(fake, w["reconnect_radius"], w["regrow_iters"], edge_invalidation=edges)
+    reps = oracle_planners(w, P, T, edges)
     assert list(loop.phase) == [r.phase for r in reps]
     for k in range(1, T + 1):
         ob = moved_obstacles(w["obstacles"], w["velocity"], k)
@@ -169,12 +179,39 @@ def test_product_loop_host_logic_equals_the_oracle_loop_on_oracle_trees():
             assert list(got["regrow_iters"][p]) == want["regrow_iters"], what
             assert_tree_equal(fake.reps[p].t.export(), r.t.export(), what)
     assert loop.stats["splits"] >= 15 and loop.stats["regrown"] >= 2 and loop.stats["moves"] > 5 * P
+    if edges:
+        assert loop.stats["edge_cuts"] >= 3, loop.stats       # the extension really cut something the node test missed
+
+
+def test_edge_invalidation_cuts_what_the_node_test_misses():
+    """An obstacle dropped BETWEEN two path nodes: valid_path (nodes only, src/algorithm.py:356) sees nothing, the edge
+    extension cuts that edge and returns the goal-side node as the separate root."""
+    case = K.case_by_name("float_star")
+    prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0)
+    t = O.OracleTree(case["start"], case["iter_num"] + 2)
+    assert t.run(prm, case["obstacles"], case["goal"], seed=case["seed"], stream_id=case["stream_id"])[0] == S.ST_DONE
+    path = [int(i) for i in t.best_path()]
+    e = t.export()
+    pos = {int(i): (e["x"][k], e["y"][k]) for k, i in enumerate(e["ids"])}
+    k = len(path) // 2
+    a, b = pos[path[k]], pos[path[k + 1]]
+    mid = (0.5 * (a[0] + b[0]), 0.5 * (a[1] + b[1]), 0.05)            # a small circle on the edge, clear of both nodes
+    obst = list(case["obstacles"]) + [mid]
+    sep, err = t.valid_path(obst, 0.0, path[-1])
+    assert not err and sep == path[-1]                                # node test: nothing is occupied (node_radius 0 here)
+    sep2, cuts = t.cut_blocked_edges(obst, sep)
+    assert cuts == 1 and sep2 == path[k]
+    e2 = t.export()
+    par = dict(zip([int(i) for i in e2["ids"]], [int(q) for q in e2["parent"]]))
+    assert par[path[k]] == -1 and len(e2["ids"]) == len(e["ids"])     # cut, nothing deleted
 
 
 @pytest.mark.gpu
-def test_gpu_fnd_loop_matches_the_oracle_loop_tick_by_tick():
+@pytest.mark.parametrize("kind,edges", [("host", False), ("device", False), ("host", True), ("device", True)],
+                         ids=["host-loop", "device-loop", "host-loop+edges", "device-loop+edges"])
+def test_gpu_fnd_loop_matches_the_oracle_loop_tick_by_tick(kind, edges):
     from rrt_star_fnd_algorithm_b200.batch import PlannerBatch, fn_capacity
-    from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner
+    from rrt_star_fnd_algorithm_b200.fnd_loop import DeviceFNDReplanner, FNDReplanner
     w = small_c5()
     P, T = 16, w["ticks"]
     s, g, seeds, sids = W.planner_problems(w, 0, P)
@@ -183,10 +220,10 @@ def test_gpu_fnd_loop_matches_the_oracle_loop_tick_by_tick():
                      max_nodes=w["max_nodes"], seeds=seeds, stream_ids=sids).run()
     b.check_status()
     b.grow_capacity(fn_capacity(w["max_nodes"]) + T * w["regrow_iters"])      # room for the regrow() extensions
-    reps = oracle_planners(w, P, T)
+    reps = oracle_planners(w, P, T, edges)
     for p in range(P):
         assert_tree_equal(b.tree(p), reps[p].t.export(), f"planned[{p}]")
-    loop = FNDReplanner(b, w["reconnect_radius"], w["regrow_iters"])
+    loop = (DeviceFNDReplanner if kind == "device" else FNDReplanner)(b, w["reconnect_radius"], w["regrow_iters"], edge_invalidation=edges)
     assert list(loop.phase) == [r.phase for r in reps]
     seen = dict(linked=0, regrown=0)
     for k in range(1, T + 1):

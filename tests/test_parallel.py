@@ -109,8 +109,17 @@ def test_bench_config_is_shared_by_both_arms():
     from rrt_star_fnd_algorithm_b200 import workloads as W
     args = argparse.Namespace(launch=0, near_cap=64)
     c = bench.bench_config(W.c3(), 16384, 1, args, 5002)
-    assert c["workload"].startswith("c3: star x 16384 planners per GPU (16384 total), 500 circular obstacles, 5000 iterations")
+    assert c["workload"].startswith("c3: star x 16384 planners in total, 16384 per GPU (strong scaling), 500 circular obstacles, 5000 iterations")
     assert bench.DEFAULT_PLANNERS["c3"] == 16384 and bench.METRIC == "rrt_star_tree_extensions_per_sec"
+    # config 3 as BASELINE.json words it: 16,384 planners SHARDED over the GPUs (strong scaling) unless a per-GPU batch is asked for
+    ns = lambda **k: argparse.Namespace(workload="c3", planners=0, scaling="strong", **k)
+    assert [bench.planner_layout(ns(), 8, r) for r in (0, 7)] == [(2048, 0, "strong"), (2048, 14336, "strong")]
+    assert bench.planner_layout(ns(), 1, 0) == (16384, 0, "strong")
+    assert bench.planner_layout(argparse.Namespace(workload="c3", planners=0, scaling="weak"), 4, 2) == (16384, 32768, "weak")
+    assert bench.planner_layout(argparse.Namespace(workload="c3", planners=512, scaling="strong"), 4, 3) == (512, 1536, "weak")
+    assert bench.planner_layout(argparse.Namespace(workload="c4", planners=0, scaling="strong"), 8, 5) == (1, 5, "weak")   # replicas
+    c8 = bench.bench_config(W.c3(), 2048, 8, args, 5002, "strong")
+    assert c8["planners_total"] == 16384 and c8["planners_per_gpu"] == 2048
 
 
 def test_bench_cpu_legs_run_on_small_samples():
