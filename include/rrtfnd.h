@@ -191,11 +191,12 @@ typedef struct rrtfnd_batch {
     rrtfnd_trace_t* trace;      /* [P][trace_cap] or NULL */
     rrtfnd_obst_grid_t grid;    /* optional culling grid over obst */
     rrtfnd_node_grid_t node_grid; /* optional grid over the nodes (RRTFND_FLAG_NODE_GRID) */
-    rrtfnd_walk_t* walk;        /* [P][capacity] scratch of rrtfnd_plan_batch or NULL: a 16-byte copy of (ecost, parent) per node
-                                 * plus a self-healing guess of the grandparent slot, rebuilt from ecost / parent at the start of
-                                 * every call. Graph.get_cost's leaf -> root walk (src/graph.py:41-46) reads ONE record per hop
-                                 * and, while the guesses hold, fetches two hops per memory round trip. Never read by the host;
-                                 * ecost / parent stay the truth. NULL = walk the ecost / parent arrays. */
+    rrtfnd_walk_t* walk;        /* [P][capacity] scratch of rrtfnd_plan_batch, required with RRTFND_FLAG_NODE_GRID, else unused (may
+                                 * be NULL): a 16-byte copy of (ecost, parent) per node plus a self-healing guess of the
+                                 * grandparent slot, rebuilt from ecost / parent at the start of every call. The node-grid kernel's
+                                 * Graph.get_cost walks (src/graph.py:41-46; hundreds of hops in a large tree) read ONE record per
+                                 * hop and, while the guesses hold, fetch two hops per memory round trip. Never read by the host;
+                                 * ecost / parent stay the truth. */
 } rrtfnd_batch_t;
 
 /* ---- library info ------------------------------------------------------------------------ */

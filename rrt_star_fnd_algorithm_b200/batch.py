@@ -129,7 +129,8 @@ class PlannerBatch:
         self.nchild = torch.empty((P, Cn), dtype=torch.int32, device=dev)
         self.id = torch.empty((P, Cn), dtype=torch.int32, device=dev)
         self.nflags = torch.zeros((P, Cn), dtype=torch.uint8, device=dev)
-        self.walk = torch.empty((P, Cn, 2), dtype=torch.float64, device=dev)     # rrtfnd_walk_t scratch of the planner kernel
+        # rrtfnd_walk_t scratch: the node-grid kernel of large single trees walks parent chains over 16-byte records
+        self.walk = torch.empty((P, Cn, 2), dtype=torch.float64, device=dev) if node_grid else None
         self.finish = torch.empty((P, prm.finish_cap), dtype=torch.int32, device=dev)
         self.best_path_t = torch.empty((P, prm.path_cap), dtype=torch.int32, device=dev)
         self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(dev)
@@ -240,7 +241,6 @@ class PlannerBatch:
             new = torch.zeros((self.P, capacity) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
             new[:, :old] = t
             setattr(self, name, new)
-        self.walk = torch.empty((self.P, capacity, 2), dtype=torch.float64, device=self.device)
         self.prm.capacity = capacity
 
     def restore_problems(self):
@@ -256,7 +256,6 @@ class PlannerBatch:
         for name in ("xy", "ecost", "parent", "nchild", "id", "nflags"):
             t = getattr(self, name)
             setattr(self, name, torch.zeros((self.P, int(capacity)) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device))
-        self.walk = torch.empty((self.P, int(capacity), 2), dtype=torch.float64, device=self.device)
         self.prm.capacity = int(capacity)
         self._initialised = False
 

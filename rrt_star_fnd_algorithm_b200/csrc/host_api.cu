@@ -167,9 +167,9 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         if (grc) return grc;
     }
 
-    DevBuf d_pl, d_xy, d_e, d_par, d_nc, d_id, d_fl, d_fin, d_bp, d_ob, d_w, d_gss, d_gsi, d_gps, d_gpi, d_wk;
+    DevBuf d_pl, d_xy, d_e, d_par, d_nc, d_id, d_fl, d_fin, d_bp, d_ob, d_w, d_gss, d_gsi, d_gps, d_gpi;
     CK(d_pl.alloc((size_t)P * sizeof(rrtfnd_planner_t)));
-    CK(d_xy.alloc(n * 16)); CK(d_e.alloc(n * 8)); CK(d_wk.alloc(n * sizeof(rrtfnd_walk_t)));
+    CK(d_xy.alloc(n * 16)); CK(d_e.alloc(n * 8));
     CK(d_par.alloc(n * 4)); CK(d_nc.alloc(n * 4)); CK(d_id.alloc(n * 4)); CK(d_fl.alloc(n));
     CK(d_gss.alloc(g_ss.size() * 4)); CK(d_gsi.alloc(g_si.size() * 4));
     CK(d_gps.alloc(g_ps.size() * 4)); CK(d_gpi.alloc(g_pi.size() * 4));
@@ -202,7 +202,6 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         bt.xy = (double*)d_xy.p; bt.ecost = (double*)d_e.p;
         bt.parent = (int32_t*)d_par.p; bt.nchild = (int32_t*)d_nc.p; bt.id = (int32_t*)d_id.p; bt.nflags = (uint8_t*)d_fl.p;
         bt.grid = grid;
-        bt.walk = (rrtfnd_walk_t*)d_wk.p;
         bt.finish = (int32_t*)d_fin.p; bt.best_path = (int32_t*)d_bp.p; bt.obst = (const double*)d_ob.p;
         bt.words = (const uint32_t*)d_w.p; bt.trace = nullptr;
         rrtfnd_params_t q = *prm;

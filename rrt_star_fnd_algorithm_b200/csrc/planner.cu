@@ -42,15 +42,15 @@
 // of a separate pass (-9 %: six more instructions in the hottest loop cost more than the pass they save), candidates split over
 // idle lanes (+-0), a first annulus bounded by the lanes' own minima (-4 %), persistent CTAs with the obstacle tables in shared
 // memory (hung), the segment test and the chain walk fused into one loop (-26 %).
-// Graph.get_cost walks of the candidate chunks: 0 = over the parent[] / ecost[] arrays (two loads per hop, one hop per memory
-// round trip); 1 = over the 16-byte walk records with the self-healing grandparent hint (walk_records: one load per hop, two
-// hops per round trip while the hints hold). Measured on B200 (profiles/r02_*): see DESIGN.md.
-#ifndef RRTFND_WALK_RECORDS
-#define RRTFND_WALK_RECORDS 0
-#endif
-// choose-parent's re-summed chain (src/algorithm.py:849) prepared by all lanes at once (1) or re-summed at each acceptance (0)
+// Graph.get_cost walks of the candidate chunks: over the parent[] / ecost[] arrays (two loads per hop, one hop per memory
+// round trip), or - kernels instantiated with WREC, the node-grid kernel of large single trees - over the 16-byte walk
+// records with the self-healing grandparent hint (walk_records: one load per hop, two hops per round trip while the hints
+// hold). Measured on B200 (profiles/r02_variants.md): +1 % on c3's 5,000-node trees, -8 % on c2's L1-resident 1,000-node
+// trees, so the batch kernels keep the arrays; parent chains of hundreds of hops (config 4) are where the records pay.
+// choose-parent's re-summed chain (src/algorithm.py:849) is prepared by all lanes at once (1: +4.7 % on c3, measured) or
+// re-summed at each acceptance (0, round 1's form).
 #ifndef RRTFND_CP_PARALLEL
-#define RRTFND_CP_PARALLEL 0
+#define RRTFND_CP_PARALLEL 1
 #endif
 // resident warps per SM the lean instances' register allocation admits: 16 -> 128 registers, 20 -> 96, 24 -> 80
 #ifndef RRTFND_LEAN_MINW
@@ -412,7 +412,7 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
 // MODE >= 0 is a LEAN instance: that planner mode with choose-parent evaluated but not committed and no trace — the
 // configuration batches run in — so the other modes' code, the trace writes and the second near-set pass are not even
 // compiled in (the kernel's instruction footprint is what limits it, profiles/). MODE = -1 takes everything at run time.
-template <int WPB, int MINW, bool NG, int MODE, bool RING>
+template <int WPB, int MINW, bool NG, int MODE, bool RING, bool WREC = NG>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     int32_t* FINISH = bt.finish + (size_t)p * prm.finish_cap;
     int32_t* BPATH = bt.best_path + (size_t)p * prm.path_cap;
     rrtfnd_planner_t* PL = bt.planners + p;
-    rrtfnd_walk_t* WREC = bt.walk + (size_t)p * C;
+    rrtfnd_walk_t* WR = WREC ? bt.walk + (size_t)p * C : nullptr;
     constexpr bool kLean = MODE >= 0;
     // Prepared attempt batches pay where rejected attempts are frequent and nothing else draws from the stream between
     // attempts; RRT*-FN draws in forced_removal after every extension once the cap is reached, which discards the batch
@@ -497,9 +497,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     rng.have_blk = false; rng.exhausted = false; rng.blk_idx = 0; rng.b0 = rng.b1 = rng.b2 = rng.b3 = 0;
     sb.pos = 0; sb.len = 0;
     __syncwarp();
-#if RRTFND_WALK_RECORDS
-    wrec_rebuild(WREC, PARENT, ECOST, PL->n_slots, lane);
-#endif
+    if (WREC) wrec_rebuild(WR, PARENT, ECOST, PL->n_slots, lane);
 
     // slot of the cached best path's leaf (ids ascend with slots: binary search around tombstones)
     int best_leaf_slot = -1;
@@ -554,9 +552,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             ++n_compactions;
             sb.pos = 0; sb.len = 0;       // the bitmap may have lain over the prepared attempts: prepare them again
             __syncwarp();
-#if RRTFND_WALK_RECORDS
-            wrec_rebuild(WREC, PARENT, ECOST, n_slots, lane);
-#endif
+            if (WREC) wrec_rebuild(WR, PARENT, ECOST, n_slots, lane);
         }
         // ================================================================ A/B. Graph.random_node (src/graph.py:96-98) and
         // Map.is_occupied_c (src/map.py:38-47; rejection at src/algorithm.py:39-40)
@@ -744,9 +740,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             XY[new_slot] = make_double2(px, py);
             ID[new_slot] = id_new; PARENT[new_slot] = near_slot; ECOST[new_slot] = e0;   // :141-142
             NCHILD[new_slot] = 0; NFLAG[new_slot] = 0;
-#if RRTFND_WALK_RECORDS
-            wrec_store(WREC, new_slot, e0, near_slot, PARENT[near_slot]);
-#endif
+            if (WREC) wrec_store(WR, new_slot, e0, near_slot, PARENT[near_slot]);
             if (NG) {                                                             // push onto its cell's list
                 const int c = grid_cell(py, ng.y0, ng.inv_cell, ng.ny) * ng.nx + grid_cell(px, ng.x0, ng.inv_cell, ng.nx);
                 NEXT[new_slot] = HEAD[c]; HEAD[c] = new_slot;
@@ -855,18 +849,17 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     PH_MARK(6);                                                   // per-candidate segment tests
                     if (rec) { w_from = walk_from; cc = walk_acc; }
                     if (w_from >= 0) {
-#if RRTFND_WALK_RECORDS
-                        depth = walk_records(WREC, w_from, rec ? chain : nullptr, cc);
-#else
-                        int wn = w_from, q = PARENT[wn];
-                        while (q >= 0) {
-                            const double e = ECOST[wn];
-                            if (rec && depth < kChainCap) chain[depth] = e;
-                            cc = dadd(cc, e);
-                            wn = q; q = PARENT[wn];
-                            ++depth;
+                        if (WREC) depth = walk_records(WR, w_from, rec ? chain : nullptr, cc);
+                        else {
+                            int wn = w_from, q = PARENT[wn];
+                            while (q >= 0) {
+                                const double e = ECOST[wn];
+                                if (rec && depth < kChainCap) chain[depth] = e;
+                                cc = dadd(cc, e);
+                                wn = q; q = PARENT[wn];
+                                ++depth;
+                            }
                         }
-#endif
                         my_hops += depth;
                     }
                     __syncwarp();
@@ -944,9 +937,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             if (pass == 0 && commit_cp && k_total > 0) {   // EXTENSION (not the shipped behaviour): adopt the returned edge
                 if (lane == 0) {
                     PARENT[new_slot] = cp_slot; ECOST[new_slot] = cp_cost;
-#if RRTFND_WALK_RECORDS
-                    wrec_store(WREC, new_slot, cp_cost, cp_slot, PARENT[cp_slot]);
-#endif
+                    if (WREC) wrec_store(WR, new_slot, cp_cost, cp_slot, PARENT[cp_slot]);
                 }
                 __syncwarp();
             }
@@ -969,9 +960,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     PARENT[s] = new_slot;
                     const double ec = dist_plain(v.x, v.y, px, py);
                     ECOST[s] = ec;
-#if RRTFND_WALK_RECORDS
-                    wrec_store(WREC, s, ec, new_slot, new_parent);            // its children keep a stale hint until a walk repairs it
-#endif
+                    if (WREC) wrec_store(WR, s, ec, new_slot, new_parent);        // its children keep a stale hint until a walk repairs it
                     flagged |= NFLAG[s] & 1;
                 };
                 const int n_list = n_rw < prm.near_cap ? n_rw : prm.near_cap;
@@ -1219,9 +1208,7 @@ static int check_params(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt) {
     if ((prm->flags & RRTFND_FLAG_TRACE) && (!bt->trace || prm->trace_cap < 1)) return RRTFND_E_BADARG;
     if (!bt->planners || !bt->xy || !bt->ecost || !bt->parent || !bt->nchild || !bt->id || !bt->nflags || !bt->finish ||
         !bt->best_path || (prm->n_obst > 0 && !bt->obst)) return RRTFND_E_BADARG;
-#if RRTFND_WALK_RECORDS
-    if (!bt->walk) return RRTFND_E_BADARG;
-#endif
+    if ((prm->flags & RRTFND_FLAG_NODE_GRID) && !bt->walk) return RRTFND_E_BADARG;     // the node-grid kernel walks the records
     if (bt->grid.nx > 0 && (!bt->grid.seg_start || !bt->grid.seg_items || !bt->grid.pt_start || !bt->grid.pt_items ||
                             bt->grid.ny <= 0)) return RRTFND_E_BADARG;
     return 0;
