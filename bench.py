@@ -157,7 +157,8 @@ def cpu_c5_run(w, first, count, threads):
         t = O.OracleTree(s[p], w["iter_num"] + 2 + T * w["regrow_iters"])
         t.run(prm, w["obstacles"], g[p], seed=int(seeds[p]), stream_id=int(sids[p]))
         ext, moves = t.planner().iter, 0
-        r = OracleReplanner(t, prm, g[p], seeds[p], sids[p], w["node_radius"], w["reconnect_radius"], w["regrow_iters"])
+        r = OracleReplanner(t, prm, g[p], seeds[p], sids[p], w["node_radius"], w["reconnect_radius"], w["regrow_iters"],
+                            edge_invalidation=w.get("edge_invalidation", False))
         for ob in tables:
             o = r.tick(ob)
             ext += sum(o["regrow_iters"]); moves += o["current"] >= 0
@@ -305,7 +306,7 @@ def measure(args, w, P, first, dev, world, rank, steps, warmup, sample_clocks):
     tight = b.prm.capacity
     replan = {"ms": [], "stats": None}
     if is_c5:
-        from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner, moved_obstacles
+        from rrt_star_fnd_algorithm_b200.fnd_loop import DeviceFNDReplanner, moved_obstacles
         tables = [moved_obstacles(w["obstacles"], w["velocity"], k) for k in range(1, w["ticks"] + 1)]
 
     def step(timed):
@@ -322,9 +323,9 @@ def measure(args, w, P, first, dev, world, rank, steps, warmup, sample_clocks):
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r0.record()
             b.grow_capacity(tight + w["ticks"] * w["regrow_iters"])
-            loop = FNDReplanner(b, w["reconnect_radius"], w["regrow_iters"])
-            for ob in tables:
-                loop.tick(ob)
+            loop = DeviceFNDReplanner(b, w["reconnect_radius"], w["regrow_iters"], edge_invalidation=w.get("edge_invalidation", False))
+            for ob in tables:                 # one C-ABI call per tick; nothing comes back to the host inside the loop
+                loop.tick(ob, fetch=False)
             r1.record()
             if timed:
                 replan["ms"].append((r0, r1)); replan["stats"] = dict(loop.stats)
@@ -406,6 +407,9 @@ def main():
     # parity spot check, while the headline batch is still alive
     roofline = parity = None
     capacity = b.prm.capacity
+    import ctypes as C
+    from rrt_star_fnd_algorithm_b200 import _abi
+    plan_launches = int(_abi.lib.rrtfnd_plan_launches(C.byref(b.prm), P))     # init_kernel + this many plan_kernel launches per step
     if rank == 0:
         k_ms = m["k_ms"]
         alg_bytes = 16.0 * pl["n_scan_nodes"].sum() + 12.0 * pl["n_chain_hops"].sum() + 32.0 * pl["iter"].sum()
@@ -464,7 +468,7 @@ def main():
         "edge_checks_ref_equiv_per_sec": edges_ref * rate,
         "circle_tests_per_sec": circles * rate,
         "attempts_per_sec": attempts * rate,
-        "solved_planners": solved, "gpu_launches": 2 * args.steps,
+        "solved_planners": solved, "gpu_launches": (1 + plan_launches) * args.steps,
         "roofline": roofline, "clocks": clk, "parity_spot_check": parity,
     }
     if weak is not None:
@@ -473,9 +477,10 @@ def main():
         st, rms = m["replan_stats"], m["replan_ms"]
         line["replanning"] = dict(st, ticks=w["ticks"], ms_per_step=rms, plan_ms_per_step=m["k_ms"],
                                   moves_per_sec=st["moves"] / (rms / 1e3), note="rank 0; one step = RRT*-FN planning "
-                                  "(plan_kernel) + `ticks` replanning ticks (select_branch, valid_path, reconnect, regrow "
-                                  "kernels; obstacle tables and per-planner ids cross the host every tick)")
-        line["gpu_launches"] = int(args.steps * (2 + w["ticks"] * 4))
+                                  "(plan_kernel) + `ticks` replanning ticks (rrtfnd_fnd_tick: select_branch, valid_path, edge cut, "
+                                  "reconnect, regrow kernels with the bookkeeping between them on the device; the moved obstacle "
+                                  "table goes up once per tick, nothing comes back)")
+        line["gpu_launches"] = int(args.steps * (1 + plan_launches + w["ticks"] * 23))
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
@@ -544,22 +549,29 @@ def run_e2e_c5(args, w, P, first, dev, kw):
     import torch.distributed as dist
     from rrt_star_fnd_algorithm_b200 import workloads as W
     from rrt_star_fnd_algorithm_b200.batch import PlannerBatch
-    from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner, moved_obstacles
+    from rrt_star_fnd_algorithm_b200.fnd_loop import DeviceFNDReplanner, moved_obstacles
     world = int(os.environ.get("WORLD_SIZE", "1"))
     starts, goals, seeds, sids = W.planner_problems(w, first, P)
     tables = [moved_obstacles(w["obstacles"], w["velocity"], k) for k in range(1, w["ticks"] + 1)]
-    sizes = {}
+    sizes, host = {}, {}
 
     def call():
         b = PlannerBatch(w["mode"], starts=starts, goals=goals, seeds=seeds, stream_ids=sids, device=dev, **kw).run()
         b.grow_capacity(b.prm.capacity + w["ticks"] * w["regrow_iters"])
-        loop = FNDReplanner(b, w["reconnect_radius"], w["regrow_iters"])
+        loop = DeviceFNDReplanner(b, w["reconnect_radius"], w["regrow_iters"], edge_invalidation=w.get("edge_invalidation", False))
         for ob in tables:
-            loop.tick(ob)
-        out = [t.cpu() for t in (b.planners_t, b.xy, b.ecost, b.parent, b.nchild, b.id, b.best_path_t)]
+            loop.tick(ob, fetch=False)
+        dev_t = (b.planners_t, b.xy, b.ecost, b.parent, b.nchild, b.id, b.best_path_t, loop.t["phase"])
+        if not host:                          # pinned result buffers, allocated by the warm-up call
+            host["bufs"] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in dev_t]
+        for h, t in zip(host["bufs"], dev_t):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.synchronize()
+        out = host["bufs"]
         sizes["d2h"] = sum(t.numel() * t.element_size() for t in out)
         sizes["h2d"] = starts.nbytes + goals.nbytes + seeds.nbytes + sids.nbytes + (1 + len(tables)) * len(w["obstacles"]) * 32
-        return float(b.planners()["iter"].sum() + loop.stats["regrow_extensions"])
+        from rrt_star_fnd_algorithm_b200._structs import PLANNER_DTYPE
+        return float(out[0].numpy().reshape(-1).view(PLANNER_DTYPE)["iter"].sum() + loop.stats["regrow_extensions"])
 
     call()
     if world > 1:
@@ -577,8 +589,9 @@ def run_e2e_c5(args, w, P, first, dev, kw):
         dt, ext = float(mx[0].item()), float(tt[1].item())
     return {"value": ext * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(sizes["h2d"]), "d2h_bytes_per_step": int(sizes["d2h"]),
             "steps": n, "ms_per_step": dt / n * 1e3,
-            "api": "PlannerBatch + FNDReplanner (Python host over the C ABI): problems from host arrays, obstacle tables per tick, "
-                   "whole trees + planner records + best paths copied back"}
+            "api": "PlannerBatch + DeviceFNDReplanner (Python host over the C ABI: rrtfnd_plan_batch, rrtfnd_fnd_tick): problems from host "
+                   "arrays, one obstacle table per tick, whole trees + planner records + best paths + phases copied back into pinned "
+                   "buffers"}
 
 
 def spot_check(w, first, b):
@@ -594,7 +607,7 @@ def spot_check(w, first, b):
             from oracle.fnd_loop import OracleReplanner
             from rrt_star_fnd_algorithm_b200.fnd_loop import moved_obstacles
             r = OracleReplanner(t, oracle_params(w, 0), g[0], seeds[0], sids[0], w["node_radius"], w["reconnect_radius"],
-                                w["regrow_iters"])
+                                w["regrow_iters"], edge_invalidation=w.get("edge_invalidation", False))
             for k in range(1, w["ticks"] + 1):
                 r.tick(moved_obstacles(w["obstacles"], w["velocity"], k))
         got, want = b.tree(0), t.export()

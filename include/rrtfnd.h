@@ -202,6 +202,9 @@ typedef struct rrtfnd_batch {
 /* ---- library info ------------------------------------------------------------------------ */
 int rrtfnd_abi_version(void);
 const char* rrtfnd_status_string(int status);
+/* kernel launches one rrtfnd_plan_batch call makes for a batch of n_planners (large batches are grown in slices whose
+ * launches overlap, csrc/planner.cu launch_plan) */
+int32_t rrtfnd_plan_launches(const rrtfnd_params_t* prm, int32_t n_planners);
 /* dynamic shared memory (bytes) per planner the fused planner kernel needs for these parameters; <0 = does not fit */
 int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm);
 

@@ -15,7 +15,7 @@ EXPORTS = [
     "rrtfnd_chain_cost", "rrtfnd_pow_libm", "rrtfnd_plan_batch", "rrtfnd_init_batch",
     "rrtfnd_fnd_select_branch", "rrtfnd_fnd_valid_path", "rrtfnd_fnd_reconnect", "rrtfnd_fnd_regrow",
     "rrtfnd_plan_host", "rrtfnd_obst_grid_build_host4", "rrtfnd_obst_grid_build_device", "rrtfnd_fnd_cut_blocked_edges",
-    "rrtfnd_fnd_tick",
+    "rrtfnd_fnd_tick", "rrtfnd_plan_launches",
 ]
 
 
@@ -36,6 +36,7 @@ def _load():
     lib.rrtfnd_status_string.argtypes = [C.c_int]
     lib.rrtfnd_plan_smem_bytes.restype = i64
     lib.rrtfnd_plan_smem_bytes.argtypes = [PP]
+    lib.rrtfnd_plan_launches.argtypes = [PP, i32]
     lib.rrtfnd_edges_vs_circles.argtypes = [vp, vp, vp, vp, i64, vp, i32, vp, vp]
     lib.rrtfnd_points_occupied.argtypes = [vp, vp, i64, vp, i32, dbl, vp, vp]
     lib.rrtfnd_edges_vs_circles_grid.argtypes = [vp, vp, vp, vp, i64, vp, i32, C.POINTER(ObstGrid), vp, vp]

@@ -421,6 +421,26 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     const rrtfnd_obst_grid_t* const obst_grid = &bt.grid;
     const int p = blockIdx.x * WPB + wib;
     if (p >= bt.n_planners) return;                       // whole warp leaves; warps never synchronise with each other
+    // ---- sliced launches (launch_sliced below): this launch grows every planner up to prm.iter_num, one slice of the run; the
+    // launch of the next slice is allowed onto the SMs as soon as every CTA of this one has STARTED (programmatic dependent
+    // launch), so the slots that the last planners of a slice leave idle are taken by the next slice instead of waiting for
+    // the slowest planner. A planner's slices are ordered through a ticket in its own record, not through the stream.
+    const int slice = prm.reserved >> 8, n_slices = (prm.reserved >> 4) & 15;
+    if (n_slices > 1) {
+        int* ticket = &bt.planners[p].reserved;
+        if (lane == 0) {
+            if (slice == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ticket), "r"(bt.reserved) : "memory");
+            else {
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ticket) : "memory");
+                    if (seen - (bt.reserved + slice) < 0) __nanosleep(2000);
+                } while (seen - (bt.reserved + slice) < 0);
+            }
+        }
+        __syncwarp();
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     {
     const int C = prm.capacity;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -445,7 +465,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     rrtfnd_trace_t* TRACE = (!kLean && bt.trace) ? bt.trace + (size_t)p * prm.trace_cap : nullptr;
 
     // per-warp shared memory
-    const int n_stages = prm.reserved;                 // resolved by the host wrapper (2 or 4)
+    const int n_stages = prm.reserved & 15;            // resolved by the host wrapper (2 or 4)
     unsigned char* ws = warp_base + (size_t)wib * warp_smem_bytes(prm, n_stages);
     unsigned char* wp = ws + (size_t)n_stages * kTileBytes;
     SampleBatch& sb = *reinterpret_cast<SampleBatch*>(wp);   // prepared attempts; identical scalars written by every lane
@@ -1123,6 +1143,10 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
         PL->root_slot = root_slot; PL->n_finish = n_finish; PL->best_len = best_len; PL->status = status;
         PL->n_rewired = n_rewired; PL->n_removed = n_removed; PL->solution_found = solution_found;
         PL->n_compactions = n_compactions; PL->fn_count = fn_count;
+        if (n_slices > 1) {                               // this planner's state is complete: its next slice may start
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(&PL->reserved), "r"(bt.reserved + slice + 1) : "memory");
+        }
     }
     }
 }
@@ -1153,7 +1177,7 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 template <int WPB, int MINW, bool NG = false, int MODE = -1, bool RING = true>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
-    size_t bytes = warp_smem_bytes(*prm, prm->reserved) * WPB;
+    size_t bytes = warp_smem_bytes(*prm, prm->reserved & 15) * WPB;
     auto kern = plan_kernel<WPB, MINW, NG, MODE, RING>;
     int blocks = (bt->n_planners + WPB - 1) / WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
@@ -1163,7 +1187,33 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<blocks, 32 * WPB, bytes, st>>>(*prm, *bt);
+    const int n_slices = (prm->reserved >> 4) & 15;
+    if (n_slices <= 1) {
+        kern<<<blocks, 32 * WPB, bytes, st>>>(*prm, *bt);
+        return (int)cudaGetLastError();
+    }
+    // Sliced run. Slice k grows every planner to iter_num * f(k / n_slices); f is chosen so that slices take about the same
+    // time (an RRT* extension costs ~ the tree size, so f = sqrt; RRT*-FN saturates at its node cap, f = identity). Every
+    // launch but the first carries the programmatic-stream-serialization attribute: it may start once all CTAs of its
+    // predecessor have started, and its warps wait for their own planner's ticket (see the kernel). Tickets are serial * 16 +
+    // slice, strictly increasing over the calls of this process, so a stale ticket in a re-used record is never ahead.
+    static int g_serial = 0;
+    rrtfnd_batch_t b = *bt;
+    b.reserved = (++g_serial) * 16;
+    for (int k = 0; k < n_slices; ++k) {
+        rrtfnd_params_t q = *prm;
+        const double f = (double)(k + 1) / n_slices;
+        q.iter_num = k + 1 == n_slices ? prm->iter_num : (int)(prm->iter_num * (MODE == RRTFND_MODE_STAR ? sqrt(f) : f));
+        q.reserved = (prm->reserved & 255) | (k << 8);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(32 * WPB); cfg.dynamicSmemBytes = bytes; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = k ? 1 : 0;
+        e = cudaLaunchKernelEx(&cfg, kern, q, b);
+        if (e != cudaSuccess) return (int)e;
+    }
     return (int)cudaGetLastError();
 }
 
@@ -1226,6 +1276,26 @@ extern "C" int rrtfnd_debug_phase_clocks(unsigned long long* out_host, int reset
 }
 #endif
 
+static bool is_lean(const rrtfnd_params_t& q, const PlanCfg& cfg) {
+    return (q.flags & (RRTFND_FLAG_TRACE | RRTFND_FLAG_COMMIT_CHOOSE_PARENT | RRTFND_FLAG_NODE_GRID)) == 0 &&
+           (q.flags & RRTFND_FLAG_EVAL_CHOOSE_PARENT) && q.mode != RRTFND_MODE_RRT && cfg.wpb == 1 && cfg.minw == 16;
+}
+// Batches of several waves of resident warps are grown in slices whose launches overlap (launch_plan): the end of a one-shot
+// launch leaves the warp slots idle for about half a planner's run time (7 - 10 % of a 16,384-planner launch,
+// profiles/r01_phase_clocks.md); with 8 slices it is half of an eighth. RRTFND_SLICES=n overrides (1 = off).
+static int plan_slices(const rrtfnd_params_t& q, int n_planners) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int n = n_planners >= 3 * sms * RRTFND_LEAN_MINW ? 8 : 1;
+    if (const char* sv = getenv("RRTFND_SLICES")) n = atoi(sv);
+    return n < 1 ? 1 : n > 15 ? 15 : n;
+}
+
+extern "C" int32_t rrtfnd_plan_launches(const rrtfnd_params_t* prm, int32_t n_planners) {
+    if (!prm || n_planners <= 0) return RRTFND_E_BADARG;
+    return is_lean(*prm, choose_cfg(*prm, n_planners)) ? plan_slices(*prm, n_planners) : 1;
+}
+
 extern "C" int64_t rrtfnd_plan_smem_bytes(const rrtfnd_params_t* prm) {
     if (!prm) return RRTFND_E_BADARG;
     const size_t b = warp_smem_bytes(*prm, 4);
@@ -1241,7 +1311,7 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     if (!(q.flags & RRTFND_FLAG_TRACE)) b.trace = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     const PlanCfg cfg = choose_cfg(q, b.n_planners);
-    q.reserved = cfg.stages;                    // the kernel reads its ring depth here
+    q.reserved = cfg.stages;                    // the kernel reads its ring depth here (+ 16 * slices, set below for big batches)
     if (q.flags & RRTFND_FLAG_NODE_GRID) {      // large single trees: node-grid kernel, one planner per CTA
         const rrtfnd_node_grid_t& g = b.node_grid;
         if (q.mode == RRTFND_MODE_FN || g.nx <= 0 || g.ny <= 0 || !g.head || !g.next || !g.cand || g.cand_cap < 32 || !(g.inv_cell > 0.0))
@@ -1249,13 +1319,13 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
         return launch_plan<1, 16, true>(&q, &b, (cudaStream_t)stream);
     }
     // the configuration batches run in gets a lean kernel instance (one planner per CTA, 128 registers)
-    const bool lean = (q.flags & (RRTFND_FLAG_TRACE | RRTFND_FLAG_COMMIT_CHOOSE_PARENT)) == 0 && (q.flags & RRTFND_FLAG_EVAL_CHOOSE_PARENT) &&
-                      cfg.wpb == 1 && cfg.minw == 16;
+    const bool lean = is_lean(q, cfg);
     // Scans of large trees stream from L2 / HBM and are faster through the TMA ring (c3, 5,002 slots: +6 %); trees of a
     // thousand nodes stay L1 / L2 resident and are faster with plain loads (c2, 1,508 slots: +7 %). The `stages` field
     // of the launch word overrides: 1 = plain loads, 2 / 4 = ring.
     const int stages_req = (prm->reserved >> 4) & 15;
     const bool ring = stages_req == 1 ? false : (stages_req == 2 || stages_req == 4) ? true : prm->capacity > 2048;
+    if (lean) q.reserved = cfg.stages | (plan_slices(q, b.n_planners) << 4);
     if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, true>(&q, &b, st)
                                                         : launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, false>(&q, &b, st);
     if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_FN, true>(&q, &b, st)

@@ -90,7 +90,8 @@ def c5():
     """Config 5: RRT*-FND dynamic replanning. The config-2 problem (RRT*-FN, 1,000-node cap, 4,096 planners) with 50
     circles r = U(1,3) that translate by a per-obstacle velocity U(-0.5,0.5)^2 every replanning tick; each tick the
     robot steps to the next path node (select_branch), the moved obstacles invalidate path nodes (valid_path) and the
-    split-off tree is reconnected or regrown (fnd_loop.FNDReplanner)."""
+    split-off tree is reconnected or regrown (fnd_loop.DeviceFNDReplanner). `edge_invalidation`: the path's EDGES are tested as
+    well as its nodes ("edge invalidation" in the config's wording; an extension, the reference's valid_path tests nodes only)."""
     start, goal, ticks, nr = (5.0, 5.0), (95.0, 95.0), 24, 1.0
     rng = np.random.default_rng(5)
     obst, vel = [], []
@@ -106,7 +107,7 @@ def c5():
     vel = np.asarray(vel)
     return dict(name="c5", mode="fn", obstacles=obst, velocity=vel, xy_range=[[0.0, 100.0], [0.0, 100.0]], iter_num=5000,
                 step_length=3.0, radius=6.0, node_radius=1.0, bias=0.01, max_nodes=1000, start=start, goal=goal,
-                seed_base=5000, planners=4096, ticks=ticks, reconnect_radius=15.0, regrow_iters=100)
+                seed_base=5000, planners=4096, ticks=ticks, reconnect_radius=15.0, regrow_iters=100, edge_invalidation=True)
 
 
 WORKLOADS = {"c1": c1, "c2": c2, "c2r": c2r, "c3": c3, "c4": c4, "c5": c5}

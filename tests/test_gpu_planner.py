@@ -188,3 +188,38 @@ def test_batch_planner_as_a_graph_object():
     assert path == [int(i) for i in g["best_path"]] and cost == float(g["best_cost"])
     assert G.get_cost(int(g["best_path"][0])) == float(g["best_cost"])
     assert sum(len(c) for c in G.children.values()) == len(G.vertices) - 1
+
+
+@pytest.mark.parametrize("name,slices", [("float_star", 5), ("float_fn", 3), ("float_star", 15)])
+def test_sliced_overlapping_launches_give_the_same_trees(name, slices, monkeypatch):
+    """Large batches are grown in slices whose launches overlap (programmatic dependent launch; a planner's slices are ordered
+    by a ticket in its record, csrc/planner.cu launch_plan). Forced here on a small batch, where every slice's warps are
+    resident at once and really wait for their tickets: same trees, records and best paths as the oracle."""
+    from rrt_star_fnd_algorithm_b200 import _abi
+    import ctypes as C
+    case = dict(K.case_by_name(name), iter_num=400)
+    rng = np.random.default_rng(9)
+    P = 96
+    (x0, x1), (y0, y1) = case["xy_range"]
+    starts, goals = [], []
+    while len(starts) < P:
+        s_ = (rng.uniform(x0, x1), rng.uniform(y0, y1)); t_ = (rng.uniform(x0, x1), rng.uniform(y0, y1))
+        if O.is_occupied(s_, case["obstacles"], case["node_radius"]) or O.is_occupied(t_, case["obstacles"], case["node_radius"]):
+            continue
+        starts.append(s_); goals.append(t_)
+    monkeypatch.setenv("RRTFND_SLICES", str(slices))
+    b = make_batch(case, seeds=np.full(P, 31), stream_ids=np.arange(P), starts=starts, goals=goals, trace=False)
+    assert _abi.lib.rrtfnd_plan_launches(C.byref(b.prm), P) == slices
+    b.run()
+    b.run()                                   # a second call on finished planners: every slice is a no-op, tickets move on
+    pls = b.planners()
+    for p in range(P):
+        prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0)
+        t = O.OracleTree(starts[p], case["iter_num"] + 2)
+        st, _ = t.run(prm, case["obstacles"], goals[p], seed=31, stream_id=p)
+        assert pls[p]["status"] == st == S.ST_DONE
+        assert_tree_equal(b.tree(p), t.export(), f"{name}[{p}] in {slices} slices")
+        opl = t.planner()
+        for f in ("iter", "cursor", "attempts", "best_cost", "n_live", "n_rewired", "n_removed", "n_edge_checks", "n_edge_checks_ref"):
+            assert pls[p][f] == getattr(opl, f), (p, f)
+        assert np.array_equal(b.best_path(p), t.best_path())

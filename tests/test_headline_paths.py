@@ -166,9 +166,10 @@ def test_default_bench_launch_matches_oracle_at_full_length(name, total, count):
 
 @pytest.mark.gpu
 def test_default_bench_launch_c5_planning_and_ticks_match_oracle():
-    """Config 5 as bench.py runs it: RRT*-FN planning with the default launch, then 24 replanning ticks."""
+    """Config 5 as bench.py runs it: RRT*-FN planning with the default launch, then 24 replanning ticks through the device-side
+    loop (rrtfnd_fnd_tick) with node AND edge invalidation."""
     from oracle.fnd_loop import OracleReplanner
-    from rrt_star_fnd_algorithm_b200.fnd_loop import FNDReplanner, LOST
+    from rrt_star_fnd_algorithm_b200.fnd_loop import DeviceFNDReplanner, LOST
     w = W.WORKLOADS["c5"]()
     idx, starts, goals, seeds, sids = spread_problems(w, 4096, 48)
     b = make_workload_batch(w, starts, goals, seeds, sids).run()
@@ -179,9 +180,9 @@ def test_default_bench_launch_c5_planning_and_ticks_match_oracle():
         assert_record_equal(pls[p], t.planner(), f"c5 planner {int(idx[p])} (planning)")
         assert_tree_equal(b.tree(p), t.export(), f"c5 planner {int(idx[p])} (planning)")
     b.grow_capacity(b.prm.capacity + extra)
-    loop = FNDReplanner(b, w["reconnect_radius"], w["regrow_iters"])
+    loop = DeviceFNDReplanner(b, w["reconnect_radius"], w["regrow_iters"], edge_invalidation=w["edge_invalidation"])
     reps = [OracleReplanner(t, oracle_params(w), goals[p], seeds[p], sids[p], w["node_radius"], w["reconnect_radius"],
-                            w["regrow_iters"]) for p, t in enumerate(trees)]
+                            w["regrow_iters"], edge_invalidation=w["edge_invalidation"]) for p, t in enumerate(trees)]
     for k in range(1, w["ticks"] + 1):
         ob = W.moved_obstacles(w["obstacles"], w["velocity"], k)
         got = loop.tick(ob)
