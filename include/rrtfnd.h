@@ -386,12 +386,15 @@ int rrtfnd_obst_grid_build_device(const double* obst, int32_t n_obst, double nod
  * RRTFND_FLAG_OBST_HAS_K obst_host is [M][4] (ox, oy, r, K) and the caller's K is used (integer-valued obstacles of
  * Map.generate_obstacles, src/map.py:59-60, are squared exactly by the interpreter). Outputs (all host, may be NULL to
  * skip): planners_host [P]; tree arrays xy [P][capacity][2], ecost, parent (slot), nchild, id [P][capacity];
- * best_path_host [P][path_cap]. The obstacle grid is built inside the call. */
+ * best_path_host [P][path_cap]. The obstacle grid is built inside the call. The device memory is an arena the library keeps
+ * between calls (grow-only; calls are serialised); rrtfnd_host_release() frees it. */
 int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t n_planners, const double* starts_goals_host,
                      const uint64_t* seeds_host, const double* obst_host, const uint32_t* words_host,
                      rrtfnd_planner_t* planners_host, double* xy_host, double* ecost_host,
                      int32_t* parent_host, int32_t* nchild_host, int32_t* id_host, int32_t* best_path_host,
                      int32_t device);
+
+int rrtfnd_host_release(void);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ EXPORTS = [
     "rrtfnd_chain_cost", "rrtfnd_pow_libm", "rrtfnd_plan_batch", "rrtfnd_init_batch",
     "rrtfnd_fnd_select_branch", "rrtfnd_fnd_valid_path", "rrtfnd_fnd_reconnect", "rrtfnd_fnd_regrow",
     "rrtfnd_plan_host", "rrtfnd_obst_grid_build_host4", "rrtfnd_obst_grid_build_device", "rrtfnd_fnd_cut_blocked_edges",
-    "rrtfnd_fnd_tick", "rrtfnd_plan_launches",
+    "rrtfnd_fnd_tick", "rrtfnd_plan_launches", "rrtfnd_host_release",
 ]
 
 

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/rrtfnd.h"
@@ -18,11 +19,26 @@
 
 namespace {
 
-struct DevBuf {
-    void* p = nullptr;
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    ~DevBuf() { if (p) cudaFree(p); }
+// Device memory of rrtfnd_plan_host: one grow-only arena per process, kept between calls (cudaMalloc / cudaFree of a few
+// hundred megabytes cost tens of milliseconds, a quarter of a config-2 call) and released by rrtfnd_host_release(). Calls are
+// serialised by the arena's mutex; a call carves its buffers out of the arena with 256-byte alignment.
+struct Arena {
+    std::mutex lock;
+    void* base = nullptr;
+    size_t cap = 0, used = 0;
+    int device = -1;
+    cudaError_t reserve(int dev, size_t bytes) {
+        used = 0;
+        if (base && device == dev && cap >= bytes) return cudaSuccess;
+        if (base) { cudaSetDevice(device); cudaFree(base); base = nullptr; cap = 0; cudaSetDevice(dev); }
+        cudaError_t e = cudaMalloc(&base, bytes);
+        if (e == cudaSuccess) { cap = bytes; device = dev; } else base = nullptr;
+        return e;
+    }
+    void* take(size_t bytes) { void* p = (char*)base + used; used += (bytes + 255) / 256 * 256; return p; }
+    void release() { if (base) { cudaSetDevice(device); cudaFree(base); } base = nullptr; cap = used = 0; device = -1; }
 };
+Arena g_arena;
 
 #define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -167,14 +183,17 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         if (grc) return grc;
     }
 
-    DevBuf d_pl, d_xy, d_e, d_par, d_nc, d_id, d_fl, d_fin, d_bp, d_ob, d_w, d_gss, d_gsi, d_gps, d_gpi;
-    CK(d_pl.alloc((size_t)P * sizeof(rrtfnd_planner_t)));
-    CK(d_xy.alloc(n * 16)); CK(d_e.alloc(n * 8));
-    CK(d_par.alloc(n * 4)); CK(d_nc.alloc(n * 4)); CK(d_id.alloc(n * 4)); CK(d_fl.alloc(n));
-    CK(d_gss.alloc(g_ss.size() * 4)); CK(d_gsi.alloc(g_si.size() * 4));
-    CK(d_gps.alloc(g_ps.size() * 4)); CK(d_gpi.alloc(g_pi.size() * 4));
-    CK(d_fin.alloc((size_t)P * prm->finish_cap * 4)); CK(d_bp.alloc((size_t)P * prm->path_cap * 4));
-    CK(d_ob.alloc(ob.size() * 8));
+    std::lock_guard<std::mutex> guard(g_arena.lock);
+    const size_t wb = prm->stream_mode == RRTFND_STREAM_WORDS ? (size_t)P * (size_t)prm->words_per_planner * 4 : 0;
+    const size_t sizes[] = {(size_t)P * sizeof(rrtfnd_planner_t), n * 16, n * 8, n * 4, n * 4, n * 4, n, (size_t)P * prm->finish_cap * 4,
+                            (size_t)P * prm->path_cap * 4, ob.size() * 8, wb, g_ss.size() * 4, g_si.size() * 4, g_ps.size() * 4, g_pi.size() * 4};
+    size_t total = 0;
+    for (size_t b_ : sizes) total += (b_ + 255) / 256 * 256 + 256;
+    CK(g_arena.reserve(device, total));
+    struct { void* p; } d_pl{g_arena.take(sizes[0])}, d_xy{g_arena.take(sizes[1])}, d_e{g_arena.take(sizes[2])}, d_par{g_arena.take(sizes[3])},
+        d_nc{g_arena.take(sizes[4])}, d_id{g_arena.take(sizes[5])}, d_fl{g_arena.take(sizes[6])}, d_fin{g_arena.take(sizes[7])},
+        d_bp{g_arena.take(sizes[8])}, d_ob{g_arena.take(sizes[9])}, d_w{g_arena.take(sizes[10])}, d_gss{g_arena.take(sizes[11])},
+        d_gsi{g_arena.take(sizes[12])}, d_gps{g_arena.take(sizes[13])}, d_gpi{g_arena.take(sizes[14])};
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     const auto t1 = now();
@@ -192,8 +211,6 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
             grid.pt_start = (const int32_t*)d_gps.p; grid.pt_items = (const int32_t*)d_gpi.p;
         }
         if (prm->stream_mode == RRTFND_STREAM_WORDS) {
-            const size_t wb = (size_t)P * (size_t)prm->words_per_planner * 4;
-            if ((rc = (int)d_w.alloc(wb))) break;
             if ((rc = (int)cudaMemcpyAsync(d_w.p, words_host, wb, cudaMemcpyHostToDevice, st))) break;
         }
         rrtfnd_batch_t bt;
@@ -203,7 +220,7 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         bt.parent = (int32_t*)d_par.p; bt.nchild = (int32_t*)d_nc.p; bt.id = (int32_t*)d_id.p; bt.nflags = (uint8_t*)d_fl.p;
         bt.grid = grid;
         bt.finish = (int32_t*)d_fin.p; bt.best_path = (int32_t*)d_bp.p; bt.obst = (const double*)d_ob.p;
-        bt.words = (const uint32_t*)d_w.p; bt.trace = nullptr;
+        bt.words = wb ? (const uint32_t*)d_w.p : nullptr; bt.trace = nullptr;
         rrtfnd_params_t q = *prm;
         q.flags &= ~(RRTFND_FLAG_TRACE | RRTFND_FLAG_OBST_HAS_K);
         if ((rc = rrtfnd_init_batch(&q, &bt, st))) break;
@@ -226,4 +243,10 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
                 ms(t2, t3), ms(t3, t4));
     }
     return rc;
+}
+
+extern "C" int rrtfnd_host_release(void) {
+    std::lock_guard<std::mutex> guard(g_arena.lock);
+    g_arena.release();
+    return 0;
 }

@@ -1280,13 +1280,15 @@ static bool is_lean(const rrtfnd_params_t& q, const PlanCfg& cfg) {
     return (q.flags & (RRTFND_FLAG_TRACE | RRTFND_FLAG_COMMIT_CHOOSE_PARENT | RRTFND_FLAG_NODE_GRID)) == 0 &&
            (q.flags & RRTFND_FLAG_EVAL_CHOOSE_PARENT) && q.mode != RRTFND_MODE_RRT && cfg.wpb == 1 && cfg.minw == 16;
 }
-// Batches of several waves of resident warps are grown in slices whose launches overlap (launch_plan): the end of a one-shot
-// launch leaves the warp slots idle for about half a planner's run time (7 - 10 % of a 16,384-planner launch,
-// profiles/r01_phase_clocks.md); with 8 slices it is half of an eighth. RRTFND_SLICES=n overrides (1 = off).
+// Batches larger than the resident warp slots are grown in slices whose launches overlap (launch_plan). A one-shot launch runs
+// planners to completion in index order: its last wave is partly empty and its end waits for the slowest planner while the
+// other slots idle. Sliced, every planner advances through the same short stages and only the last eighth of a run is exposed.
+// Measured on B200 (profiles/r02_s3_slices_raw.txt): c3 16,384 planners +7.0 % (8 slices; 4: +6.3 %, 15: +4.3 %), c3 4,096
+// planners +15 %, c2 4,096 planners +11.8 %. RRTFND_SLICES=n overrides (1 = off).
 static int plan_slices(const rrtfnd_params_t& q, int n_planners) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int n = n_planners >= 3 * sms * RRTFND_LEAN_MINW ? 8 : 1;
+    int n = n_planners > sms * RRTFND_LEAN_MINW ? 8 : 1;
     if (const char* sv = getenv("RRTFND_SLICES")) n = atoi(sv);
     return n < 1 ? 1 : n > 15 ? 15 : n;
 }

@@ -156,17 +156,20 @@ def test_node_grid_gives_the_same_tree_as_the_scans(name, cell):
 
 
 def test_node_grid_large_tree_matches_the_oracle():
-    """20,000 nodes in a 400 x 400 map, 60 obstacles: grid from 256 nodes on, every node equal to the CPU oracle's."""
+    """40,000 nodes (RRTFND_LONG_TESTS=1: 200,000 - minutes of brute-force oracle) in a 400 x 400 map, 60 obstacles: grid from 256
+    nodes on, walk records with grandparent hints, every node equal to the CPU oracle's."""
+    import os
     import oracle as O
+    n_nodes = 200000 if os.environ.get("RRTFND_LONG_TESTS") == "1" else 40000
     rng = np.random.default_rng(8)
     obst = [(float(x), float(y), float(r)) for x, y, r in zip(rng.uniform(20, 380, 60), rng.uniform(20, 380, 60), rng.uniform(3, 12, 60))]
     case = dict(name="big", mode="star", seed=21, stream_id=3, start=(5.0, 5.0), goal=(390.0, 390.0), xy_range=[[0, 400], [0, 400]],
-                obstacles=obst, iter_num=20000, step_length=2.0, radius=4.0, node_radius=1.0, bias=0.01, max_nodes=0)
+                obstacles=obst, iter_num=n_nodes, step_length=2.0, radius=4.0, node_radius=1.0, bias=0.01, max_nodes=0)
     b = make_batch(case, seeds=[21], stream_ids=[3], trace=False, node_grid=True, node_grid_min_nodes=256,
-                   finish_cap=8192, path_cap=8192).run()
+                   finish_cap=32768, path_cap=32768).run()
     b.check_status()
-    t = O.OracleTree(case["start"], case["iter_num"] + 2, finish_cap=8192, path_cap=8192)
-    prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0, finish_cap=8192, path_cap=8192)
+    t = O.OracleTree(case["start"], case["iter_num"] + 2, finish_cap=32768, path_cap=32768)
+    prm = K.params_for(case, stream_mode=S.STREAM_PHILOX, flags=0, finish_cap=32768, path_cap=32768)
     st, _ = t.run(prm, obst, case["goal"], seed=21, stream_id=3)
     assert st == S.ST_DONE
     assert_tree_equal(b.tree(0), t.export(), "big")
