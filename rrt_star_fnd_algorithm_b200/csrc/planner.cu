@@ -71,7 +71,11 @@ namespace rrtfnd {
 constexpr int kReserveWords = 64;   // must equal RESERVE_WORDS in _structs.py / ORC_RESERVE_WORDS
 constexpr int kStage = 160;         // slots staged per warp: < 32 left over + one 128-node block of the scan
 constexpr int kIntMax = 0x7fffffff;
-constexpr int kChainCap = 96;       // edge costs of the new node's parent chain cached per warp (choose-parent re-sums them)
+// edge costs of the new node's parent chain cached per warp (choose-parent re-sums them): 96 hops cover the batch workloads'
+// trees; a single large tree (node grid, config 4) has chains of several hundred hops - without the cache every acceptance of
+// choose-parent re-walked them at memory latency (44 % of an extension at 10^5 nodes, profiles/r02_c4.md)
+constexpr int kChainCapBatch = 96, kChainCapLarge = 1024;
+__host__ __device__ inline int chain_cap(const rrtfnd_params_t& prm) { return (prm.flags & RRTFND_FLAG_NODE_GRID) ? kChainCapLarge : kChainCapBatch; }
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline int bitmap_words(const rrtfnd_params_t& prm) { return prm.capacity / 32 + 1; }
@@ -88,13 +92,13 @@ struct SampleBatch {
     int last_goal;             // the last valid entry is a goal-bias hit (2 words instead of 6)
 };
 
-// shared memory of one warp: xy ring (n_stages tiles) | attempt batch | chain[kChainCap] | stage[kStage] | rwlist[near_cap]
+// shared memory of one warp: xy ring (n_stages tiles) | attempt batch | chain[chain_cap] | stage[kStage] | rwlist[near_cap]
 // (re-parented slots of one iteration; overflow goes to nflags) | mbarriers | word source | [live bitmap + prefix counts].
 // The compaction's live bitmap and prefix counts are only alive inside compact_tree(), at an attempt boundary, when the
 // ring, the attempt batch and the per-iteration scratch hold nothing: they ALIAS that region (scratch_bytes) when they fit
 // and get their own space behind the word source otherwise. Every kilobyte not allocated here is L1 for the tree gathers.
 __host__ __device__ inline size_t scratch_bytes(const rrtfnd_params_t& prm, int n_stages) {
-    return (size_t)n_stages * kTileBytes + align_up(sizeof(SampleBatch), 16) + kChainCap * 8 + kStage * 4 +
+    return (size_t)n_stages * kTileBytes + align_up(sizeof(SampleBatch), 16) + (size_t)chain_cap(prm) * 8 + kStage * 4 +
            align_up((size_t)prm.near_cap * 4, 16);
 }
 __host__ __device__ inline size_t compact_bytes(const rrtfnd_params_t& prm) {
@@ -255,7 +259,7 @@ static __device__ __noinline__ void wrec_rebuild(rrtfnd_walk_t* W, const int32_t
 // Graph.get_cost over the walk records: leaf -> root, `acc` the running sum to start from; `rec_chain` (one lane per chunk at
 // most) receives the addends in order. Returns the hops walked. One round = the parent's and the guessed grandparent's
 // records requested together; a confirmed guess advances two hops for one memory round trip.
-__device__ __forceinline__ int walk_records(rrtfnd_walk_t* W, int from, double* rec_chain, double& acc) {
+__device__ __forceinline__ int walk_records(rrtfnd_walk_t* W, int from, double* rec_chain, double& acc, int kChainCap) {
     int depth = 0, v = from;
     WRec rv = wrec_load(W, v);
     while (rv.parent >= 0) {
@@ -471,6 +475,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     SampleBatch& sb = *reinterpret_cast<SampleBatch*>(wp);   // prepared attempts; identical scalars written by every lane
     wp += align_up(sizeof(SampleBatch), 16);
     double* chain = reinterpret_cast<double*>(wp);     // edge costs along the new node's parent chain, leaf side first
+    constexpr int kChainCap = NG ? kChainCapLarge : kChainCapBatch;
     wp += kChainCap * 8;
     int* stage = reinterpret_cast<int*>(wp);
     int* rwlist = stage + kStage;
@@ -869,7 +874,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                     PH_MARK(6);                                                   // per-candidate segment tests
                     if (rec) { w_from = walk_from; cc = walk_acc; }
                     if (w_from >= 0) {
-                        if (WREC) depth = walk_records(WR, w_from, rec ? chain : nullptr, cc);
+                        if (WREC) depth = walk_records(WR, w_from, rec ? chain : nullptr, cc, kChainCap);
                         else {
                             int wn = w_from, q = PARENT[wn];
                             while (q >= 0) {
