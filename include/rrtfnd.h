@@ -43,6 +43,10 @@ extern "C" {
 #define RRTFND_FLAG_TRACE 4                /* write one rrtfnd_trace_t per successful iteration */
 #define RRTFND_FLAG_NODE_GRID 8            /* answer nearest / near-set queries of large trees through batch.node_grid (RRT, RRT* only) */
 #define RRTFND_FLAG_OBST_HAS_K 16          /* rrtfnd_plan_host only: obst_host rows are (ox, oy, r, K) instead of (ox, oy, r) */
+#define RRTFND_FLAG_RECTANGLES 32          /* the obstacle table holds rectangle rows (extension below): rrtfnd_plan_batch then runs the
+                                            * kernel instances that look for them; without the flag its batch kernels treat every row
+                                            * as a circle (the dispatch costs 6 % on circle-only maps). The stateless operators and the
+                                            * FND operators always look. rrtfnd_plan_host sets it itself. */
 
 /* per-planner status (rrtfnd_planner_t.status) */
 #define RRTFND_ST_RUNNING 0        /* iter < iter_num, can be resumed */

@@ -5,7 +5,7 @@ ABI_VERSION = 3
 
 MODE_RRT, MODE_STAR, MODE_FN = 0, 1, 2
 STREAM_WORDS, STREAM_PHILOX = 0, 1
-FLAG_EVAL_CHOOSE_PARENT, FLAG_COMMIT_CHOOSE_PARENT, FLAG_TRACE, FLAG_NODE_GRID, FLAG_OBST_HAS_K = 1, 2, 4, 8, 16
+FLAG_EVAL_CHOOSE_PARENT, FLAG_COMMIT_CHOOSE_PARENT, FLAG_TRACE, FLAG_NODE_GRID, FLAG_OBST_HAS_K, FLAG_RECTANGLES = 1, 2, 4, 8, 16, 32
 
 ST_RUNNING, ST_DONE, ST_NEED_WORDS, ST_ATTEMPT_CAP = 0, 1, 2, 3
 ST_CAPACITY, ST_NEAR_CAP, ST_FINISH_CAP, ST_PATH_CAP, ST_DUPLICATE, ST_NO_CHILDLESS, ST_STREAM_EXHAUSTED, ST_REGROW_NEED_WORDS = -1, -2, -3, -4, -5, -6, -7, -8

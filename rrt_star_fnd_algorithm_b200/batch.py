@@ -9,7 +9,7 @@ import torch
 from . import _abi
 from ._structs import (
     Batch, NodeGrid, ObstGrid, Params, FLAG_NODE_GRID, PLANNER_BYTES, PLANNER_DTYPE, TRACE_BYTES, TRACE_DTYPE,
-    MODE_RRT, MODE_STAR, MODE_FN, STREAM_WORDS, STREAM_PHILOX, FLAG_EVAL_CHOOSE_PARENT, FLAG_TRACE,
+    MODE_RRT, MODE_STAR, MODE_FN, STREAM_WORDS, STREAM_PHILOX, FLAG_EVAL_CHOOSE_PARENT, FLAG_TRACE, FLAG_RECTANGLES,
     ST_DONE, ST_RUNNING, ST_NEED_WORDS, STATUS_NAMES,
 )
 
@@ -106,6 +106,7 @@ class PlannerBatch:
         prm.goal_node_radius = float(node_radius if goal_node_radius is None else goal_node_radius)
         (prm.x_lo, prm.x_hi), (prm.y_lo, prm.y_hi) = [(float(a), float(b)) for a, b in xy_range]
         self.prm = prm
+        self._flag_rectangles()
 
         dev = self.device
         pl = np.zeros(P, dtype=PLANNER_DTYPE)
@@ -170,6 +171,11 @@ class PlannerBatch:
         if smem < 0:
             raise _abi.LibraryError(f"planner does not fit in shared memory: {_abi.status_string(smem)}")
         self.smem_bytes = int(smem)
+
+    def _flag_rectangles(self):
+        """RRTFND_FLAG_RECTANGLES follows the table: the batch kernels of circle-only maps are compiled without the dispatch."""
+        has = self.obst_host is not None and len(self.obst_host) > 0 and bool((self.obst_host[:, 2] < 0).any())
+        self.prm.flags = (self.prm.flags | FLAG_RECTANGLES) if has else (self.prm.flags & ~FLAG_RECTANGLES)
 
     # ------------------------------------------------------------------ C-ABI plumbing
     def _batch(self) -> Batch:
@@ -273,6 +279,7 @@ class PlannerBatch:
         node coordinates themselves read back to bound them."""
         self.obst_host = obstacle_table(obstacles, rectangles) if _table is None else _table     # _table: rows that already carry K
         self.prm.n_obst = len(self.obst_host)
+        self._flag_rectangles()
         self.obst = torch.from_numpy(self.obst_host if len(self.obst_host) else np.zeros((1, 4))).to(self.device)
         self.grid, self._grid_t = ObstGrid(), None
         if grid and len(self.obst_host):
@@ -302,6 +309,7 @@ class PlannerBatch:
                               abs(b[0]), abs(b[1]), abs(b[2]), abs(b[3])))
         self.set_obstacles_device(torch.from_numpy(t).to(self.device, non_blocking=True), coord_max, grid_cell)
         self.obst_host = t
+        self._flag_rectangles()
 
     def set_obstacles_device(self, table4_dev, coord_max, grid_cell=0.0):
         """Replace the obstacle table by `table4_dev` (a float64 CUDA tensor [M][4] holding ox, oy, r, K rows, same M as

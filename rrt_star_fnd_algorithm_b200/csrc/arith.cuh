@@ -117,11 +117,13 @@ static __device__ __noinline__ bool point_in_inflated_rect(double px, double py,
 
 // intersection_circle (src/algorithm.py:555-578) for one circle (ox, oy, r) with
 // K = ((-(r*r)) + ox*ox) + oy*oy precomputed (first three terms of `c`, :619).
+// RECT = false compiles the rectangle dispatch out: measured on B200, the never-taken branch and the call behind it cost
+// the fused planner 5.8 % on config 3 (registers held across the circle loop), so the batch kernels of circle-only tables
+// are instantiated without it (RRTFND_FLAG_RECTANGLES selects the instances with it).
+template <bool RECT = true>
 __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double oy, double r, double K) {
-#ifndef RRTFND_NO_RECT
-    if (r < 0.0)                                                                // a rectangle row (cx, cy, -hx, hy): extension above
+    if (RECT && r < 0.0)                                                        // a rectangle row (cx, cy, -hx, hy): extension above
         return seg_hits_rect(s.p1x, s.p1y, s.p1x == s.lo ? s.hi : s.lo, s.p1y == s.ylo ? s.yhi : s.ylo, ox, oy, -r, K);
-#endif
     if (s.vertical) return fabs(dsub(ox, s.p1x)) <= r;                          // :563-567
     const double b = dmul(2.0, dsub(dadd(-ox, s.mk), dmul(s.m, oy)));           // :618
     const double c = dadd(dsub(K, dmul(dadd(oy, oy), s.k)), s.kk);              // :619
@@ -133,11 +135,10 @@ __device__ __forceinline__ bool seg_hits_circle(const Seg& s, double ox, double 
 }
 
 // Map.is_occupied_c for one circle (src/map.py:44-45)
+template <bool RECT = true>
 __device__ __forceinline__ bool point_in_inflated(double px, double py, double ox, double oy, double r,
                                                   double node_radius, double K = 0.0) {
-#ifndef RRTFND_NO_RECT
-    if (r < 0.0) return point_in_inflated_rect(px, py, ox, oy, -r, K, node_radius);   // rectangle row (extension)
-#endif
+    if (RECT && r < 0.0) return point_in_inflated_rect(px, py, ox, oy, -r, K, node_radius);   // rectangle row (extension)
     const double dx = dsub(px, ox), dy = dsub(py, oy);
     return dsqrt(dadd(pow2_ref(dx), pow2_ref(dy))) < dadd(node_radius, r);      // np.sqrt((..) ** 2 + (..) ** 2)
 }

@@ -51,6 +51,7 @@ __device__ __forceinline__ void load_obst(const double2* __restrict__ tab, int j
 
 // through_obstacle(Line(p1, p2), obstacles) over the circles first, first + stride, ... of the candidate list.
 // Returns (circle tests performed << 1) | hit. Stops at the first hit.
+template <bool RECT = true>
 static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, const rrtfnd_obst_grid_t* __restrict__ g, int M,
                                         int full_cells, double p1x, double p1y, double p2x, double p2y, int first,
                                         int stride) {
@@ -96,13 +97,14 @@ static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, 
             double ox, oy, r, K;
             load_obst(tab, cull ? __ldg(items + j) : j, ox, oy, r, K);
             ++tests;
-            if (seg_hits_circle(sg, ox, oy, r, K)) return (tests << 1) | 1;
+            if (seg_hits_circle<RECT>(sg, ox, oy, r, K)) return (tests << 1) | 1;
         }
     }
     return tests << 1;
 }
 
 // Map.is_occupied_c for ONE point held by every lane of the warp
+template <bool RECT = true>
 __device__ __forceinline__ bool point_occupied_warp(const Obst& ob, double px, double py, double node_radius, int lane,
                                                     long long& tests) {
     const bool cull = ob.full_cells > 0;
@@ -118,7 +120,7 @@ __device__ __forceinline__ bool point_occupied_warp(const Obst& ob, double px, d
         double ox, oy, r, K;
         load_obst(ob.tab, cull ? __ldg(ob.g->pt_items + j) : j, ox, oy, r, K);
         ++tests;
-        occ |= point_in_inflated(px, py, ox, oy, r, node_radius, K);
+        occ |= point_in_inflated<RECT>(px, py, ox, oy, r, node_radius, K);
     }
     return __any_sync(kFull, occ);
 }

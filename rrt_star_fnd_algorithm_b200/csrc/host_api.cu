@@ -222,7 +222,8 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
         bt.finish = (int32_t*)d_fin.p; bt.best_path = (int32_t*)d_bp.p; bt.obst = (const double*)d_ob.p;
         bt.words = wb ? (const uint32_t*)d_w.p : nullptr; bt.trace = nullptr;
         rrtfnd_params_t q = *prm;
-        q.flags &= ~(RRTFND_FLAG_TRACE | RRTFND_FLAG_OBST_HAS_K);
+        q.flags &= ~(RRTFND_FLAG_TRACE | RRTFND_FLAG_OBST_HAS_K | RRTFND_FLAG_RECTANGLES);
+        for (size_t j = 0; j < M; ++j) if (ob[4 * j + 2] < 0.0) q.flags |= RRTFND_FLAG_RECTANGLES;
         if ((rc = rrtfnd_init_batch(&q, &bt, st))) break;
         if (timing) { cudaStreamSynchronize(st); t2 = now(); }
         if ((rc = rrtfnd_plan_batch(&q, &bt, st))) break;

@@ -104,8 +104,14 @@ __host__ __device__ inline size_t scratch_bytes(const rrtfnd_params_t& prm, int 
 __host__ __device__ inline size_t compact_bytes(const rrtfnd_params_t& prm) {
     return can_compact(prm) ? 2 * align_up((size_t)bitmap_words(prm) * 4, 16) : 0;
 }
+// RRT*-FN keeps one bit per slot "live and childless" in shared memory: forced_removal's random.choice(childless_nodes)
+// (src/algorithm.py:812-813) needs the r-th childless node in id order, which is a popcount prefix over these words instead of
+// a scan of the slot array per removal (16 % of a config-2 extension, profiles/r02_phase_clocks.md).
+__host__ __device__ inline size_t childless_bytes(const rrtfnd_params_t& prm) {
+    return prm.mode == RRTFND_MODE_FN ? align_up((size_t)bitmap_words(prm) * 4, 16) : 0;
+}
 __host__ __device__ inline size_t warp_smem_bytes(const rrtfnd_params_t& prm, int n_stages) {
-    size_t o = scratch_bytes(prm, n_stages) + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16);
+    size_t o = scratch_bytes(prm, n_stages) + align_up((size_t)n_stages * 8, 16) + align_up(sizeof(WordSrc), 16) + childless_bytes(prm);
     if (compact_bytes(prm) > scratch_bytes(prm, n_stages)) o += compact_bytes(prm);
     return align_up(o, 128);
 }
@@ -132,6 +138,7 @@ __device__ __forceinline__ double random_from(uint32_t w0, uint32_t w1) {       
 }
 
 // Map.is_occupied_c for a point of this lane alone (lanes hold different points): bit 0 = occupied, the rest = circles tested
+template <bool RECT>
 static __device__ __noinline__ int point_occupied_lane(const double2* tab, const rrtfnd_obst_grid_t* g, int M, int full_cells,
                                                        double px, double py, double node_radius) {
     const bool cull = full_cells > 0;
@@ -146,12 +153,13 @@ static __device__ __noinline__ int point_occupied_lane(const double2* tab, const
         double ox, oy, r, K;
         load_obst(tab, cull ? __ldg(g->pt_items + j) : j, ox, oy, r, K);
         ++tests;
-        if (point_in_inflated(px, py, ox, oy, r, node_radius, K)) return 2 * tests + 1;
+        if (point_in_inflated<RECT>(px, py, ox, oy, r, node_radius, K)) return 2 * tests + 1;
     }
     return 2 * tests;
 }
 
 // returns the number of circles this lane tested
+template <bool RECT>
 static __device__ __noinline__ int fill_batch(SampleBatch& sb, const WordSrc& rng, const rrtfnd_params_t& prm, const Obst& ob,
                                               double gx, double gy, long long attempts, int lane) {
     const unsigned long long c0 = rng.cursor, cj = c0 + 6ull * (unsigned)lane;
@@ -178,7 +186,7 @@ static __device__ __noinline__ int fill_batch(SampleBatch& sb, const WordSrc& rn
     if (hits && __ffs(hits) - 1 < len) { len = __ffs(hits); last_goal = 1; }
     int tests = 0;
     if (lane < len) {
-        const int r = point_occupied_lane(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, prm.node_radius);
+        const int r = point_occupied_lane<RECT>(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, prm.node_radius);
         occ = r & 1; tests = r >> 1;
     }
     const unsigned free_mask = __ballot_sync(kFull, lane < len && !occ);
@@ -416,7 +424,7 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
 // MODE >= 0 is a LEAN instance: that planner mode with choose-parent evaluated but not committed and no trace — the
 // configuration batches run in — so the other modes' code, the trace writes and the second near-set pass are not even
 // compiled in (the kernel's instruction footprint is what limits it, profiles/). MODE = -1 takes everything at run time.
-template <int WPB, int MINW, bool NG, int MODE, bool RING, bool WREC = NG>
+template <int WPB, int MINW, bool NG, int MODE, bool RING, bool WREC = NG, bool RECT = (MODE < 0)>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -485,6 +493,8 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     wp += align_up((size_t)n_stages * 8, 16);
     WordSrc& rng = *reinterpret_cast<WordSrc*>(wp);    // identical values written by every lane
     wp += align_up(sizeof(WordSrc), 16);
+    uint32_t* cb = reinterpret_cast<uint32_t*>(wp);    // RRT*-FN: bit s = slot s is live and childless (lane 0 maintains it)
+    wp += childless_bytes(prm);
     // compaction scratch: over the (then idle) ring / batch / scratch region when it fits, else its own space
     uint32_t* bm = reinterpret_cast<uint32_t*>(compact_bytes(prm) > scratch_bytes(prm, n_stages) ? wp : ws);
     uint32_t* pre = bm + align_up((size_t)bitmap_words(prm) * 4, 16) / 4;
@@ -541,12 +551,18 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
     }
     // childless live nodes (forced_removal draws among them); kept incrementally afterwards
     int n_childless = 0;
-    if (mode == RRTFND_MODE_FN) {
-        for (int base = 0; base < n_slots; base += 32) {
-            const int s = base + lane;
-            n_childless += __popc(__ballot_sync(kFull, s < n_slots && NCHILD[s] == 0));
+    auto childless_rebuild = [&](int slots) {
+        int n = 0;
+        for (int w = 0; w < bitmap_words(prm); ++w) {
+            const int s = w * 32 + lane;
+            const unsigned m = __ballot_sync(kFull, s < slots && NCHILD[s] == 0);
+            if (lane == 0) cb[w] = m;
+            n += __popc(m);
         }
-    }
+        __syncwarp();
+        return n;
+    };
+    if (mode == RRTFND_MODE_FN) n_childless = childless_rebuild(n_slots);
 
     const double r2 = dmul(prm.radius, prm.radius);
     const double goal_thresh = dmul(2.0, prm.goal_node_radius);
@@ -578,6 +594,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             sb.pos = 0; sb.len = 0;       // the bitmap may have lain over the prepared attempts: prepare them again
             __syncwarp();
             if (WREC) wrec_rebuild(WR, PARENT, ECOST, n_slots, lane);
+            if (mode == RRTFND_MODE_FN) n_childless = childless_rebuild(n_slots);
         }
         // ================================================================ A/B. Graph.random_node (src/graph.py:96-98) and
         // Map.is_occupied_c (src/map.py:38-47; rejection at src/algorithm.py:39-40)
@@ -587,7 +604,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             int pos = sb.pos, len = sb.len;
             const bool stale = pos < len && rng.cursor != sb.c0 + 6ull * (unsigned)pos;   // something else drew from the stream
             __syncwarp();
-            if (pos >= len || stale) { my_tests += fill_batch(sb, rng, prm, ob, gx, gy, attempts, lane); pos = 0; len = sb.len; }
+            if (pos >= len || stale) { my_tests += fill_batch<RECT>(sb, rng, prm, ob, gx, gy, attempts, lane); pos = 0; len = sb.len; }
             const unsigned rest = sb.free_mask >> pos;
             free_sample = rest != 0;
             const int e = free_sample ? pos + __ffs(rest) - 1 : len - 1;      // occupied entries before it are rejected attempts
@@ -605,7 +622,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 qx = dadd(prm.x_lo, dmul(dsub(prm.x_hi, prm.x_lo), next_random(rng)));
                 qy = dadd(prm.y_lo, dmul(dsub(prm.y_hi, prm.y_lo), next_random(rng)));
             }
-            free_sample = !point_occupied_warp(ob, qx, qy, prm.node_radius, lane, my_tests);
+            free_sample = !point_occupied_warp<RECT>(ob, qx, qy, prm.node_radius, lane, my_tests);
         }
         PH_MARK(0);                                                               // sample + occupancy
         if (!free_sample) continue;                                               // src/algorithm.py:39-40
@@ -661,7 +678,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             int rounds = 1;
             {
                 const double2 nb = XY[bs];
-                const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, lane, 32);
+                const int r = seg_blocked<RECT>(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, lane, 32);
                 my_tests += r >> 1;
                 if (!__any_sync(kFull, r & 1)) near_slot = bs;
             }
@@ -711,7 +728,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                             if (lane < n) {
                                 const int s = stage[head + lane];
                                 const double2 nb = XY[s];
-                                const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, 0, 1);
+                                const int r = seg_blocked<RECT>(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, 0, 1);
                                 my_tests += r >> 1;
                                 if (!(r & 1)) {
                                     const double d = dist2(nb.x, nb.y, qx, qy);
@@ -862,7 +879,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
                         if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
                         // Line(node, q_new): p1 = node (:846 / :903)
-                        const int r = seg_blocked(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
+                        const int r = seg_blocked<RECT>(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
                         my_tests += r >> 1;
                         hit = r & 1;
                         if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
@@ -980,7 +997,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                 const int new_parent = PARENT[new_slot];
                 auto reparent = [&](int s) {
                     const int oldp = PARENT[s];
-                    if (--NCHILD[oldp] == 0) ++d_childless;
+                    if (--NCHILD[oldp] == 0) { ++d_childless; if (mode == RRTFND_MODE_FN) cb[oldp >> 5] |= 1u << (oldp & 31); }
                     const double2 v = XY[s];
                     PARENT[s] = new_slot;
                     const double ec = dist_plain(v.x, v.y, px, py);
@@ -995,8 +1012,9 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         if (NFLAG[s] & 2) { NFLAG[s] &= (uint8_t)~2; reparent(s); }
                 }
                 NCHILD[new_slot] = n_rw;
-                if (n_rw == 0) ++d_childless;
-                if (NCHILD[PARENT[new_slot]]++ == 0) --d_childless;
+                if (n_rw == 0) { ++d_childless; if (mode == RRTFND_MODE_FN) cb[new_slot >> 5] |= 1u << (new_slot & 31); }
+                const int par_new = PARENT[new_slot];
+                if (NCHILD[par_new]++ == 0) { --d_childless; if (mode == RRTFND_MODE_FN) cb[par_new >> 5] &= ~(1u << (par_new & 31)); }
                 if (flagged) {   // the moved subtree holds a goal-reaching node: mark its new ancestors
                     int n = new_slot;
                     while (n >= 0 && !(NFLAG[n] & 1)) { NFLAG[n] |= 1; n = PARENT[n]; }
@@ -1023,15 +1041,29 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             for (;;) {
                 const uint32_t r = next_randbelow(rng, (uint32_t)total);          // random.choice (:813 / :816)
                 if (rng.exhausted) { status = RRTFND_ST_STREAM_EXHAUSTED; break; }
-                // r-th childless node in ascending slot order (tombstones hold nchild = -1)
-                int running = 0; pick = -1;
-                for (int base = 0; base < n_slots; base += 32) {
-                    const int s = base + lane;
-                    const unsigned m = __ballot_sync(kFull, s < n_slots && NCHILD[s] == 0);
-                    const int c = __popc(m);
-                    if ((int)r < running + c) { pick = base + (int)__fns(m, 0, (int)r - running + 1); break; }
-                    running += c;
+                // r-th childless node in ascending slot order: every lane counts a contiguous run of bitmap words, a warp
+                // prefix sum names the lane whose run holds it, that lane picks the bit
+                const int nw = (n_slots + 31) >> 5, wpl = (nw + 31) >> 5;
+                int cnt = 0;
+                for (int i = 0; i < wpl; ++i) { const int w = lane * wpl + i; if (w < nw) cnt += __popc(cb[w]); }
+                int incl = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(kFull, incl, off); if (lane >= off) incl += t; }
+                const int excl = incl - cnt;
+                const unsigned owner = __ballot_sync(kFull, (int)r >= excl && (int)r < incl);
+                int found = -1;
+                if (owner >> lane & 1u) {
+                    int rem = (int)r - excl;
+                    for (int i = 0; i < wpl; ++i) {
+                        const int w = lane * wpl + i;
+                        const unsigned bits = w < nw ? cb[w] : 0u;
+                        const int c = __popc(bits);
+                        if (rem < c) { found = w * 32 + (int)__fns(bits, 0, rem + 1); break; }
+                        rem -= c;
+                    }
                 }
+                pick = owner ? __shfl_sync(kFull, found, __ffs(owner) - 1) : -1;
+                if (pick < 0) { status = RRTFND_ST_NO_CHILDLESS; break; }          // the count and the bitmap disagree (cannot happen)
                 if (pick != new_slot && pick != leaf) break;                      // :815
             }
             if (status != RRTFND_ST_RUNNING) break;
@@ -1058,7 +1090,8 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             __syncwarp();
             if (lane == 0) {                                                      // Graph.remove_vertex (src/graph.py:64-77)
                 const int par = PARENT[pick];
-                if (par >= 0 && --NCHILD[par] == 0) ++d_childless;
+                if (par >= 0 && --NCHILD[par] == 0) { ++d_childless; cb[par >> 5] |= 1u << (par & 31); }
+                cb[pick >> 5] &= ~(1u << (pick & 31));
                 ID[pick] = -1; NCHILD[pick] = -1; PARENT[pick] = -1;
                 XY[pick] = nan2;
             }
@@ -1180,10 +1213,10 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int WPB, int MINW, bool NG = false, int MODE = -1, bool RING = true>
+template <int WPB, int MINW, bool NG = false, int MODE = -1, bool RING = true, bool RECT = (MODE < 0)>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
     size_t bytes = warp_smem_bytes(*prm, prm->reserved & 15) * WPB;
-    auto kern = plan_kernel<WPB, MINW, NG, MODE, RING>;
+    auto kern = plan_kernel<WPB, MINW, NG, MODE, RING, NG, RECT>;
     int blocks = (bt->n_planners + WPB - 1) / WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -1333,10 +1366,16 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     const int stages_req = (prm->reserved >> 4) & 15;
     const bool ring = stages_req == 1 ? false : (stages_req == 2 || stages_req == 4) ? true : prm->capacity > 2048;
     if (lean) q.reserved = cfg.stages | (plan_slices(q, b.n_planners) << 4);
-    if (lean && q.mode == RRTFND_MODE_STAR) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, true>(&q, &b, st)
-                                                        : launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_STAR, false>(&q, &b, st);
-    if (lean && q.mode == RRTFND_MODE_FN) return ring ? launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_FN, true>(&q, &b, st)
-                                                      : launch_plan<1, RRTFND_LEAN_MINW, false, RRTFND_MODE_FN, false>(&q, &b, st);
+    // circle-only tables (no RRTFND_FLAG_RECTANGLES) get the instances without the rectangle dispatch
+    const bool rect = (q.flags & RRTFND_FLAG_RECTANGLES) != 0;
+#define RRTFND_LEAN(M_, R_, X_) launch_plan<1, RRTFND_LEAN_MINW, false, M_, R_, X_>(&q, &b, st)
+    if (lean && q.mode == RRTFND_MODE_STAR)
+        return rect ? (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, true) : RRTFND_LEAN(RRTFND_MODE_STAR, false, true))
+                    : (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, false) : RRTFND_LEAN(RRTFND_MODE_STAR, false, false));
+    if (lean && q.mode == RRTFND_MODE_FN)
+        return rect ? (ring ? RRTFND_LEAN(RRTFND_MODE_FN, true, true) : RRTFND_LEAN(RRTFND_MODE_FN, false, true))
+                    : (ring ? RRTFND_LEAN(RRTFND_MODE_FN, true, false) : RRTFND_LEAN(RRTFND_MODE_FN, false, false));
+#undef RRTFND_LEAN
     switch (cfg.wpb) {
         case 1: return launch_wpb<1>(&q, &b, cfg.minw, st);
         case 2: return launch_wpb<2>(&q, &b, cfg.minw, st);
