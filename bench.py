@@ -505,12 +505,18 @@ def run_e2e(args, w, P, first, b, dev):
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
     sg = pin((P, 4), torch.float64); sg.copy_(torch.from_numpy(np.concatenate([starts, goals], 1)))
     sd = pin((P, 2), torch.int64); sd.copy_(torch.from_numpy(np.stack([seeds, sids], 1).astype(np.int64)))
-    ob = pin((max(prm.n_obst, 1), 3), torch.float64); ob[:prm.n_obst].copy_(torch.from_numpy(np.asarray(w["obstacles"], np.float64)))
+    rows = np.asarray(w["obstacles"], np.float64)          # (ox, oy, r) circles, or table rows (cx, cy, -hx, hy) of the rectangle variant
+    ob = pin((max(prm.n_obst, 1), rows.shape[1]), torch.float64); ob[:prm.n_obst].copy_(torch.from_numpy(rows))
+    if rows.shape[1] == 4:                                 # rows that carry their fourth column: rrtfnd_plan_host takes them as they are
+        import copy
+        from rrt_star_fnd_algorithm_b200._structs import FLAG_OBST_HAS_K
+        prm = copy.copy(prm)
+        prm.flags |= FLAG_OBST_HAS_K
     o_pl = pin((P, PLANNER_BYTES), torch.uint8)
     o_xy, o_e = pin((P, Cn, 2), torch.float64), pin((P, Cn), torch.float64)
     o_par, o_nc, o_id = pin((P, Cn), torch.int32), pin((P, Cn), torch.int32), pin((P, Cn), torch.int32)
     o_bp = pin((P, prm.path_cap), torch.int32)
-    h2d = sg.numel() * 8 + sd.numel() * 8 + prm.n_obst * 24
+    h2d = sg.numel() * 8 + sd.numel() * 8 + prm.n_obst * 8 * rows.shape[1]
     d2h = o_pl.numel() + o_xy.numel() * 8 + o_e.numel() * 8 + 3 * o_par.numel() * 4 + o_bp.numel() * 4
 
     def call():
