@@ -386,6 +386,7 @@ def main():
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         import datetime
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version / debug lines go to stderr: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     w, _ = load_workload(args)
