@@ -1240,8 +1240,13 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
     b.reserved = (++g_serial) * 16;
     for (int k = 0; k < n_slices; ++k) {
         rrtfnd_params_t q = *prm;
-        const double f = (double)(k + 1) / n_slices;
-        q.iter_num = k + 1 == n_slices ? prm->iter_num : (int)(prm->iter_num * (MODE == RRTFND_MODE_STAR ? sqrt(f) : f));
+        const double x = (double)(k + 1) / n_slices;
+        double f = MODE == RRTFND_MODE_STAR ? sqrt(x) : x;
+        if (const char* sh = getenv("RRTFND_SLICE_SHAPE")) {          // experiment: 1 linear, 2 / 3 slices shrinking towards the end
+            const int shape = atoi(sh);
+            f = shape == 1 ? x : shape == 2 ? 1.0 - (1.0 - x) * (1.0 - x) : shape == 3 ? 1.0 - (1.0 - x) * (1.0 - x) * (1.0 - x) : f;
+        }
+        q.iter_num = k + 1 == n_slices ? prm->iter_num : (int)(prm->iter_num * f);
         q.reserved = (prm->reserved & 255) | (k << 8);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(32 * WPB); cfg.dynamicSmemBytes = bytes; cfg.stream = st;
