@@ -41,7 +41,10 @@
 // Measured on B200 in round 2 and removed (profiles/r02_variants.md): the winner's rank counted inside the near-set scan instead
 // of a separate pass (-9 %: six more instructions in the hottest loop cost more than the pass they save), candidates split over
 // idle lanes (+-0), a first annulus bounded by the lanes' own minima (-4 %), persistent CTAs with the obstacle tables in shared
-// memory (hung), the segment test and the chain walk fused into one loop (-26 %).
+// memory (hung), the segment test and the chain walk fused into one loop (-26 %), and an annulus search that stages a whole
+// annulus, narrows it when it holds more than 96 nodes and tests it in key order 32 at a time with an early exit (-13 % on
+// 16,384 planners, -32 % on 2,048: the circle tests it saves are few - segments stop at their first blocking circle - and the
+// extra scans and the threshold bisection cost more; profiles/r02_s8_raw.txt).
 // Graph.get_cost walks of the candidate chunks: over the parent[] / ecost[] arrays (two loads per hop, one hop per memory
 // round trip), or - kernels instantiated with WREC, the node-grid kernel of large single trees - over the 16-byte walk
 // records with the self-healing grandparent hint (walk_records: one load per hop, two hops per round trip while the hints
@@ -1230,8 +1233,7 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
         kern<<<blocks, 32 * WPB, bytes, st>>>(*prm, *bt);
         return (int)cudaGetLastError();
     }
-    // Sliced run. Slice k grows every planner to iter_num * f(k / n_slices); f is chosen so that slices take about the same
-    // time (an RRT* extension costs ~ the tree size, so f = sqrt; RRT*-FN saturates at its node cap, f = identity). Every
+    // Sliced run. Slice k grows every planner to iter_num * f(k / n_slices) (f below). Every
     // launch but the first carries the programmatic-stream-serialization attribute: it may start once all CTAs of its
     // predecessor have started, and its warps wait for their own planner's ticket (see the kernel). Tickets are serial * 16 +
     // slice, strictly increasing over the calls of this process, so a stale ticket in a re-used record is never ahead.
@@ -1240,12 +1242,12 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
     b.reserved = (++g_serial) * 16;
     for (int k = 0; k < n_slices; ++k) {
         rrtfnd_params_t q = *prm;
+        // slice k ends at iter_num * f(x), x = (k + 1) / n_slices. RRT*: f = 1 - (1 - x)^3 - long first slices, ever shorter
+        // last ones, because what is exposed at the end of the call is half of the LAST slice (measured on c3: 35.4 M ext/s
+        // with f = sqrt(x), 34.7 M linear, 35.8 M with 1 - (1 - x)^2, 36.0 M with the cube; profiles/r02_s7_raw.txt).
+        // RRT*-FN: linear (the cap makes every extension cost the same; the shrinking schedule measured -7.5 % on c2).
         const double x = (double)(k + 1) / n_slices;
-        double f = MODE == RRTFND_MODE_STAR ? sqrt(x) : x;
-        if (const char* sh = getenv("RRTFND_SLICE_SHAPE")) {          // experiment: 1 linear, 2 / 3 slices shrinking towards the end
-            const int shape = atoi(sh);
-            f = shape == 1 ? x : shape == 2 ? 1.0 - (1.0 - x) * (1.0 - x) : shape == 3 ? 1.0 - (1.0 - x) * (1.0 - x) * (1.0 - x) : f;
-        }
+        const double f = MODE == RRTFND_MODE_STAR ? 1.0 - (1.0 - x) * (1.0 - x) * (1.0 - x) : x;
         q.iter_num = k + 1 == n_slices ? prm->iter_num : (int)(prm->iter_num * f);
         q.reserved = (prm->reserved & 255) | (k << 8);
         cudaLaunchConfig_t cfg = {};
