@@ -79,7 +79,12 @@ static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, 
     const int32_t* __restrict__ start = g->seg_start;
     const int32_t* __restrict__ items = g->seg_items;
     int tests = 0;
-    for (int cy = cy0; cy <= cy1; ++cy) {
+    // rows are visited from p1's end of the segment: the nearest-visible search puts the SAMPLE there (Line(q_rand, node)), and a
+    // sample that no node can see - most samples while a tree is young - is boxed in by circles next to it, so its segments end
+    // at their first rows instead of after half of them (the OR over circles does not care about the order)
+    const int n_rows = cy1 - cy0, dcy = p1y <= p2y ? 1 : -1;
+    int cy = p1y <= p2y ? cy0 : cy1;
+    for (int row = 0; row <= n_rows; ++row, cy += dcy) {
         int j = 0, e = M;
         if (cull) {
             double xa = sg.lo, xb = sg.hi;
