@@ -51,7 +51,10 @@ __device__ __forceinline__ void load_obst(const double2* __restrict__ tab, int j
 
 // through_obstacle(Line(p1, p2), obstacles) over the circles first, first + stride, ... of the candidate list.
 // Returns (circle tests performed << 1) | hit. Stops at the first hit.
-template <bool RECT = true>
+// XORD: the circles of a grid row are tested from p1's end as well (a row lists its cells in ascending x). Measured: +9.5 % on a
+// single-wave batch, +6.6 % on c2, -1.8 % on c3's 16,384 planners (the extra index arithmetic), and -8.7 % when one kernel holds
+// both forms (a second copy of this function does not fit the instruction cache): a kernel instance uses ONE form throughout.
+template <bool RECT = true, bool XORD = true>
 static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, const rrtfnd_obst_grid_t* __restrict__ g, int M,
                                         int full_cells, double p1x, double p1y, double p2x, double p2y, int first,
                                         int stride) {
@@ -98,11 +101,21 @@ static __device__ __noinline__ int seg_blocked(const double2* __restrict__ tab, 
             j = __ldg(start + cy * nx + cx0);
             e = __ldg(start + cy * nx + cx1 + 1);
         }
-        for (j += first; j < e; j += stride) {
-            double ox, oy, r, K;
-            load_obst(tab, cull ? __ldg(items + j) : j, ox, oy, r, K);
-            ++tests;
-            if (seg_hits_circle<RECT>(sg, ox, oy, r, K)) return (tests << 1) | 1;
+        if (XORD) {   // ... and the circles of a row from p1's end as well (the row's cells are listed in ascending x)
+            const int n_row = e - j, base = p1x <= p2x ? j : e - 1, dj = p1x <= p2x ? 1 : -1;
+            for (int k = first; k < n_row; k += stride) {
+                double ox, oy, r, K;
+                load_obst(tab, cull ? __ldg(items + base + dj * k) : base + dj * k, ox, oy, r, K);
+                ++tests;
+                if (seg_hits_circle<RECT>(sg, ox, oy, r, K)) return (tests << 1) | 1;
+            }
+        } else {
+            for (j += first; j < e; j += stride) {
+                double ox, oy, r, K;
+                load_obst(tab, cull ? __ldg(items + j) : j, ox, oy, r, K);
+                ++tests;
+                if (seg_hits_circle<RECT>(sg, ox, oy, r, K)) return (tests << 1) | 1;
+            }
         }
     }
     return tests << 1;

@@ -427,7 +427,7 @@ __device__ __forceinline__ void fetch_tile(XYStream& xs, const double2* XY, cons
 // MODE >= 0 is a LEAN instance: that planner mode with choose-parent evaluated but not committed and no trace — the
 // configuration batches run in — so the other modes' code, the trace writes and the second near-set pass are not even
 // compiled in (the kernel's instruction footprint is what limits it, profiles/). MODE = -1 takes everything at run time.
-template <int WPB, int MINW, bool NG, int MODE, bool RING, bool WREC = NG, bool RECT = (MODE < 0)>
+template <int WPB, int MINW, bool NG, int MODE, bool RING, bool WREC = NG, bool RECT = (MODE < 0), bool XORD = true>
 __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd_params_t prm, const __grid_constant__ rrtfnd_batch_t bt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
             int rounds = 1;
             {
                 const double2 nb = XY[bs];
-                const int r = seg_blocked<RECT>(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, lane, 32);
+                const int r = seg_blocked<RECT, XORD>(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, lane, 32);
                 my_tests += r >> 1;
                 if (!__any_sync(kFull, r & 1)) near_slot = bs;
             }
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                             if (lane < n) {
                                 const int s = stage[head + lane];
                                 const double2 nb = XY[s];
-                                const int r = seg_blocked<RECT>(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, 0, 1);
+                                const int r = seg_blocked<RECT, XORD>(ob.tab, ob.g, ob.M, ob.full_cells, qx, qy, nb.x, nb.y, 0, 1);
                                 my_tests += r >> 1;
                                 if (!(r & 1)) {
                                     const double d = dist2(nb.x, nb.y, qx, qy);
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(32 * WPB, MINW / WPB) plan_kernel(const rrtfnd
                         dpl = dist_plain(c.x, c.y, px, py);                       // :842 / :899
                         if (dpl == 0.0 && c.x == px && c.y == py) dup = true;     // src/graph.py:54-56 corner (B9)
                         // Line(node, q_new): p1 = node (:846 / :903)
-                        const int r = seg_blocked<RECT>(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
+                        const int r = seg_blocked<RECT, XORD>(ob.tab, ob.g, ob.M, ob.full_cells, c.x, c.y, px, py, 0, 1);
                         my_tests += r >> 1;
                         hit = r & 1;
                         if (!hit) w_from = s;                                     // Graph.get_cost(id) (:848 / :905)
@@ -1216,10 +1216,10 @@ __global__ void init_kernel(const rrtfnd_params_t prm, const rrtfnd_batch_t bt) 
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int WPB, int MINW, bool NG = false, int MODE = -1, bool RING = true, bool RECT = (MODE < 0)>
+template <int WPB, int MINW, bool NG = false, int MODE = -1, bool RING = true, bool RECT = (MODE < 0), bool XORD = true>
 static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cudaStream_t st) {
     size_t bytes = warp_smem_bytes(*prm, prm->reserved & 15) * WPB;
-    auto kern = plan_kernel<WPB, MINW, NG, MODE, RING, NG, RECT>;
+    auto kern = plan_kernel<WPB, MINW, NG, MODE, RING, NG, RECT, XORD>;
     int blocks = (bt->n_planners + WPB - 1) / WPB;
     if (bytes > kMaxSmem) return RRTFND_E_SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -1375,13 +1375,20 @@ extern "C" int rrtfnd_plan_batch(const rrtfnd_params_t* prm, const rrtfnd_batch_
     if (lean) q.reserved = cfg.stages | (plan_slices(q, b.n_planners) << 4);
     // circle-only tables (no RRTFND_FLAG_RECTANGLES) get the instances without the rectangle dispatch
     const bool rect = (q.flags & RRTFND_FLAG_RECTANGLES) != 0;
-#define RRTFND_LEAN(M_, R_, X_) launch_plan<1, RRTFND_LEAN_MINW, false, M_, R_, X_>(&q, &b, st)
-    if (lean && q.mode == RRTFND_MODE_STAR)
-        return rect ? (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, true) : RRTFND_LEAN(RRTFND_MODE_STAR, false, true))
-                    : (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, false) : RRTFND_LEAN(RRTFND_MODE_STAR, false, false));
+#define RRTFND_LEAN(M_, R_, X_, O_) launch_plan<1, RRTFND_LEAN_MINW, false, M_, R_, X_, O_>(&q, &b, st)
+    // XORD (cull.cuh: the circles of a grid row are tested from p1's end) pays where a launch waits for its slowest planner -
+    // a batch that fits the warp slots (+9.5 % at 2,048 planners) - and on RRT*-FN (+6.6 % on c2); on a multi-wave RRT* batch,
+    // bound by aggregate throughput, its extra index arithmetic costs 1.8 %: those launches take the instance without it.
+    if (lean && q.mode == RRTFND_MODE_STAR) {
+        const bool xord = plan_slices(q, b.n_planners) <= 1;
+        if (xord) return rect ? (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, true, true) : RRTFND_LEAN(RRTFND_MODE_STAR, false, true, true))
+                              : (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, false, true) : RRTFND_LEAN(RRTFND_MODE_STAR, false, false, true));
+        return rect ? (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, true, false) : RRTFND_LEAN(RRTFND_MODE_STAR, false, true, false))
+                    : (ring ? RRTFND_LEAN(RRTFND_MODE_STAR, true, false, false) : RRTFND_LEAN(RRTFND_MODE_STAR, false, false, false));
+    }
     if (lean && q.mode == RRTFND_MODE_FN)
-        return rect ? (ring ? RRTFND_LEAN(RRTFND_MODE_FN, true, true) : RRTFND_LEAN(RRTFND_MODE_FN, false, true))
-                    : (ring ? RRTFND_LEAN(RRTFND_MODE_FN, true, false) : RRTFND_LEAN(RRTFND_MODE_FN, false, false));
+        return rect ? (ring ? RRTFND_LEAN(RRTFND_MODE_FN, true, true, true) : RRTFND_LEAN(RRTFND_MODE_FN, false, true, true))
+                    : (ring ? RRTFND_LEAN(RRTFND_MODE_FN, true, false, true) : RRTFND_LEAN(RRTFND_MODE_FN, false, false, true));
 #undef RRTFND_LEAN
     switch (cfg.wpb) {
         case 1: return launch_wpb<1>(&q, &b, cfg.minw, st);

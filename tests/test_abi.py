@@ -97,7 +97,7 @@ def test_planner_kernel_sass_streams_the_tree_through_tma():
     if not os.path.exists(tool):
         pytest.skip("cuobjdump not available")
     from rrt_star_fnd_algorithm_b200 import _abi
-    out = subprocess.run([tool, "-sass", "-fun", "_ZN6rrtfnd11plan_kernelILi1ELi16ELb0ELi1ELb1ELb0ELb0EEEv13rrtfnd_params12rrtfnd_batch",
+    out = subprocess.run([tool, "-sass", "-fun", "_ZN6rrtfnd11plan_kernelILi1ELi16ELb0ELi1ELb1ELb0ELb0ELb0EEEv13rrtfnd_params12rrtfnd_batch",
                           _abi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "UBLKCP" in out and "SYNCS.ARRIVE.TRANS64" in out and "SYNCS.PHASECHK" in out
