@@ -166,6 +166,8 @@ class DeviceFNDReplanner:
     @property
     def stats(self):
         s = self.stats_t.cpu().numpy()
+        if getattr(self.b, "_grid_overflow", None) is not None and int(self.b._grid_overflow.item()):
+            raise RuntimeError("rrtfnd_obst_grid_build_device: a culling list did not fit its buffer during the ticks")
         ph = self.phase
         return dict(moves=int(s[0]), splits=int(s[1]), reconnected=int(s[2]), regrown=int(s[3]), regrow_extensions=int(s[4]),
                     lost=int((ph == LOST).sum()), arrived=int((ph == ARRIVED).sum()), edge_cuts=int(s[8]))
