@@ -376,7 +376,8 @@ int rrtfnd_fnd_tick(const rrtfnd_params_t* prm, const rrtfnd_batch_t* batch, con
 /* The culling grid of rrtfnd_obst_grid_build_host4, built by a kernel from the DEVICE table obst [M][4] into the caller's
  * device arrays (grid->seg_start / pt_start hold cells_cap entries, seg_items / pt_items seg_cap / pt_cap). The grid
  * geometry depends on the box, M and `cell` only; coord_max must bound every |coordinate| and radius the table will hold
- * (it sets the exactness margin; larger is still exact). *overflow (device int) = 1 if a list did not fit. */
+ * (it sets the exactness margin; larger is still exact). *overflow (device int, zeroed by the caller, never cleared here) is set
+ * to 1 if a list did not fit. */
 int rrtfnd_obst_grid_build_device(const double* obst, int32_t n_obst, double node_radius, double lo_x, double hi_x,
                                   double lo_y, double hi_y, double cell, double coord_max, rrtfnd_obst_grid_t* grid,
                                   int32_t seg_cap, int32_t pt_cap, int32_t cells_cap, int32_t* overflow, void* stream);

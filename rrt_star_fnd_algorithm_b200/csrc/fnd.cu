@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const double* __restric
                 s_tot[tid] = run;
             }
             __syncthreads();
-            if (tid == 0) *overflow = (s_tot[0] > seg_cap || s_tot[1] > pt_cap) ? 1 : 0;
+            if (tid == 0 && (s_tot[0] > seg_cap || s_tot[1] > pt_cap)) *overflow = 1;      // sticky: the caller zeroes it
         }
     }
 }

@@ -148,12 +148,22 @@ def make_workload_batch(w, starts, goals, seeds, sids, **kw):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,total,count", [("c3", 16384, 64), ("c2", 4096, 64)])
-def test_default_bench_launch_matches_oracle_at_full_length(name, total, count):
-    """The kernel instance bench.py runs (launch word 0 at the workload's own capacity), 5,000 iterations per planner."""
+@pytest.mark.parametrize("name,total,count,slices", [("c3", 16384, 64, 0), ("c2", 4096, 64, 0), ("c3", 16384, 64, 8), ("c2", 4096, 64, 8)],
+                         ids=["c3-one-wave", "c2-one-wave", "c3-as-benchmarked", "c2-as-benchmarked"])
+def test_default_bench_launch_matches_oracle_at_full_length(name, total, count, slices, monkeypatch):
+    """The kernel instances bench.py runs (launch word 0 at the workload's own capacity), 5,000 iterations per planner. A batch
+    that fits the warp slots takes one launch of the single-wave instance (what a rank runs when config 3 is sharded over 8
+    GPUs); `slices = 8` forces what the library does for the benchmarked 16,384- / 4,096-planner batches: eight overlapped slice
+    launches of the multi-wave instance (circles of a grid row in list order)."""
+    import ctypes as C
+    from rrt_star_fnd_algorithm_b200 import _abi
     w = W.WORKLOADS[name]()
     idx, starts, goals, seeds, sids = spread_problems(w, total, count)
-    b = make_workload_batch(w, starts, goals, seeds, sids).run()
+    if slices:
+        monkeypatch.setenv("RRTFND_SLICES", str(slices))
+    b = make_workload_batch(w, starts, goals, seeds, sids)
+    assert _abi.lib.rrtfnd_plan_launches(C.byref(b.prm), len(idx)) == max(1, slices)
+    b.run()
     assert (b.prm.capacity > 2048) == (name == "c3")         # c3 takes the TMA ring, c2 the plain-load scans
     pls = b.planners()
     trees = oracle_run(w, starts, goals, seeds, sids)
