@@ -153,6 +153,7 @@ extern "C" int rrtfnd_plan_host(const rrtfnd_params_t* prm, int32_t P, const dou
     for (size_t j = 0; j < M; ++j) {
         const double ox = obst_host[ostride * j], oy = obst_host[ostride * j + 1], r = obst_host[ostride * j + 2];
         double K;
+        if (!has_k && r < 0.0) return RRTFND_E_BADARG;          // rectangle rows need their fourth column (RRTFND_FLAG_OBST_HAS_K)
         if (has_k) K = obst_host[4 * j + 3];
         else {
             volatile double two = 2.0;

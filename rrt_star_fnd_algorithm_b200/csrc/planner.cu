@@ -21,6 +21,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "../../include/rrtfnd.h"
 #include "arith.cuh"
 #include "cull.cuh"
@@ -1237,9 +1239,9 @@ static int launch_plan(const rrtfnd_params_t* prm, const rrtfnd_batch_t* bt, cud
     // launch but the first carries the programmatic-stream-serialization attribute: it may start once all CTAs of its
     // predecessor have started, and its warps wait for their own planner's ticket (see the kernel). Tickets are serial * 16 +
     // slice, strictly increasing over the calls of this process, so a stale ticket in a re-used record is never ahead.
-    static int g_serial = 0;
+    static std::atomic<int> g_serial{0};
     rrtfnd_batch_t b = *bt;
-    b.reserved = (++g_serial) * 16;
+    b.reserved = (g_serial.fetch_add(1) + 1) * 16;
     for (int k = 0; k < n_slices; ++k) {
         rrtfnd_params_t q = *prm;
         // slice k ends at iter_num * f(x), x = (k + 1) / n_slices. RRT*: f = 1 - (1 - x)^3 - long first slices, ever shorter

@@ -102,3 +102,19 @@ def test_planner_kernel_sass_streams_the_tree_through_tma():
     assert "sm_100a" in out
     assert "UBLKCP" in out and "SYNCS.ARRIVE.TRANS64" in out and "SYNCS.PHASECHK" in out
     assert out.count("DADD") > 100 and out.count("DMUL") > 50     # fp64 arithmetic as separately rounded adds and multiplies
+
+
+def test_plan_launches_reports_the_slicing_rule():
+    """rrtfnd_plan_launches: batches larger than the resident warp slots (148 SMs x 16 warps when no device answers) are grown in 8
+    overlapped slices by the lean instances; everything else is one launch."""
+    from rrt_star_fnd_algorithm_b200 import _abi, _structs as S
+    p = S.Params()
+    p.mode, p.iter_num, p.capacity, p.near_cap, p.finish_cap, p.path_cap = S.MODE_STAR, 5000, 5002, 64, 1024, 1024
+    p.flags = S.FLAG_EVAL_CHOOSE_PARENT
+    assert _abi.lib.rrtfnd_plan_launches(C.byref(p), 16384) == 8 and _abi.lib.rrtfnd_plan_launches(C.byref(p), 4096) == 8
+    assert _abi.lib.rrtfnd_plan_launches(C.byref(p), 2048) == 1
+    p.flags = S.FLAG_EVAL_CHOOSE_PARENT | S.FLAG_TRACE
+    assert _abi.lib.rrtfnd_plan_launches(C.byref(p), 16384) == 1          # the generic instance (trace) is never sliced
+    p.flags, p.mode = S.FLAG_EVAL_CHOOSE_PARENT, S.MODE_RRT
+    assert _abi.lib.rrtfnd_plan_launches(C.byref(p), 16384) == 1          # RRT stops at the goal: no resumable slices
+    assert _abi.lib.rrtfnd_plan_launches(None, 5) == -100
