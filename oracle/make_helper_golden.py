@@ -1,6 +1,7 @@
 """Golden vectors for the per-iteration helper functions (new_node, nearest_node[_kdtree], steer, choose_parent[_kdtree],
-rewire[_kdtree], forced_removal, intersection_circle, remove_children, get_near_nodes, check_for_tree_associativity;
-src/algorithm.py:36-51, :328-341, :407-434, :555-578, :666-746, :800-935) from the UNMODIFIED reference driven by Python's real
+rewire[_kdtree], forced_removal, intersection_circle and its pieces calc_delta / delta_solutions / is_between, remove_children,
+reconnect_ancestors, delete_ancestors, get_near_nodes, check_for_tree_associativity;
+src/algorithm.py:36-51, :328-341, :407-434, :531-551, :555-635, :666-746, :800-935) from the UNMODIFIED reference driven by Python's real
 global `random` — TEST INFRASTRUCTURE, build container only.
 
     python -m oracle.make_helper_golden        # writes tests/golden/helpers_*.npz
@@ -145,7 +146,43 @@ def drive(alg, graph_mod, map_mod, line_mod, kdtree_cls, case):
     _arrays_present(R, "rc", out)
     out["assoc"] = np.array([bool(alg.check_for_tree_associativity(G, 0, i)) for i in sorted(G.vertices)][:64])
     out["near_nodes"] = np.array(sorted(alg.get_near_nodes(G, 7, radius * 2, 0)))
+
+    # ---- reconnect_ancestors (re-rooting) / delete_ancestors on copies; children ORDER matters to later draws, so keep it
+    A = copy.deepcopy(G)
+    deep = max(A.vertices, key=lambda i: len(path_to_root(A, i)))
+    alg.reconnect_ancestors(A, deep)
+    _arrays_present(A, "ra", out)
+    out["ra_children"] = np.array([c for i in sorted(A.vertices) for c in A.children[i] + [-1]], np.int32)
+    A2 = copy.deepcopy(G)
+    alg.reconnect_ancestors(A2, A2.children[0][0])                  # a child of the root: the loop body never runs
+    _arrays_present(A2, "ra2", out)
+    D = copy.deepcopy(G)
+    with contextlib.redirect_stdout(io.StringIO()):
+        alg.delete_ancestors(D, deep)
+    out["da_ids"] = np.array(sorted(D.vertices), np.int32)
+
+    # ---- the scalar pieces of intersection_circle
+    cd = []
+    for k in range(120):
+        s = out["ic_segs"][k]
+        if s[0] == s[2]:
+            continue
+        ln = line_mod.Line((float(s[0]), float(s[1])), (float(s[2]), float(s[3])))
+        delta, a, b = alg.calc_delta(ln, obstacles[int(s[4])])
+        row = [float(delta), float(a), float(b), np.nan, np.nan, 0.0, 0.0]
+        if delta >= 0:
+            x1, x2 = alg.delta_solutions(delta, a, b)
+            row[3:] = [float(x1[0]), float(x2[0]), float(alg.is_between(x1, ln.p1, ln.p2)), float(alg.is_between(x2, ln.p1, ln.p2))]
+        cd.append(row)
+    out["calc_delta"] = np.array(cd)
     return out
+
+
+def path_to_root(G, i):
+    p = [i]
+    while G.parent[p[-1]] is not None:
+        p.append(G.parent[p[-1]])
+    return p
 
 
 def _arrays_present(G, prefix, out):

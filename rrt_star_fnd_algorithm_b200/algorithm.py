@@ -375,6 +375,29 @@ def intersection_circle(line, circle: list) -> bool:
     return bool(through_obstacle_batch([line.p1], [line.p2], [circle])[0])
 
 
+def calc_delta(line, circle: list) -> tuple:
+    """(discriminant, a, b) of the quadratic in x that intersects the infinite line y = dir * x + const_term with the circle
+    `[(x0, y0), r]` (src/algorithm.py:607-621). Host scalars in the reference's operation order, Python `**` included; the
+    kernels evaluate the same expressions per circle with the constant part of `c` precomputed (arith.cuh)."""
+    (x0, y0), r = (circle[0][0], circle[0][1]), circle[1]
+    m, n = line.dir, line.const_term
+    a = (1 + m ** 2)
+    b = 2 * (-x0 + m * n - m * y0)
+    c = -r ** 2 + x0 ** 2 + y0 ** 2 - 2 * y0 * n + n ** 2
+    return b ** 2 - 4 * a * c, a, b
+
+
+def delta_solutions(delta: float, a: float, b: float) -> tuple:
+    """The two roots' x as `[x, None]` lists, larger root first for a > 0 (src/algorithm.py:594-604); the caller fills in y."""
+    root = delta ** 0.5
+    return [(-b + root) / (2 * a), None], [(-b - root) / (2 * a), None]
+
+
+def is_between(pb, p1, p2) -> bool:
+    """Is pb's x STRICTLY inside the x-interval of (p1, p2)? y is not looked at (src/algorithm.py:624-635)."""
+    return pb[0] > min(p1[0], p2[0]) and pb[0] < max(p1[0], p2[0])
+
+
 def steer(to_vertex: tuple, from_vertex: tuple, max_length: float) -> tuple:
     """Point at most `max_length` from `from_vertex` towards `to_vertex`; `to_vertex` itself, untouched, when it is closer
     (src/algorithm.py:731-746). Six scalar operations in the reference's order (the planner kernel does the same on the
@@ -561,6 +584,36 @@ def remove_children(G: Graph, id_node: int, path: list) -> None:
         stack.extend(c for c in G.children[n] if c not in path)
     for n in reversed(order):                       # leaves first, as the recursion deletes them; an off-path node goes
         G.remove_vertex(n)                          # even when an on-path child of it stays behind (as in the reference)
+
+
+def reconnect_ancestors(G: Graph, id_node: int) -> None:
+    """Make id_node the root of its tree by turning every edge on its way up around (src/algorithm.py:531-543; what
+    reconnect and regrow do to the separate tree once a link is found, fnd.cu `reroot`). As in the reference, the last flip is
+    half done - the old root gets its new parent but is not entered in that parent's children list, nor is the parent taken out
+    of the old root's -, costs are not touched, and id_node keeps its old parent pointer (the callers overwrite it with the
+    link they found)."""
+    child, up = id_node, G.parent[id_node]
+    if up is None:
+        return
+    while G.parent[up] is not None:
+        above = G.parent[up]
+        G.parent[up] = child
+        G.children[child].append(up)
+        G.children[up].remove(child)
+        child, up = up, above
+    G.parent[up] = child
+
+
+def delete_ancestors(G: Graph, id_node: int) -> None:
+    """Walk from id_node to its root and strip every ancestor of ALL its subtrees (remove_children with an empty path):
+    id_node goes with the first of them, and in the end only the root is left. Unused in the reference (its one call is
+    commented out, src/algorithm.py:514, :546-551); kept for name parity."""
+    node = id_node
+    up = G.parent[node]
+    while up is not None:
+        node = up
+        remove_children(G, node, [])
+        up = G.parent[node]
 
 
 def check_for_tree_associativity(G: Graph, root_node: int, node_to_check: int) -> bool:

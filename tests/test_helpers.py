@@ -1,5 +1,6 @@
 """The reference's per-iteration helpers on Graph objects (new_node, nearest_node[_kdtree], steer, choose_parent[_kdtree],
-rewire[_kdtree], forced_removal, intersection_circle, Line, remove_children, get_near_nodes, check_for_tree_associativity).
+rewire[_kdtree], forced_removal, intersection_circle with calc_delta / delta_solutions / is_between, Line, remove_children,
+reconnect_ancestors, delete_ancestors, get_near_nodes, check_for_tree_associativity).
 
 tests/golden/helpers_*.npz hold what the UNMODIFIED reference returns for one fixed call sequence
 (oracle/make_helper_golden.py `drive`); the same sequence runs here on the product's modules and every return value, side
