@@ -699,7 +699,7 @@ extern "C" int rrtfnd_obst_grid_build_device(const double* obst, int32_t n_obst,
     if (!grid->seg_start || !grid->seg_items || !grid->pt_start || !grid->pt_items) return RRTFND_E_BADARG;
     int32_t* ss = const_cast<int32_t*>(grid->seg_start); int32_t* si = const_cast<int32_t*>(grid->seg_items);
     int32_t* ps = const_cast<int32_t*>(grid->pt_start); int32_t* pi = const_cast<int32_t*>(grid->pt_items);
-    const double slope_max = 256.0;
+    const double slope_max = rrtfnd::grid_slope_max();
     const double w = hi_x - lo_x, h = hi_y - lo_y;
     if (n_obst == 0) { grid->nx = grid->ny = 0; return 0; }
     if (!(cell > 0.0)) cell = sqrt(w * h / (double)n_obst);

@@ -59,7 +59,7 @@ static int grid_build(const double* obst_host, int stride, int32_t M, double nod
         if (stride == 4 && obst_host[4 * j + 2] < 0.0) S = fmax(S, fabs(obst_host[4 * j + 3]));   // a rectangle's half height
     }
     if (!(S < 1e100)) return RRTFND_E_BADARG;
-    const double slope_max = 256.0;
+    const double slope_max = rrtfnd::grid_slope_max();
     const double margin = rrtfnd::grid_seg_margin(S, slope_max);
     const double w = hi_x - lo_x, h = hi_y - lo_y;
     if (!(cell > 0.0)) cell = sqrt(w * h / (double)M);

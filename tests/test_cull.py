@@ -23,6 +23,15 @@ def test_no_culled_circle_ever_hits(coord_max):
     assert hits == 0
 
 
+@pytest.mark.parametrize("slope_max", [1024.0, 4096.0, 65536.0])      # 1024 is what the builders ship (grid_slope_max, grid.cuh)
+def test_claim_holds_for_larger_slope_bounds(slope_max):
+    """The margin follows the slope bound (it is linear in 1 + slope_max), so the claim is the same claim at any bound."""
+    for coord_max in (256.0, 8192.0):
+        for scale in (1.0, 0.25):
+            hits, valid = O.cull_probe(31, 2_000_000, coord_max, slope_max, seg_margin(coord_max, slope_max), scale=scale)
+            assert valid > 1_000_000 and hits == 0
+
+
 def test_probe_is_adversarial():
     """With (almost) no margin the same placements do produce hits, i.e. the probe looks in the right place."""
     hits, valid = O.cull_probe(13, 3_000_000, 256.0, 256.0, seg_margin(256.0), scale=1e-6)
