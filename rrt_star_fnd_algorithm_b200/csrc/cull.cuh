@@ -3,8 +3,9 @@
 //   point_occupied_warp    Map.is_occupied_c     src/map.py:38-47
 //
 // Code size matters here: the fused planner keeps dozens of warps in different phases on one SM, so its
-// instruction footprint has to stay inside the instruction cache. The segment test (one division for the line,
-// two divisions and a square root per circle) therefore exists ONCE, not inlined, and serves both uses through a
+// instruction footprint has to stay inside the instruction cache. The segment test (one division for the line; per
+// circle the quadratic's discriminant, the root filter and - rarely - a square root and two divisions, arith.cuh)
+// therefore exists ONCE, not inlined, and serves both uses through a
 // (first, stride) pair: a lane testing its own segment walks its circles with (0, 1), a warp sharing one segment
 // splits them with (lane, 32).
 #pragma once

@@ -7,7 +7,7 @@
 // coordinates / radii bounded by coord_max, intersection_circle can only return True if the circle's
 // centre lies within r + margin of the segment's bounding box. A circle is therefore listed in every cell
 // its box inflated by r + margin overlaps, and a segment looks only at the cells its own bounding box
-// overlaps. Everything else (vertical segments, steep slopes, NaN) takes the full table.
+// overlaps. Everything else (vertical segments, slopes beyond grid_slope_max(), NaN) takes the full table.
 //
 // The cell function is the same monotone expression on the host (builder) and the device (queries), which
 // is all the overlap argument needs.
