@@ -32,6 +32,27 @@ def test_claim_holds_for_larger_slope_bounds(slope_max):
             assert valid > 1_000_000 and hits == 0
 
 
+def test_builders_ship_slope_bound_1024_and_follow_the_override():
+    """grid_slope_max (grid.cuh): 1024 by default, RRTFND_SLOPE_MAX for A/B runs; the margin follows the bound either way (the host
+    builder runs on the CPU, so this needs no GPU)."""
+    import subprocess, sys, os
+    code = ("import numpy as np\n"
+            "from rrt_star_fnd_algorithm_b200.batch import build_obstacle_grid\n"
+            "t = np.array([[10.0, 10.0, 2.0, 196.0], [30.0, 40.0, 3.0, 2491.0]])\n"
+            "g, _ = build_obstacle_grid(t, 1.0, (0.0, 64.0, 0.0, 64.0), 0.0)\n"
+            "print(g.slope_max, g.margin, g.coord_max)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env_value, want in ((None, 1024.0), ("4096", 4096.0), ("0.5", 1024.0), ("junk", 1024.0)):
+        env = dict(os.environ)
+        env.pop("RRTFND_SLOPE_MAX", None)
+        if env_value is not None:
+            env["RRTFND_SLOPE_MAX"] = env_value
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=env, timeout=120)
+        assert out.returncode == 0, out.stderr
+        slope, margin, coord = (float(v) for v in out.stdout.split())
+        assert slope == want and margin == seg_margin(coord, want)
+
+
 def test_probe_is_adversarial():
     """With (almost) no margin the same placements do produce hits, i.e. the probe looks in the right place."""
     hits, valid = O.cull_probe(13, 3_000_000, 256.0, 256.0, seg_margin(256.0), scale=1e-6)
