@@ -53,6 +53,26 @@ static int setup(double p1x, double p1y, double p2x, double p2y, double ox, doub
 #ifdef ORC_ROOT_FILTER_LIB
 int orc_root_filter(double b, double delta, double a2, double lo, double hi) { return rrtfnd_root_filter(b, delta, a2, lo, hi); }
 int orc_root_slow(double b, double delta, double a2, double lo, double hi) { return slow_decision(b, delta, a2, lo, hi); }
+/* through_obstacle (src/algorithm.py:581-591) for n segments against M circles (x, y, r) the way the device evaluates a circle
+ * (arith.cuh seg_hits_circle): vertical rule, discriminant, root filter, and the reference's expressions only when the filter
+ * declines. hit[i] = the OR over the circles; counts[0] += circle tests with delta >= 0, counts[1] += those the filter declined. */
+void orc_root_through_obstacle(const double* segs, long long n, const double* circles, int M, unsigned char* hit, long long* counts) {
+    for (long long i = 0; i < n; ++i) {
+        const double* s = segs + 4 * i;
+        int h = 0;
+        for (int j = 0; j < M && !h; ++j) {
+            const double* c = circles + 3 * j;
+            if (s[2] == s[0]) { h = fabs(vsub(c[0], s[0])) <= c[2]; continue; }
+            double b, delta, a2, lo, hi;
+            if (!setup(s[0], s[1], s[2], s[3], c[0], c[1], c[2], &b, &delta, &a2, &lo, &hi)) continue;
+            ++counts[0];
+            int f = rrtfnd_root_filter(b, delta, a2, lo, hi);
+            if (f < 0) { ++counts[1]; f = slow_decision(b, delta, a2, lo, hi); }
+            h = f;
+        }
+        hit[i] = (unsigned char)h;
+    }
+}
 int orc_root_setup(const double* seg, const double* circle, double* out5) {
     return setup(seg[0], seg[1], seg[2], seg[3], circle[0], circle[1], circle[2], out5, out5 + 1, out5 + 2, out5 + 3, out5 + 4);
 }

@@ -74,6 +74,30 @@ def test_random_and_borderline_segments(lib):
     assert decided > 0.7 * total and decided < total       # most are decided, the nudged ones are not
 
 
+def test_recorded_through_obstacle_calls_of_the_reference(lib):
+    """tests/golden/collision.npz: segments the UNMODIFIED reference passed to through_obstacle while planning, with its
+    answers. Evaluated the way the device does (filter first, the plain expressions only when it declines) every answer is
+    the reference's - and on planner segments, whose ends keep node_radius away from the circles, the filter practically never
+    declines."""
+    from oracle import cases as K
+    from util import load_npz
+    g = load_npz("collision.npz")
+    names = sorted(k[:-4] for k in g if k.endswith("_seg"))      # synth_*: adversarial segments on the same maps
+    assert len(names) >= 12
+    lib.orc_root_through_obstacle.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    tests = declined = 0
+    for name in names:
+        case = K.case_by_name(name.replace("synth_", ""))
+        circles = np.ascontiguousarray([[float(x), float(y), float(r)] for x, y, r in case["obstacles"]], dtype=np.float64)
+        segs = np.ascontiguousarray(g[name + "_seg"], dtype=np.float64)
+        hit = np.zeros(len(segs), np.uint8)
+        counts = np.zeros(2, np.int64)
+        lib.orc_root_through_obstacle(segs.ctypes.data, len(segs), circles.ctypes.data, len(circles), hit.ctypes.data, counts.ctypes.data)
+        assert np.array_equal(hit, g[name + "_hit"].astype(np.uint8)), name
+        tests += int(counts[0]); declined += int(counts[1])
+    assert tests > 50_000 and declined <= tests // 1000, (tests, declined)      # measured: 60,131 tests, none declined
+
+
 def test_bulk_checker_finds_no_mismatch(lib):
     """oracle/_build/root_filter_check: six families of generated input, ~12 million cases here (hundreds of millions when run
     by hand, see profiles/); exit status 1 on any disagreement."""
