@@ -1,12 +1,11 @@
 #!/bin/sh
 # Build an A/B variant of librrtfnd.so with extra -D flags into rrt_star_fnd_algorithm_b200/_variants/<name>.so (git-ignored,
 # travels with gpurun); select it at run time with RRTFND_LIB=<path>.
-#   scripts/build_variant.sh libm_pow -DRRTFND_LIBM_POW=1
-#   scripts/build_variant.sh rank_near -DRRTFND_RANK_IN_NEAR=1
-#   scripts/build_variant.sh split -DRRTFND_SPLIT_CANDIDATES=1
-#   scripts/build_variant.sh smem_tables -DRRTFND_SMEM_TABLES=1
-#   scripts/build_variant.sh lane_hint -DRRTFND_LANE_MIN_HINT=1
+#   scripts/build_variant.sh libm_pow -DRRTFND_LIBM_POW=1         (the interpreter's `**` at the reference's sites; -47 %)
 #   scripts/build_variant.sh phase -DRRTFND_PHASE_CLOCKS          (scripts/phase_probe.py)
+#   scripts/build_variant.sh no_rf -DRRTFND_ROOT_FILTER=0         (circle tests always through the square root and the divisions)
+#   scripts/build_variant.sh ann4 -DRRTFND_ANN_FIRST=4 -DRRTFND_ANN_GROW=4   (annulus schedule of the nearest-visible search)
+# (the variants measured and removed in round 2 are listed in profiles/r02_variants.md)
 set -e
 name=$1; shift
 cd "$(dirname "$0")/../rrt_star_fnd_algorithm_b200"
